@@ -276,8 +276,12 @@ def share_threshold(p):
     return 1.25 * (p + 5 * np.sqrt(p))
 
 
-def final_factorisation(theta, g, gvar_damped, hyp, s0=SIG2_OF_CONST):
-    """Full-n stage of __fitGP1d: nug, sig2, pw (+ R, Vh, Rinv)     (PCGPwM.py:810-846)."""
+def final_factorisation(theta, g, gvar_damped, hyp, s0=SIG2_OF_CONST, shared=False):
+    """Full-n stage of __fitGP1d: nug, sig2, pw (+ R, Vh, Rinv)     (PCGPwM.py:810-846).
+
+    shared=True follows the share-branch, which forms Rinv = V diag(1/W) V' (PCGPwM.py:827);
+    the own-branch forms Vh Vh' (PCGPwM.py:844).  They differ only by rounding when R is SPD.
+    """
     out = {}
     out['hypcov'] = hyp[:-2]
     out['hypvarconst'] = hyp[-2]
@@ -293,7 +297,7 @@ def final_factorisation(theta, g, gvar_damped, hyp, s0=SIG2_OF_CONST):
     out['R'] = R
     out['Vh'] = Vh
     out['sig2'] = (np.mean(fc ** 2) * n + s0) / (n + s0)
-    out['Rinv'] = Vh @ Vh.T
+    out['Rinv'] = (V @ np.diag(1 / W) @ V.T) if shared else (Vh @ Vh.T)
     out['pw'] = out['Rinv'] @ g
     return out
 
@@ -345,13 +349,14 @@ def fit_gp_1d(theta, g, hyp1, hyp2, hypvarconst, gvar, dampalpha, eta,
         likdiff = L0 - nll(hypn, sub)
     else:
         likdiff = 0
-    if lead > -0.5 and (2 * likdiff) < share_threshold(p):       # share-or-own (808-833)
+    shared = bool(lead > -0.5 and (2 * likdiff) < share_threshold(p))
+    if shared:                                                   # share-or-own (808-833)
         sub['hypind'] = lead
     else:
         sub['hyp'] = hypn
         sub['hypind'] = -1
     sub['gvar'] = gvar[rows]
-    sub.update(final_factorisation(theta, g, gvar, sub['hyp'], sig2ofconst))
+    sub.update(final_factorisation(theta, g, gvar, sub['hyp'], sig2ofconst, shared=shared))
     return sub
 
 

@@ -76,17 +76,19 @@ def _ref_state_as_fitinfo(g):
 def test_predict_and_loglik_from_reference_state(golden, tag):
     g = golden('emu_' + tag)
     fi = _ref_state_as_fitinfo(g)
-    assert rel(np.array([e['pw'] for e in fi['emulist']]).T, g['st_pw']) < 1e-6
-    assert rel(np.array([e['sig2'] for e in fi['emulist']]), g['st_sig2']) < 1e-9
+    # re-factorising at the reference's hyper-parameters: agreement is bounded by cond(R) * eps
+    tol = max(1e-8, 100 * 2.2e-16 * float(g['st_condR'].max()))
+    assert rel(np.array([e['pw'] for e in fi['emulist']]).T, g['st_pw']) < 10 * tol
+    assert rel(np.array([e['sig2'] for e in fi['emulist']]), g['st_sig2']) < tol
     pred = {}
     po.predict(pred, fi, None, g['thetanew'], return_grad=True)
-    assert rel(pred['mean'], g['mean']) < 1e-7
-    assert rel(pred['var'], g['var']) < 1e-6
-    assert rel(pred['mean_gradtheta'], g['mean_grad']) < 1e-6
-    assert rel(pred['covxhalf'][:, :2, :], g['covxhalf_sample']) < 1e-6
+    assert rel(pred['mean'], g['mean']) < tol
+    assert rel(pred['var'], g['var']) < 10 * tol
+    assert rel(pred['mean_gradtheta'], g['mean_grad']) < 10 * tol
+    assert rel(pred['covxhalf'][:, :2, :], g['covxhalf_sample']) < 10 * tol
     ll, dll = wo.loglik_mspace(fi, g['yvar'], g['thetanew'], g['y'], return_grad=True)
-    assert np.max(np.abs(ll - g['loglik_g']) / np.abs(g['loglik_g'])) < 1e-6
-    assert rel(dll, g['dloglik']) < 1e-5
+    assert np.max(np.abs(ll - g['loglik_g']) / np.abs(g['loglik_g'])) < 10 * tol
+    assert rel(dll, g['dloglik']) < 100 * tol
     # k-space restatement fed with the reference's own PC-space predictions: tight
     spc = fi['standardpcinfo']
     phi = fi['pcti'] * spc['scale'][:, None]
