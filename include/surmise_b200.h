@@ -1,0 +1,118 @@
+/* surmise_b200 -- C ABI of the B200 (sm_100a) hot path for bandframework/surmise.
+ *
+ * Scope: the PCGPwM emulator's covariance / likelihood / factorisation / prediction and the
+ * directbayeswoodbury calibration log-likelihood.  Each entry point names the reference code it
+ * replaces (paths relative to the surmise source tree).
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer to fp64 (or int32 where typed so), row-major;
+ *   - the caller owns all memory, including workspaces (size them with the *_workspace queries);
+ *     the library never allocates or frees device memory and keeps no global mutable state
+ *     apart from a thread-local last-error string and one-time kernel attribute set-up;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); outputs are valid
+ *     after the stream is synchronised;
+ *   - return value: 0 success, < 0 invalid argument, > 0 a cudaError_t; sb200_last_error() explains;
+ *   - numerical breakdown (a non-positive pivot) is reported per problem in `info` (LAPACK
+ *     convention: j > 0 = leading minor j not positive definite), never by aborting;
+ *   - parameter dimension d <= 16, principal components k <= 112 for the Woodbury kernel.
+ */
+#ifndef SURMISE_B200_H
+#define SURMISE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int sb200_version(void);
+const char* sb200_last_error(void);
+
+/* Replaces surmise.emulationsupport.matern_covmat.covmat (emulationsupport/matern_covmat.pyx:27-64,
+ * map4 at :13-24).  R[i][j] (n1 x n2, leading dimension ldr) is the separable Matern-3/2 correlation
+ * between x1[i] and x2[j] (both (.,d) contiguous) for gammav (d+1).
+ * grad_mode 0: R only.  1: also dR = d/dgammav as (d+1) planes of n1 x n2 (the reference returns the
+ * (1,2,0)-transpose view of exactly such a buffer, pyx:52).  2: dR = d/dx1 as d planes of n1 x n2. */
+int sb200_matern_covmat(const double* x1, int n1, const double* x2, int n2, int d, const double* gammav,
+                        double* R, long ldr, double* dR, int grad_mode, void* stream);
+
+/* Replaces PCGPwM.__negloglik and PCGPwM.__negloglikgrad (emulationmethods/PCGPwM.py:850-868, 871-907)
+ * for `batch` problems at once (principal components and/or candidate hyper-parameter vectors).
+ * theta (n,d), g (n), gvar (n, may be NULL) with per-problem strides in elements (0 = shared);
+ * hyp (batch, d+3) = [gamma_0..gamma_d, log var-const, logit nugget]; regmean/regstd (d+3) shared.
+ * Outputs nll (batch), grad (batch, d+3; only if want_grad), info (batch). */
+size_t sb200_gp_nll_grad_workspace(int batch, int n, int d, int want_grad);
+int sb200_gp_nll_grad(int batch, int n, int d, const double* theta, long stride_theta, const double* g,
+                      long stride_g, const double* gvar, long stride_gvar, const double* hyp,
+                      const double* regmean, const double* regstd, double sig2ofconst, int want_grad,
+                      double* nll, double* grad, int* info, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces the full-data stage of PCGPwM.__fitGP1d (PCGPwM.py:810-846): for each problem builds
+ * R = (1-nug) R0 + nug I + exp(h_v) diag(gvar), factors it and returns
+ *   Linv (n x n lower triangular, leading dimension ldl, zero above the diagonal) with Linv' Linv = R^-1
+ *        -- stored instead of the reference's R, Rinv and Vh;
+ *   pw = R^-1 g (n), sig2 = (g' R^-1 g + sig2ofconst)/(n + sig2ofconst), logdet_half = 1/2 log|R|. */
+size_t sb200_gp_factorize_workspace(int batch, int n);
+int sb200_gp_factorize(int batch, int n, int d, const double* theta, long stride_theta, const double* g,
+                       long stride_g, const double* gvar, long stride_gvar, const double* hyp, double sig2ofconst,
+                       double* Linv, long ldl, long stride_linv, double* pw, double* sig2, double* logdet_half,
+                       int* info, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Companion of sb200_gp_factorize for principal components that share a factor (identical hyper-parameters
+ * and gvar, PCGPwM.py:808-833): pw_j = R^-1 g_j and sig2_j (PCGPwM.py:823-846) for scores g (k,n) through
+ * Linv[fidx[j]] (fidx NULL = identity).  ytmp: (k,n) scratch. */
+int sb200_gp_weights(int k, int n, const double* Linv, long ldl, long stride_linv, const int* fidx, const double* g,
+                     double sig2ofconst, double* pw, double* sig2, double* ytmp, void* stream);
+
+/* Replaces the per-PC loop of PCGPwM.predict (PCGPwM.py:219-270): predvecs/predvars (B,k) and, if
+ * want_grad, their gradients (B,k,d) at thetanew (B,d).
+ *   hypcov (nu, d+1): the distinct covariance hyper-parameter sets;  fu (nf): set used by factor f;
+ *   Linv (nf, n, ldl): distinct factors;  fidx (k): factor used by PC j;  nug, sig2 (k);  pw (k, n). */
+size_t sb200_gp_predict_workspace(int k, int nf, int nu, int n, int d, int B, int want_grad);
+int sb200_gp_predict(int k, int nf, int nu, int n, int d, int B, const double* theta, const double* thetanew,
+                     const double* hypcov, const int* fu, const int* fidx, const double* nug, const double* sig2,
+                     const double* Linv, long ldl, long stride_linv, const double* pw, int want_grad,
+                     double* predvecs, double* predvars, double* predvecs_grad, double* predvars_grad,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces the back-projection of PCGPwM.predict (PCGPwM.py:273-327).  phi (m,k) = pcti * scale;
+ * outputs mean, var (m,B); optional (NULL to skip) covxhalf (m,B,k), mean_grad (m,B,d),
+ * covxhalf_grad (m,B,k,d). */
+int sb200_pc_backproject(int m, int k, int B, int d, const double* phi, const double* offset,
+                         const double* extravar, const double* predvecs, const double* predvars,
+                         const double* predvecs_grad, const double* predvars_grad, double* mean, double* var,
+                         double* covxhalf, double* mean_grad, double* covxhalf_grad, void* stream);
+
+/* Replaces directbayeswoodbury.loglik / loglik_grad (calibrationmethods/directbayeswoodbury.py:261-306,
+ * 309-383) for a whole batch of theta in one launch, in principal-component space.
+ *   phiT (k,m); resid0 (m) = y - offset; extravar (m); sinv (2,m) = 1/yvar, 1/(yvar+|extravar|);
+ *   G (2,k,k) = Phi' diag(sinv[v]) Phi.  Outputs ll (B), dll (B,d; if want_grad) and *fired (device int):
+ *   1 when the batch-wide unmodelled-variance test (dbw.py:277-284) selected the second variant. */
+int sb200_woodbury_loglik(int B, int k, int m, int d, const double* predvecs, const double* predvars,
+                          const double* predvecs_grad, const double* predvars_grad, const double* phiT,
+                          const double* resid0, const double* extravar, const double* sinv, const double* G,
+                          int want_grad, double* ll, double* dll, int* fired, void* stream);
+
+/* Building blocks, exported for testing and reuse (no reference counterpart: the reference calls LAPACK).
+ * sb200_dgemm: C[m][n] = alpha sum_k Aop[m][k] Bop[n][k] + beta C[m][n] on the FP64 tensor cores (DMMA);
+ *   a_kc != 0: Aop[m][k] = A[m*lda+k] else A[k*lda+m]; same for B.  flags: 1 A lower, 2 A upper,
+ *   4 B lower, 8 B upper (triangular operands must hold zeros in the empty triangle), 16 lower-C only.
+ * sb200_potrf_batched: in-place lower Cholesky of `batch` matrices (rows n..mrows-1 are solved as
+ *   right-hand sides X <- X L^-T); Linv receives the inverted diagonal blocks and is zeroed elsewhere.
+ * sb200_trtri_batched: completes Linv = L^-1 from the output of sb200_potrf_batched.
+ * sb200_lauum_batched: lower triangle of C = Linv' Linv. */
+int sb200_dgemm(int a_kc, int b_kc, int M, int N, int K, double alpha, const double* A, long lda, long stride_a,
+                const double* B, long ldb, long stride_b, double beta, double* C, long ldc, long stride_c,
+                int batch, int flags, int tile, void* stream);
+int sb200_potrf_batched(int batch, int n, int mrows, double* A, long lda, long stride_a, double* Linv, long ldl,
+                        long stride_linv, int* info, void* stream);
+size_t sb200_trtri_tmp_elems(int n);
+int sb200_trtri_batched(int batch, int n, const double* L, long lda, long stride_a, double* Linv, long ldl,
+                        long stride_linv, double* tmp, size_t tmp_elems_per_matrix, void* stream);
+int sb200_lauum_batched(int batch, int n, const double* Linv, long ldl, long stride_linv, double* C, long ldc,
+                        long stride_c, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURMISE_B200_H */

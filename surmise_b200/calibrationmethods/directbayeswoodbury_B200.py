@@ -1,0 +1,188 @@
+"""directbayeswoodbury_B200 -- surmise calibration method with the Woodbury log-likelihood on a B200.
+
+Drop-in sibling of surmise/calibrationmethods/directbayeswoodbury.py behind the same plugin contract
+(`fit(fitinfo, emu, x, y, **args)`, optional `predict`, `thetarnd`, `thetalpdf`;
+surmise/calibration.py:196-234, 271-272, 506-577):
+`calibrator(emu, y, x, thetaprior, method='directbayeswoodbury_B200', yvar=..., args={'sampler': ...})`.
+
+The sampler plugins of surmise are used unmodified: they call the log-posterior closure once per step
+with the whole population as one (B, d) array; each such call is ONE fused device evaluation
+(cross-covariance -> two triangular DMMA products -> PC-space reduction -> batched Woodbury kernel).
+Nothing of size m x B x k x d is ever formed (the reference builds covxhalf_gradtheta of that size,
+directbayeswoodbury.py:319-324).
+
+Requires an emulator fitted with method='PCGPwM_B200' (its device state is read from emu._info).
+"""
+import copy
+
+import numpy as np
+
+from ..emulationmethods import PCGPwM_B200 as _emu_method
+
+
+def _ops():
+    from .. import ops
+    return ops
+
+
+def _device_state(emu):
+    info = getattr(emu, '_info', None)
+    if not isinstance(info, dict) or '_b200' not in info:
+        raise ValueError("directbayeswoodbury_B200 needs an emulator fitted with method='PCGPwM_B200'.")
+    return info
+
+
+def woodbury_constants(fitinfo, emu, x, y):
+    """theta-independent device constants for (x, y, yvar); cached in fitinfo['_b200cal']."""
+    if 'yvar' not in fitinfo:
+        raise ValueError('Must provide yvar in this software.')            # dbw.py:266-269
+    ops = _ops()
+    torch = ops._torch()
+    info = _device_state(emu)
+    st = info['_b200']
+    y = np.squeeze(np.asarray(y, dtype=np.float64))
+    yvar = 1 * np.squeeze(np.asarray(fitinfo['yvar'], dtype=np.float64))
+    xind, xnewind = _emu_method.match_rows(x, info['x'])
+    nx = info['x'].shape[0] if x is None else x.shape[0]
+    if xind.shape[0] != nx or not np.array_equal(xnewind, np.arange(nx)):
+        raise ValueError('Every calibration x must match exactly one row of the emulator x.')
+    cache = fitinfo.get('_b200cal')
+    key = (xind.tobytes(), y.tobytes(), yvar.tobytes(), id(st['Linv']))
+    if cache is not None and cache['key'] == key:
+        return cache
+    dev = st['phi'].device
+    sel = torch.from_numpy(xind.astype(np.int64)).to(dev)
+    phi = st['phi'][sel].cpu().numpy()
+    offset = st['offset'][sel].cpu().numpy()
+    extravar = st['extravar'][sel].cpu().numpy()
+    yv = yvar * np.ones(phi.shape[0])
+    sinv = np.stack([1 / yv, 1 / (yv + np.abs(extravar))])                   # dbw.py:280-284 when triggered
+    G = np.stack([phi.T @ (phi * s[:, None]) for s in sinv])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    cache = {'key': key, 'phiT': t(phi.T), 'resid0': t(y - offset), 'extravar': t(extravar), 'sinv': t(sinv),
+             'G': t(G), 'xind': xind}
+    fitinfo['_b200cal'] = cache
+    return cache
+
+
+def loglik_device(fitinfo, emu, theta, y, x, return_grad=False, chunk=4096):
+    """Device tensors (ll (B,), dll (B,d) or None, fired) -- the fused evaluation."""
+    ops = _ops()
+    torch = ops._torch()
+    consts = woodbury_constants(fitinfo, emu, x, y)
+    info = _device_state(emu)
+    tn = ops._f64(torch, np.atleast_2d(theta) if not isinstance(theta, torch.Tensor) else theta)
+    pv, pvar, dpv, dpvar = _emu_method.predict_pcspace(info, tn, return_grad, chunk=chunk)
+    return ops.woodbury_loglik(consts, pv, pvar, dpv, dpvar)
+
+
+def loglik(fitinfo, emu, theta, y, x):
+    """(B,1) log-likelihoods; same contract as directbayeswoodbury.loglik (dbw.py:261-306)."""
+    ll, _, _ = loglik_device(fitinfo, emu, theta, y, x, return_grad=False)
+    return ll.cpu().numpy().reshape(-1, 1)
+
+
+def loglik_grad(fitinfo, emu, theta, y, x):
+    """(B,1), (B,d); same contract as directbayeswoodbury.loglik_grad (dbw.py:309-383)."""
+    ops = _ops()
+    torch = ops._torch()
+    ll, dll, _ = loglik_device(fitinfo, emu, theta, y, x, return_grad=True)
+    packed = torch.cat([ll[:, None], dll], dim=1).cpu().numpy()              # one D2H copy per call
+    return packed[:, :1].copy(), packed[:, 1:].copy()
+
+
+def make_logpost(fitinfo, emu, x, y):
+    """The closure handed to the sampler (dbw.py:100-129) and the initial-draw function (132-146)."""
+    thetaprior = fitinfo['thetaprior']
+    if 'lpdf_grad' not in dir(thetaprior):                                    # dbw.py:82-98
+        def lpdf_grad(theta):
+            base = thetaprior.lpdf(theta)
+            inds = np.where(np.isfinite(base))[0]
+            grad = np.zeros((theta.shape[0], theta.shape[1]))
+            for k in range(theta.shape[1]):
+                prop = copy.copy(theta)
+                prop[:, k] += 10 ** (-6)
+                grad[inds, k] = 10 ** 6 * (thetaprior.lpdf(prop[inds, :]) - base[inds]).reshape(len(inds),)
+            return grad
+        thetaprior.lpdf_grad = lpdf_grad
+
+    def logpostfull_wgrad(theta, return_grad=True):
+        logpost = thetaprior.lpdf(theta)
+        inds = np.where(np.isfinite(logpost))[0]
+        if return_grad:
+            dlogpost = thetaprior.lpdf_grad(theta)
+            if len(inds):
+                ll, dll = loglik_grad(fitinfo, emu, theta[inds, :], y, x)
+                logpost[inds] += ll
+                dlogpost[inds] += dll
+            return logpost, dlogpost
+        if len(inds) > 0:
+            logpost[inds] += loglik(fitinfo, emu, theta[inds, :], y, x)
+        return logpost
+
+    def draw_func(n):
+        p = thetaprior.rnd(1).shape[1]
+        theta0 = np.array([]).reshape(0, p)
+        if 'thetarnd' in fitinfo:
+            theta0 = fitinfo['thetarnd']
+        if '_emulator__theta' in dir(emu):
+            theta0 = np.vstack((theta0, copy.copy(emu._emulator__theta)))
+        n0 = len(theta0)
+        if n0 < n:
+            theta0 = np.vstack((thetaprior.rnd(n - n0), theta0))
+        else:
+            theta0 = theta0[np.random.randint(theta0.shape[0], size=n), :]
+        return theta0
+
+    return logpostfull_wgrad, draw_func
+
+
+def fit(fitinfo, emu, x, y, **bayeswoodbury_args):
+    """Posterior sampling with surmise's own sampler plugins (dbw.py:7-163)."""
+    from surmise.utilities import sampler            # the reference's dispatcher, used unmodified
+    woodbury_constants(fitinfo, emu, x, y)
+    logpost, draw_func = make_logpost(fitinfo, emu, x, y)
+    sampler_obj = sampler(logpost_func=logpost, draw_func=draw_func, **bayeswoodbury_args)
+    theta = sampler_obj.sampler_info['theta']
+    ladj = logpost(theta, return_grad=False)
+    mladj = np.max(ladj)
+    fitinfo['lpdfapproxnorm'] = np.log(np.mean(np.exp(ladj - mladj))) + mladj
+    fitinfo['thetarnd'] = theta
+    fitinfo['y'] = y
+    fitinfo['x'] = x
+    fitinfo['emu'] = emu
+    return
+
+
+def predict(predinfo, fitinfo, emu, x, args=None):
+    """Posterior predictive summaries at x (dbw.py:166-216)."""
+    theta = fitinfo['thetarnd']
+    if theta.ndim == 1:
+        theta = theta.reshape((1, theta.shape[0]))
+    pred = emu.predict(x, theta)
+    mean = pred.mean()
+    cxh = pred.covxhalf()
+    rnd = copy.deepcopy(mean).T
+    z = np.random.standard_normal(size=(theta.shape[0], cxh.shape[2]))
+    rnd += np.einsum('xbk,bk->bx', cxh, z)
+    predinfo['rnd'] = rnd
+    predinfo['mean'] = np.mean(mean, 1)
+    predinfo['var'] = np.mean(np.sum(np.square(cxh), axis=2), 1) + np.var(mean, 1)
+    return
+
+
+def thetarnd(fitinfo, s=100, args=None):
+    """s draws from the stored posterior sample (dbw.py:219-238)."""
+    return fitinfo['thetarnd'][np.random.choice(fitinfo['thetarnd'].shape[0], size=s), :]
+
+
+def thetalpdf(fitinfo, theta, args=None):
+    """Normalised log-posterior at theta (dbw.py:241-258)."""
+    emu, y, x = fitinfo['emu'], fitinfo['y'], fitinfo['x']
+    logpost = fitinfo['thetaprior'].lpdf(theta)
+    if logpost.ndim > 0.5 and logpost.shape[0] > 1.5:
+        inds = np.where(np.isfinite(logpost))[0]
+        logpost[inds] += loglik(fitinfo, emu, theta[inds], y, x)
+    elif np.isfinite(logpost):
+        logpost += loglik(fitinfo, emu, theta, y, x)
+    return logpost - fitinfo['lpdfapproxnorm']

@@ -1,0 +1,136 @@
+// extern "C" boundary: plain pointers and sizes only (see include/surmise_b200.h).
+#include "../../include/surmise_b200.h"
+#include "chol.cuh"
+#include "covmat.cuh"
+#include "dgemm.cuh"
+#include "gp.cuh"
+#include <cstdarg>
+
+namespace sb {
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace sb
+
+using namespace sb;
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" {
+
+int sb200_version(void) { return 100; }
+const char* sb200_last_error(void) { return sb::g_err; }
+
+int sb200_matern_covmat(const double* x1, int n1, const double* x2, int n2, int d, const double* gammav,
+                        double* R, long ldr, double* dR, int grad_mode, void* stream) {
+    SB_CHECK_ARG(x1 && x2 && gammav && R, "matern_covmat: NULL pointer");
+    SB_CHECK_ARG(n1 >= 0 && n2 >= 0 && ldr >= n2, "matern_covmat: bad shape n1=%d n2=%d ldr=%ld", n1, n2, ldr);
+    return matern_covmat(x1, n1, x2, n2, d, gammav, R, ldr, dR, grad_mode, ST(stream));
+}
+
+size_t sb200_gp_nll_grad_workspace(int batch, int n, int d, int want_grad) {
+    return gp_nll_grad_workspace(batch, n, d, want_grad);
+}
+int sb200_gp_nll_grad(int batch, int n, int d, const double* theta, long stride_theta, const double* g,
+                      long stride_g, const double* gvar, long stride_gvar, const double* hyp,
+                      const double* regmean, const double* regstd, double sig2ofconst, int want_grad,
+                      double* nll, double* grad, int* info, void* workspace, size_t workspace_bytes, void* stream) {
+    SB_CHECK_ARG(theta && g && hyp && regmean && regstd && nll && info && workspace, "gp_nll_grad: NULL pointer");
+    return gp_nll_grad(batch, n, d, theta, stride_theta, g, stride_g, gvar, stride_gvar, hyp, regmean, regstd,
+                       sig2ofconst, want_grad, nll, grad, info, workspace, workspace_bytes, ST(stream));
+}
+
+size_t sb200_gp_factorize_workspace(int batch, int n) { return gp_factorize_workspace(batch, n); }
+int sb200_gp_factorize(int batch, int n, int d, const double* theta, long stride_theta, const double* g,
+                       long stride_g, const double* gvar, long stride_gvar, const double* hyp, double sig2ofconst,
+                       double* Linv, long ldl, long stride_linv, double* pw, double* sig2, double* logdet_half,
+                       int* info, void* workspace, size_t workspace_bytes, void* stream) {
+    SB_CHECK_ARG(theta && g && hyp && Linv && pw && sig2 && info && workspace, "gp_factorize: NULL pointer");
+    return gp_factorize(batch, n, d, theta, stride_theta, g, stride_g, gvar, stride_gvar, hyp, sig2ofconst, Linv, ldl,
+                        stride_linv, pw, sig2, logdet_half, info, workspace, workspace_bytes, ST(stream));
+}
+
+int sb200_gp_weights(int k, int n, const double* Linv, long ldl, long stride_linv, const int* fidx, const double* g,
+                     double sig2ofconst, double* pw, double* sig2, double* ytmp, void* stream) {
+    SB_CHECK_ARG(Linv && g && pw && sig2 && ytmp, "gp_weights: NULL pointer");
+    return gp_weights(k, n, Linv, ldl, stride_linv, fidx, g, sig2ofconst, pw, sig2, ytmp, ST(stream));
+}
+
+size_t sb200_gp_predict_workspace(int k, int nf, int nu, int n, int d, int B, int want_grad) {
+    return gp_predict_workspace(k, nf, nu, n, d, B, want_grad);
+}
+int sb200_gp_predict(int k, int nf, int nu, int n, int d, int B, const double* theta, const double* thetanew,
+                     const double* hypcov, const int* fu, const int* fidx, const double* nug, const double* sig2,
+                     const double* Linv, long ldl, long stride_linv, const double* pw, int want_grad,
+                     double* predvecs, double* predvars, double* predvecs_grad, double* predvars_grad,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    SB_CHECK_ARG(theta && thetanew && hypcov && fu && fidx && nug && sig2 && Linv && pw && predvecs && predvars &&
+                     workspace, "gp_predict: NULL pointer");
+    return gp_predict(k, nf, nu, n, d, B, theta, thetanew, hypcov, fu, fidx, nug, sig2, Linv, ldl, stride_linv, pw,
+                      want_grad, predvecs, predvars, predvecs_grad, predvars_grad, workspace, workspace_bytes,
+                      ST(stream));
+}
+
+int sb200_pc_backproject(int m, int k, int B, int d, const double* phi, const double* offset,
+                         const double* extravar, const double* predvecs, const double* predvars,
+                         const double* predvecs_grad, const double* predvars_grad, double* mean, double* var,
+                         double* covxhalf, double* mean_grad, double* covxhalf_grad, void* stream) {
+    SB_CHECK_ARG(phi && offset && extravar && predvecs && predvars && mean && var, "pc_backproject: NULL pointer");
+    return pc_backproject(m, k, B, d, phi, offset, extravar, predvecs, predvars, predvecs_grad, predvars_grad, mean,
+                          var, covxhalf, mean_grad, covxhalf_grad, ST(stream));
+}
+
+int sb200_woodbury_loglik(int B, int k, int m, int d, const double* predvecs, const double* predvars,
+                          const double* predvecs_grad, const double* predvars_grad, const double* phiT,
+                          const double* resid0, const double* extravar, const double* sinv, const double* G,
+                          int want_grad, double* ll, double* dll, int* fired, void* stream) {
+    SB_CHECK_ARG(predvecs && predvars && phiT && resid0 && extravar && sinv && G && ll && fired,
+                 "woodbury_loglik: NULL pointer");
+    return woodbury_loglik(B, k, m, d, predvecs, predvars, predvecs_grad, predvars_grad, phiT, resid0, extravar, sinv,
+                           G, want_grad, ll, dll, fired, ST(stream));
+}
+
+int sb200_dgemm(int a_kc, int b_kc, int M, int N, int K, double alpha, const double* A, long lda, long stride_a,
+                const double* B, long ldb, long stride_b, double beta, double* C, long ldc, long stride_c,
+                int batch, int flags, int tile, void* stream) {
+    SB_CHECK_ARG(A && B && C, "dgemm: NULL pointer");
+    SB_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && ldc >= N, "dgemm: bad shape");
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = K;
+    g.A = A; g.lda = lda; g.strideA = stride_a; g.a_kc = a_kc != 0;
+    g.B = B; g.ldb = ldb; g.strideB = stride_b; g.b_kc = b_kc != 0;
+    g.C = C; g.ldc = ldc; g.strideC = stride_c;
+    g.alpha = alpha; g.beta = beta; g.flags = flags;
+    return launch_dgemm(g, batch, tile, ST(stream));
+}
+
+int sb200_potrf_batched(int batch, int n, int mrows, double* A, long lda, long stride_a, double* Linv, long ldl,
+                        long stride_linv, int* info, void* stream) {
+    SB_CHECK_ARG(A && Linv && info, "potrf: NULL pointer");
+    SB_CHECK_ARG(ldl >= n && stride_linv >= (long)n * ldl, "potrf: bad Linv layout");
+    SB_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, ST(stream)));
+    SB_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * ((size_t)(batch - 1) * stride_linv + (size_t)n * ldl), ST(stream)));
+    CholBatch c{};
+    c.batch = batch; c.n = n; c.mrows = mrows; c.A = A; c.lda = lda; c.strideA = stride_a; c.info = info;
+    c.Dinv = Linv; c.ldd = ldl; c.strideD = stride_linv; c.blockD = (long)CHOL_NB * ldl + CHOL_NB;
+    return potrf_batched(c, ST(stream));
+}
+
+size_t sb200_trtri_tmp_elems(int n) { return trtri_tmp_elems(n); }
+
+int sb200_trtri_batched(int batch, int n, const double* L, long lda, long stride_a, double* Linv, long ldl,
+                        long stride_linv, double* tmp, size_t tmp_elems_per_matrix, void* stream) {
+    SB_CHECK_ARG(L && Linv, "trtri: NULL pointer");
+    return trtri_batched(batch, n, L, lda, stride_a, Linv, ldl, stride_linv, tmp, (long)tmp_elems_per_matrix, ST(stream));
+}
+
+int sb200_lauum_batched(int batch, int n, const double* Linv, long ldl, long stride_linv, double* C, long ldc,
+                        long stride_c, void* stream) {
+    SB_CHECK_ARG(Linv && C, "lauum: NULL pointer");
+    return lauum_batched(batch, n, Linv, ldl, stride_linv, C, ldc, stride_c, ST(stream));
+}
+
+}  // extern "C"

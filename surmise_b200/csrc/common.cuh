@@ -1,0 +1,95 @@
+// Shared helpers for the surmise_b200 CUDA library (sm_100a only, fp64 throughout).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <cstddef>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "surmise_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace sb {
+
+// ---- error plumbing: every C-ABI entry point returns 0, <0 (bad argument) or >0 (cudaError_t) ----
+void set_last_error(const char* fmt, ...);
+
+#define SB_CHECK_ARG(cond, ...)                         \
+    do {                                                \
+        if (!(cond)) {                                  \
+            sb::set_last_error(__VA_ARGS__);            \
+            return -1;                                  \
+        }                                               \
+    } while (0)
+
+#define SB_CUDA(expr)                                                                   \
+    do {                                                                                \
+        cudaError_t e__ = (expr);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            sb::set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                               __FILE__, __LINE__);                                     \
+            return (int)e__;                                                            \
+        }                                                                               \
+    } while (0)
+
+#define SB_LAUNCH_CHECK() SB_CUDA(cudaGetLastError())
+
+#define SB_TRY(expr)            \
+    do {                        \
+        int rc__ = (expr);      \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+static inline long round_up(long v, long a) { return (v + a - 1) / a * a; }
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// bump allocator over a caller-provided workspace (the library never allocates device memory)
+struct Workspace {
+    char* base;
+    size_t cap;
+    size_t off;
+    Workspace(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0) {}
+    template <typename T>
+    T* take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
+        if (base == nullptr) {           // sizing pass
+            off += bytes;
+            return nullptr;
+        }
+        if (off + bytes > cap) return nullptr;
+        T* r = (T*)(base + off);
+        off += bytes;
+        return r;
+    }
+};
+
+constexpr int MAXD = 16;          // max parameter dimension d supported by the register-resident loops
+constexpr int MAXP = MAXD + 3;    // hyper-parameters per GP: d length-scales + scale + log var-const + logit nugget
+
+// ---- device helpers ----
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum; `red` must hold >= 32 doubles; result valid in all threads
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+    if (w == 0) {
+        t = warp_sum(t);
+        if (lane == 0) red[0] = t;
+    }
+    __syncthreads();
+    return red[0];
+}
+#endif
+
+}  // namespace sb

@@ -1,0 +1,240 @@
+// DMMA (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4) GEMM for sm_100a.
+//
+// tcgen05.mma has no f64 kind, so on B200 the FP64 tensor path is the warp-level DMMA.  The kernel
+// is a classic 3-stage cp.async pipeline: 128x128 (or 128x64) CTA tile, BK = 16, 8 warps, each warp
+// owning a 64x32 (32x32) accumulator block held in registers.  Operand tiles are staged in shared
+// memory in a fragment-friendly order so that every LDS.64 of a warp is bank-conflict free:
+//   k-contiguous operand : [k/4][row][k%4]  -> a warp's 8x4 fragment is 256 contiguous bytes
+//   row-contiguous operand: [k][row + pad 4] -> (4t + g) mod 16 distinct per half-warp
+// Algorithmic work: 2*M*N*Keff flop where Keff is the (possibly triangular) k-range per tile.
+#include "dgemm.cuh"
+
+namespace sb {
+namespace {
+
+constexpr int BK = 16;
+constexpr int STAGES = 3;
+constexpr int NTHREADS = 256;
+
+__device__ __forceinline__ void cp_async16(double* smem, const double* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(double* smem, const double* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// Stage one BMN x BK operand tile.  Elements outside [0,MN) x [kbase,k_hi) are zero-filled by
+// cp.async's src-size mechanism, so ragged M/N/K and triangular k-ranges need no special code.
+template <int BMN, bool KC>
+__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ G, long ld, int mn0, int MN,
+                                          int kbase, int k_hi, bool vec16, int tid) {
+    const double* dummy = (const double*)((uintptr_t)G & ~(uintptr_t)15);
+    if (KC) {
+        constexpr int CHUNKS = BMN * (BK / 2);
+#pragma unroll
+        for (int c = tid; c < CHUNKS; c += NTHREADS) {
+            int mn = c / (BK / 2), kl = 2 * (c % (BK / 2));
+            int gk = kbase + kl, gmn = mn0 + mn;
+            bool rok = gmn < MN;
+            bool v0 = rok && gk < k_hi, v1 = rok && (gk + 1) < k_hi;
+            double* dst = s + ((kl >> 2) * BMN + mn) * 4 + (kl & 3);
+            const double* src = G + (long)gmn * ld + gk;
+            if (vec16) {
+                cp_async16(dst, v0 ? src : dummy, v1 ? 16 : (v0 ? 8 : 0));
+            } else {
+                cp_async8(dst, v0 ? src : dummy, v0 ? 8 : 0);
+                cp_async8(dst + 1, v1 ? src + 1 : dummy, v1 ? 8 : 0);
+            }
+        }
+    } else {
+        constexpr int CHUNKS = BK * (BMN / 2);
+#pragma unroll
+        for (int c = tid; c < CHUNKS; c += NTHREADS) {
+            int k = c / (BMN / 2), ml = 2 * (c % (BMN / 2));
+            int gk = kbase + k, gmn = mn0 + ml;
+            bool kok = gk < k_hi;
+            bool v0 = kok && gmn < MN, v1 = kok && (gmn + 1) < MN;
+            double* dst = s + k * (BMN + 4) + ml;
+            const double* src = G + (long)gk * ld + gmn;
+            if (vec16) {
+                cp_async16(dst, v0 ? src : dummy, v1 ? 16 : (v0 ? 8 : 0));
+            } else {
+                cp_async8(dst, v0 ? src : dummy, v0 ? 8 : 0);
+                cp_async8(dst + 1, v1 ? src + 1 : dummy, v1 ? 8 : 0);
+            }
+        }
+    }
+}
+
+template <int BM, int BN, int WM, int WN, bool AKC, bool BKC>
+__global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
+    constexpr int A_TILE = BK * (BM + 4);
+    constexpr int B_TILE = BK * (BN + 4);
+    constexpr int WARPS_N = BN / WN;
+    constexpr int WARPS_M = BM / WM;
+    static_assert(WARPS_M * WARPS_N * 32 == NTHREADS, "warp grid must cover the CTA tile");
+    constexpr int MI = WM / 8, NI = WN / 8;
+
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + STAGES * A_TILE;
+
+    const int tid = threadIdx.x;
+    const int z = blockIdx.z;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int m_end = min(p.M, m0 + BM), n_end = min(p.N, n0 + BN);
+    if ((p.flags & GEMM_C_LOWER) && n0 > m_end - 1) return;
+
+    const double* A = p.A + (long)(p.idxA ? p.idxA[z] : z) * p.strideA;
+    const double* B = p.B + (long)(p.idxB ? p.idxB[z] : z) * p.strideB;
+    double* C = p.C + (long)z * p.strideC;
+
+    int k_lo = 0, k_hi = p.K;
+    if (p.flags & GEMM_A_LOWER) k_hi = min(k_hi, m_end);
+    if (p.flags & GEMM_A_UPPER) k_lo = max(k_lo, m0);
+    if (p.flags & GEMM_B_LOWER) k_hi = min(k_hi, n_end);
+    if (p.flags & GEMM_B_UPPER) k_lo = max(k_lo, n0);
+    k_lo &= ~(BK - 1);
+    const int ktiles = (k_hi > k_lo) ? (k_hi - k_lo + BK - 1) / BK : 0;
+
+    const bool a16 = ((p.lda & 1) == 0) && (((uintptr_t)A & 15) == 0);
+    const bool b16 = ((p.ldb & 1) == 0) && (((uintptr_t)B & 15) == 0);
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; i++)
+#pragma unroll
+        for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < ktiles) {
+            load_tile<BM, AKC>(As + s * A_TILE, A, p.lda, m0, p.M, k_lo + s * BK, k_hi, a16, tid);
+            load_tile<BN, BKC>(Bs + s * B_TILE, B, p.ldb, n0, p.N, k_lo + s * BK, k_hi, b16, tid);
+        }
+        cp_async_commit();
+    }
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
+
+    for (int kt = 0; kt < ktiles; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nx = kt + STAGES - 1;
+            if (nx < ktiles) {
+                int slot = nx % STAGES;
+                load_tile<BM, AKC>(As + slot * A_TILE, A, p.lda, m0, p.M, k_lo + nx * BK, k_hi, a16, tid);
+                load_tile<BN, BKC>(Bs + slot * B_TILE, B, p.ldb, n0, p.N, k_lo + nx * BK, k_hi, b16, tid);
+            }
+            cp_async_commit();
+        }
+        const double* as = As + (kt % STAGES) * A_TILE;
+        const double* bs = Bs + (kt % STAGES) * B_TILE;
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 4; k4++) {
+            double a[MI], b[NI];
+#pragma unroll
+            for (int i = 0; i < MI; i++)
+                a[i] = AKC ? as[((k4 * BM) + wm0 + i * 8 + g) * 4 + t] : as[(k4 * 4 + t) * (BM + 4) + wm0 + i * 8 + g];
+#pragma unroll
+            for (int j = 0; j < NI; j++)
+                b[j] = BKC ? bs[((k4 * BN) + wn0 + j * 8 + g) * 4 + t] : bs[(k4 * 4 + t) * (BN + 4) + wn0 + j * 8 + g];
+#pragma unroll
+            for (int i = 0; i < MI; i++)
+#pragma unroll
+                for (int j = 0; j < NI; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    const bool c16 = ((p.ldc & 1) == 0) && (((uintptr_t)C & 15) == 0);
+    const double alpha = p.alpha, beta = p.beta;
+    const bool lower_only = (p.flags & GEMM_C_LOWER) != 0;
+#pragma unroll
+    for (int i = 0; i < MI; i++) {
+        int row = m0 + wm0 + i * 8 + g;
+        if (row >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < NI; j++) {
+            int col = n0 + wn0 + j * 8 + 2 * t;
+            double* ptr = C + (long)row * p.ldc + col;
+            double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+            // lower-only output: never touch an element above the diagonal of C
+            const bool w0 = (col < p.N) && !(lower_only && col > row);
+            const bool w1 = (col + 1 < p.N) && !(lower_only && col + 1 > row);
+            if (w0 && w1 && c16) {
+                if (beta != 0.0) {
+                    double2 o = *reinterpret_cast<const double2*>(ptr);
+                    v0 += beta * o.x;
+                    v1 += beta * o.y;
+                }
+                *reinterpret_cast<double2*>(ptr) = make_double2(v0, v1);
+            } else {
+                if (w0) {
+                    if (beta != 0.0) v0 += beta * ptr[0];
+                    ptr[0] = v0;
+                }
+                if (w1) {
+                    if (beta != 0.0) v1 += beta * ptr[1];
+                    ptr[1] = v1;
+                }
+            }
+        }
+    }
+}
+
+template <int BM, int BN, int WM, int WN, bool AKC, bool BKC>
+int launch_one(const GemmArgs& g, int batch, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)STAGES * (BK * (BM + 4) + BK * (BN + 4)) * sizeof(double);
+    auto kern = dgemm_dmma_kernel<BM, BN, WM, WN, AKC, BKC>;
+    static bool configured[64] = {false};
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !configured[dev]) {
+        SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = true;
+    }
+    dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), batch);
+    kern<<<grid, NTHREADS, smem, stream>>>(g);
+    SB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int BM, int BN, int WM, int WN>
+int launch_layout(const GemmArgs& g, int batch, cudaStream_t stream) {
+    if (g.a_kc) {
+        if (g.b_kc) return launch_one<BM, BN, WM, WN, true, true>(g, batch, stream);
+        return launch_one<BM, BN, WM, WN, true, false>(g, batch, stream);
+    }
+    if (g.b_kc) return launch_one<BM, BN, WM, WN, false, true>(g, batch, stream);
+    return launch_one<BM, BN, WM, WN, false, false>(g, batch, stream);
+}
+
+}  // namespace
+
+int launch_dgemm(const GemmArgs& g, int batch, int tile, cudaStream_t stream) {
+    if (g.M <= 0 || g.N <= 0 || batch <= 0) return 0;
+    SB_CHECK_ARG(batch <= 65535, "dgemm: batch %d exceeds grid.z limit", batch);
+    SB_CHECK_ARG(cdiv(g.M, 128) <= 65535, "dgemm: M %d too large", g.M);
+    if (tile < 0) tile = (round_up(g.N, 64) < round_up(g.N, 128)) ? 1 : 0;
+    if (tile == 1) return launch_layout<128, 64, 32, 32>(g, batch, stream);
+    return launch_layout<128, 128, 64, 32>(g, batch, stream);
+}
+
+}  // namespace sb

@@ -1,0 +1,35 @@
+// FP64 tensor-core (DMMA) GEMM used by every dense step of the GP path: Cholesky trailing
+// updates, triangular solves through inverted diagonal blocks, triangular inversion, L^-T L^-1
+// and the predict products.  One kernel template, four operand-layout instantiations.
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+// C[m][n] = alpha * sum_k Aop[m][k] * Bop[n][k] + beta * C[m][n]      (row-major C, ldc)
+//   a_kc : Aop[m][k] = A[m*lda + k]   (k contiguous)      else  A[k*lda + m]   (m contiguous)
+//   b_kc : Bop[n][k] = B[n*ldb + k]   (k contiguous)      else  B[k*ldb + n]   (n contiguous)
+// Triangular structure only narrows the k-range visited per tile; the operand memory must hold
+// real zeros in its "empty" triangle (all such operands are buffers this library zero-fills).
+enum GemmFlags : int {
+    GEMM_A_LOWER = 1,   // Aop[m][k] == 0 for k > m
+    GEMM_A_UPPER = 2,   // Aop[m][k] == 0 for k < m
+    GEMM_B_LOWER = 4,   // Bop[n][k] == 0 for k > n
+    GEMM_B_UPPER = 8,   // Bop[n][k] == 0 for k < n
+    GEMM_C_LOWER = 16   // skip tiles lying strictly above the diagonal of C
+};
+
+struct GemmArgs {
+    int M, N, K;
+    const double* A; long lda; long strideA; const int* idxA;   // batch z uses A + (idxA ? idxA[z] : z) * strideA
+    const double* B; long ldb; long strideB; const int* idxB;
+    double* C;       long ldc; long strideC;
+    double alpha, beta;
+    bool a_kc, b_kc;
+    int flags;
+};
+
+// tile: 0 = 128x128 CTA tile, 1 = 128x64 (narrow N, e.g. panel solves), -1 = pick from N
+int launch_dgemm(const GemmArgs& g, int batch, int tile, cudaStream_t stream);
+
+}  // namespace sb

@@ -1,0 +1,459 @@
+// GP-level operations of the PCGPwM hot path, orchestrated over the kernels in covmat.cu / chol.cu /
+// dgemm.cu.  Everything is batched over "problems" (principal components or candidate
+// hyper-parameter sets) that share n and d.
+//
+//   gp_nll_grad   : PCGPwM.__negloglik + __negloglikgrad in one pass        (PCGPwM.py:850-907)
+//   gp_factorize  : full-n stage of __fitGP1d -> Linv, pw, sig2             (PCGPwM.py:810-846)
+//   gp_predict    : PC-space predictive mean/variance (+ d/dtheta)          (PCGPwM.py:219-270)
+//   pc_backproject: mean/var/covxhalf (+ gradients) through Phi             (PCGPwM.py:273-327)
+#include "gp.cuh"
+#include "chol.cuh"
+#include "covmat.cuh"
+#include "dgemm.cuh"
+
+namespace sb {
+namespace {
+
+constexpr int NB = CHOL_NB;
+
+// nll = sum log L_ii + n/2 log sig2hat + 1/2 sum ((1e-8 + hyp - mu)/s)^2 ;  sig2hat = (|y|^2 + s0)/(n + s0)
+__global__ void __launch_bounds__(256) nll_finalize_kernel(int n, int d, const double* __restrict__ Ab, long lda,
+                                                           long strideA, const double* __restrict__ hypb,
+                                                           const double* __restrict__ regmean,
+                                                           const double* __restrict__ regstd, double s0,
+                                                           double* __restrict__ nll, double* __restrict__ sig2hat,
+                                                           double* __restrict__ logdet_half) {
+    __shared__ double red[32];
+    const int z = blockIdx.x;
+    const double* A = Ab + (long)z * strideA;
+    double ld = 0.0, yy = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        ld += log(A[(long)i * lda + i]);
+        double y = A[(long)n * lda + i];
+        yy += y * y;
+    }
+    ld = block_sum(ld, red);
+    yy = block_sum(yy, red);
+    if (threadIdx.x == 0) {
+        double s2 = (yy + s0) / (n + s0);
+        if (sig2hat) sig2hat[z] = s2;
+        if (logdet_half) logdet_half[z] = ld;
+        if (nll) {
+            double pr = 0.0;
+            const int p = d + 3;
+            for (int k = 0; k < p; k++) {
+                double t = (1e-8 + hypb[(long)z * p + k] - regmean[k]) / regstd[k];
+                pr += t * t;
+            }
+            nll[z] = ld + 0.5 * n * log(s2) + 0.5 * pr;
+        }
+    }
+}
+
+struct CovConsts {
+    double ell[MAXD], ginv[MAXD];
+    double onemc;
+};
+
+constexpr int JC = 256;          // design points per CTA in the predict epilogue
+constexpr int XLD = MAXD + 1;
+
+// Per (PC, 32 new thetas, 256 design points): partial sums over j of
+//   T1^2, r pw, and (with gradients) T2 dr_i, dr_i pw, where dr_i = dR0/dtheta*_i rebuilt from r.
+__global__ void __launch_bounds__(256) predict_partial_kernel(
+    int n, int d, int B, const double* __restrict__ theta, const double* __restrict__ thetanew,
+    const double* __restrict__ hypcovb, const int* __restrict__ fidx, const int* __restrict__ fu,
+    const double* __restrict__ pwb, const double* __restrict__ rTb, long ldb, long strideU,
+    const double* __restrict__ T1b, const double* __restrict__ T2b, long strideT, int want_grad,
+    double* __restrict__ partial, int nchunks, int Q) {
+    __shared__ double xj[JC * XLD];
+    __shared__ double xb[32 * XLD];
+    __shared__ double pwj[JC];
+    __shared__ double red[8][33];
+    __shared__ CovConsts cc;
+    const int k = blockIdx.z, chunk = blockIdx.y, b0 = blockIdx.x * 32;
+    const int f = fidx[k], u = fu[f];
+    const double* hc = hypcovb + (long)u * (d + 1);
+    if (threadIdx.x < d) {
+        cc.ell[threadIdx.x] = exp(hc[threadIdx.x]);
+        cc.ginv[threadIdx.x] = exp(-hc[threadIdx.x]);
+    }
+    if (threadIdx.x == 32) {
+        double e = exp(hc[d]);
+        cc.onemc = e / (1.0 + e);
+    }
+    __syncthreads();
+    const int j0 = chunk * JC;
+    for (int idx = threadIdx.x; idx < JC * d; idx += blockDim.x) {
+        int r = idx / d, c = idx % d;
+        xj[r * XLD + c] = (j0 + r < n) ? theta[(long)(j0 + r) * d + c] / cc.ell[c] : 0.0;
+    }
+    for (int idx = threadIdx.x; idx < 32 * d; idx += blockDim.x) {
+        int r = idx / d, c = idx % d;
+        xb[r * XLD + c] = (b0 + r < B) ? thetanew[(long)(b0 + r) * d + c] / cc.ell[c] : 0.0;
+    }
+    for (int idx = threadIdx.x; idx < JC; idx += blockDim.x) pwj[idx] = (j0 + idx < n) ? pwb[(long)k * n + j0 + idx] : 0.0;
+    __syncthreads();
+
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int b = b0 + tx;
+    double s1 = 0.0, s2 = 0.0, dv[MAXD], dp[MAXD];
+#pragma unroll
+    for (int i = 0; i < MAXD; i++) dv[i] = dp[i] = 0.0;
+    if (b < B) {
+        const double* rT = rTb + (long)u * strideU;
+        const double* T1 = T1b + (long)f * strideT;
+        const double* T2 = T2b ? T2b + (long)f * strideT : nullptr;
+        for (int jl = ty; jl < JC; jl += 8) {
+            int j = j0 + jl;
+            if (j >= n) break;
+            double r = rT[(long)j * ldb + b];
+            double t1 = T1[(long)j * ldb + b];
+            double pwv = pwj[jl];
+            s1 += t1 * t1;
+            s2 += r * pwv;
+            if (want_grad) {
+                double t2 = T2[(long)j * ldb + b];
+                double rp = r - cc.onemc;                          // R_pre
+#pragma unroll
+                for (int i = 0; i < MAXD; i++)
+                    if (i < d) {
+                        double s = xb[tx * XLD + i] - xj[jl * XLD + i];
+                        double dr = rp * (-cc.ginv[i] * s / (1.0 + fabs(s)));   // matern_covmat.pyx:13-24
+                        dv[i] += t2 * dr;
+                        dp[i] += dr * pwv;
+                    }
+            }
+        }
+    }
+    // fixed-order reduction over the 8 j-lanes, one quantity at a time
+    double* out = partial + (((long)k * nchunks + chunk) * Q) * ldb;
+    for (int q = 0; q < Q; q++) {
+        double v;
+        if (q == 0) v = s1;
+        else if (q == 1) v = s2;
+        else {
+            int i = (q - 2) >> 1;
+            double sel = 0.0;
+#pragma unroll
+            for (int ii = 0; ii < MAXD; ii++)
+                if (ii == i) sel = ((q - 2) & 1) ? dp[ii] : dv[ii];
+            v = sel;
+        }
+        __syncthreads();
+        red[ty][tx] = v;
+        __syncthreads();
+        if (ty == 0 && b < B) {
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; r++) s += red[r][tx];
+            out[(long)q * ldb + b] = s;
+        }
+    }
+}
+
+__global__ void predict_reduce_kernel(int K, int d, int B, long ldb, int nchunks, int Q, const double* __restrict__ partial,
+                                      const double* __restrict__ nug, const double* __restrict__ sig2, int want_grad,
+                                      int single_quirk, double* __restrict__ predvecs, double* __restrict__ predvars,
+                                      double* __restrict__ dpv, double* __restrict__ dpvar) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (b >= B) return;
+    const double omn = 1.0 - nug[k], s2k = sig2[k];
+    for (int q = 0; q < Q; q++) {
+        double s = 0.0;
+        for (int c = 0; c < nchunks; c++) s += partial[((((long)k * nchunks + c) * Q) + q) * ldb + b];
+        if (q == 0) predvars[(long)b * K + k] = s2k * fabs(1.0 - omn * omn * s);           // PCGPwM.py:270
+        else if (q == 1) predvecs[(long)b * K + k] = omn * s;                               // PCGPwM.py:246
+        else if (want_grad) {
+            int i = (q - 2) >> 1;
+            if ((q - 2) & 1) {
+                // the reference applies (1-nug) twice here (PCGPwM.py:236,268) except when B == 1 and d == 1
+                double extra = single_quirk ? 1.0 : omn;
+                dpv[((long)b * K + k) * d + i] = extra * omn * s;
+            } else {
+                dpvar[((long)b * K + k) * d + i] = -2.0 * s2k * omn * omn * s;              // PCGPwM.py:269
+            }
+        }
+    }
+}
+
+__global__ void backproject_meanvar_kernel(int m, int K, int B, const double* __restrict__ phi,
+                                           const double* __restrict__ offset, const double* __restrict__ extravar,
+                                           const double* __restrict__ pv, const double* __restrict__ pvar,
+                                           double* __restrict__ mean, double* __restrict__ var) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, x = blockIdx.y;
+    if (b >= B) return;
+    double sm = 0.0, sv = 0.0;
+    for (int k = 0; k < K; k++) {
+        double ph = phi[(long)x * K + k];
+        sm += pv[(long)b * K + k] * ph;
+        sv += pvar[(long)b * K + k] * ph * ph;
+    }
+    mean[(long)x * B + b] = sm + offset[x];                        // PCGPwM.py:277-278
+    var[(long)x * B + b] = extravar[x] + sv;                       // PCGPwM.py:279-280
+}
+
+__global__ void backproject_covxhalf_kernel(int m, int K, int B, const double* __restrict__ phi,
+                                            const double* __restrict__ pvar, double* __restrict__ cxh) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)m * B * K;
+    if (idx >= total) return;
+    int k = (int)(idx % K);
+    long xb = idx / K;
+    int b = (int)(xb % B), x = (int)(xb / B);
+    cxh[idx] = sqrt(pvar[(long)b * K + k]) * phi[(long)x * K + k];  // PCGPwM.py:291
+}
+
+__global__ void backproject_meangrad_kernel(int m, int K, int B, int d, const double* __restrict__ phi,
+                                            const double* __restrict__ dpv, double* __restrict__ mg) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)m * B * d;
+    if (idx >= total) return;
+    int i = (int)(idx % d);
+    long xb = idx / d;
+    int b = (int)(xb % B), x = (int)(xb / B);
+    double s = 0.0;
+    for (int k = 0; k < K; k++) s += dpv[((long)b * K + k) * d + i] * phi[(long)x * K + k];
+    mg[idx] = s;                                                    // PCGPwM.py:302-304
+}
+
+__global__ void backproject_covxgrad_kernel(int m, int K, int B, int d, const double* __restrict__ phi,
+                                            const double* __restrict__ pvar, const double* __restrict__ dpvar,
+                                            double* __restrict__ cg) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)m * B * K * d;
+    if (idx >= total) return;
+    int i = (int)(idx % d);
+    long r = idx / d;
+    int k = (int)(r % K);
+    r /= K;
+    int b = (int)(r % B), x = (int)(r / B);
+    double ds = 0.5 * dpvar[((long)b * K + k) * d + i] / sqrt(pvar[(long)b * K + k]);      // PCGPwM.py:309-310
+    cg[idx] = ds * phi[(long)x * K + k];
+}
+
+long lda_for(int n) { return round_up(n, 8); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+size_t gp_nll_grad_workspace(int batch, int n, int d, int want_grad) {
+    Workspace w(nullptr, 0);
+    long lda = lda_for(n);
+    w.take<double>((size_t)batch * (n + 1) * lda);
+    w.take<double>((size_t)batch);                                  // sig2hat
+    if (want_grad) {
+        w.take<double>((size_t)batch * n * lda);                    // Linv
+        w.take<double>((size_t)batch * trtri_tmp_elems(n));
+        w.take<double>((size_t)batch * n);                          // alpha
+        w.take<double>((size_t)batch * grad_contract_tiles(n) * MAXP);
+    } else {
+        w.take<double>((size_t)batch * cdiv(n, NB) * NB * NB);      // compact Dinv
+    }
+    return w.off;
+}
+
+int gp_nll_grad(int batch, int n, int d, const double* theta, long strideTheta, const double* g, long strideG,
+                const double* gvar, long strideGvar, const double* hyp, const double* regmean, const double* regstd,
+                double s0, int want_grad, double* nll, double* grad, int* info, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream) {
+    SB_CHECK_ARG(batch > 0 && n > 0, "gp_nll_grad: batch=%d n=%d", batch, n);
+    SB_CHECK_ARG(d >= 1 && d <= MAXD, "gp_nll_grad: d=%d outside [1,%d]", d, MAXD);
+    SB_CHECK_ARG(workspace_bytes >= gp_nll_grad_workspace(batch, n, d, want_grad), "gp_nll_grad: workspace too small");
+    SB_CHECK_ARG(!want_grad || grad != nullptr, "gp_nll_grad: grad is NULL");
+    Workspace w(workspace, workspace_bytes);
+    const long lda = lda_for(n);
+    const long strideA = (long)(n + 1) * lda;
+    double* A = w.take<double>((size_t)batch * strideA);
+    double* sig2hat = w.take<double>((size_t)batch);
+    SB_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, stream));
+    SB_TRY(gp_assemble(batch, n, d, theta, strideTheta, g, strideG, gvar, strideGvar, hyp, A, lda, strideA, stream));
+
+    CholBatch c{};
+    c.batch = batch; c.n = n; c.mrows = n + 1; c.A = A; c.lda = lda; c.strideA = strideA; c.info = info;
+    double *Linv = nullptr, *tmp = nullptr, *alpha = nullptr, *partial = nullptr;
+    const long strideL = (long)n * lda;
+    if (want_grad) {
+        Linv = w.take<double>((size_t)batch * strideL);
+        tmp = w.take<double>((size_t)batch * trtri_tmp_elems(n));
+        alpha = w.take<double>((size_t)batch * n);
+        partial = w.take<double>((size_t)batch * grad_contract_tiles(n) * MAXP);
+        SB_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * batch * strideL, stream));
+        c.Dinv = Linv; c.ldd = lda; c.strideD = strideL; c.blockD = (long)NB * lda + NB;
+    } else {
+        c.Dinv = w.take<double>((size_t)batch * cdiv(n, NB) * NB * NB);
+        c.ldd = NB; c.strideD = (long)cdiv(n, NB) * NB * NB; c.blockD = (long)NB * NB;
+    }
+    SB_TRY(potrf_batched(c, stream));
+    nll_finalize_kernel<<<batch, 256, 0, stream>>>(n, d, A, lda, strideA, hyp, regmean, regstd, s0, nll, sig2hat, nullptr);
+    SB_LAUNCH_CHECK();
+    if (!want_grad) return 0;
+    SB_TRY(trtri_batched(batch, n, A, lda, strideA, Linv, lda, strideL, tmp, (long)trtri_tmp_elems(n), stream));
+    SB_TRY(trmv_lower_t_batched(batch, n, Linv, lda, strideL, nullptr, A + (long)n * lda, strideA, alpha, n, stream));
+    SB_TRY(lauum_batched(batch, n, Linv, lda, strideL, A, lda, strideA, stream));     // Rinv (lower) overwrites L
+    SB_TRY(gp_grad_contract(batch, n, d, theta, strideTheta, gvar, strideGvar, hyp, regmean, regstd, A, lda, strideA,
+                            alpha, n, sig2hat, s0, partial, grad, stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t gp_factorize_workspace(int batch, int n) {
+    Workspace w(nullptr, 0);
+    long lda = lda_for(n);
+    w.take<double>((size_t)batch * (n + 1) * lda);
+    w.take<double>((size_t)batch * trtri_tmp_elems(n));
+    return w.off;
+}
+
+int gp_factorize(int batch, int n, int d, const double* theta, long strideTheta, const double* g, long strideG,
+                 const double* gvar, long strideGvar, const double* hyp, double s0, double* Linv, long ldl,
+                 long strideL, double* pw, double* sig2, double* logdet_half, int* info, void* workspace,
+                 size_t workspace_bytes, cudaStream_t stream) {
+    SB_CHECK_ARG(batch > 0 && n > 0, "gp_factorize: batch=%d n=%d", batch, n);
+    SB_CHECK_ARG(d >= 1 && d <= MAXD, "gp_factorize: d=%d outside [1,%d]", d, MAXD);
+    SB_CHECK_ARG(ldl >= n && strideL >= (long)n * ldl, "gp_factorize: bad Linv layout");
+    SB_CHECK_ARG(workspace_bytes >= gp_factorize_workspace(batch, n), "gp_factorize: workspace too small");
+    Workspace w(workspace, workspace_bytes);
+    const long lda = lda_for(n);
+    const long strideA = (long)(n + 1) * lda;
+    double* A = w.take<double>((size_t)batch * strideA);
+    double* tmp = w.take<double>((size_t)batch * trtri_tmp_elems(n));
+    SB_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, stream));
+    SB_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * ((size_t)(batch - 1) * strideL + (size_t)n * ldl), stream));
+    SB_TRY(gp_assemble(batch, n, d, theta, strideTheta, g, strideG, gvar, strideGvar, hyp, A, lda, strideA, stream));
+    CholBatch c{};
+    c.batch = batch; c.n = n; c.mrows = n + 1; c.A = A; c.lda = lda; c.strideA = strideA; c.info = info;
+    c.Dinv = Linv; c.ldd = ldl; c.strideD = strideL; c.blockD = (long)NB * ldl + NB;
+    SB_TRY(potrf_batched(c, stream));
+    nll_finalize_kernel<<<batch, 256, 0, stream>>>(n, d, A, lda, strideA, hyp, nullptr, nullptr, s0, nullptr, sig2,
+                                                   logdet_half);
+    SB_LAUNCH_CHECK();
+    SB_TRY(trtri_batched(batch, n, A, lda, strideA, Linv, ldl, strideL, tmp, (long)trtri_tmp_elems(n), stream));
+    SB_TRY(trmv_lower_t_batched(batch, n, Linv, ldl, strideL, nullptr, A + (long)n * lda, strideA, pw, n, stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PCs that share a factor (same hyper-parameters and gvar) still have their own scores g_j:
+//   y_j = Linv g_j,  pw_j = Linv' y_j = R^-1 g_j,  sig2_j = (|y_j|^2 + s0)/(n + s0)     (PCGPwM.py:823-846)
+__global__ void __launch_bounds__(256) sig2_kernel(int n, const double* __restrict__ y, double s0,
+                                                   double* __restrict__ sig2) {
+    __shared__ double red[32];
+    const int z = blockIdx.x;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double v = y[(long)z * n + i];
+        acc += v * v;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) sig2[z] = (acc + s0) / (n + s0);
+}
+
+int gp_weights(int K, int n, const double* Linv, long ldl, long strideL, const int* fidx, const double* g, double s0,
+               double* pw, double* sig2, double* ytmp, cudaStream_t stream) {
+    SB_CHECK_ARG(K > 0 && n > 0, "gp_weights: empty problem");
+    SB_TRY(trmv_lower_batched(K, n, Linv, ldl, strideL, fidx, g, n, ytmp, n, stream));
+    sig2_kernel<<<K, 256, 0, stream>>>(n, ytmp, s0, sig2);
+    SB_LAUNCH_CHECK();
+    SB_TRY(trmv_lower_t_batched(K, n, Linv, ldl, strideL, fidx, ytmp, n, pw, n, stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+static long ldb_for(int B) { return round_up(B, 8); }
+
+size_t gp_predict_workspace(int K, int nf, int nu, int n, int d, int B, int want_grad) {
+    Workspace w(nullptr, 0);
+    long ldb = ldb_for(B);
+    int Q = 2 + (want_grad ? 2 * d : 0);
+    w.take<double>((size_t)nu * n * ldb);
+    w.take<double>((size_t)nf * n * ldb);
+    if (want_grad) w.take<double>((size_t)nf * n * ldb);
+    w.take<double>((size_t)K * cdiv(n, JC) * Q * ldb);
+    return w.off;
+}
+
+int gp_predict(int K, int nf, int nu, int n, int d, int B, const double* theta, const double* thetanew,
+               const double* hypcov, const int* fu, const int* fidx, const double* nug, const double* sig2,
+               const double* Linv, long ldl, long strideL, const double* pw, int want_grad, double* predvecs,
+               double* predvars, double* dpv, double* dpvar, void* workspace, size_t workspace_bytes,
+               cudaStream_t stream) {
+    SB_CHECK_ARG(K > 0 && nf > 0 && nu > 0 && n > 0 && B > 0, "gp_predict: empty problem");
+    SB_CHECK_ARG(d >= 1 && d <= MAXD, "gp_predict: d=%d outside [1,%d]", d, MAXD);
+    SB_CHECK_ARG(workspace_bytes >= gp_predict_workspace(K, nf, nu, n, d, B, want_grad), "gp_predict: workspace too small");
+    SB_CHECK_ARG(!want_grad || (dpv && dpvar), "gp_predict: gradient outputs are NULL");
+    Workspace w(workspace, workspace_bytes);
+    const long ldb = ldb_for(B);
+    const int Q = 2 + (want_grad ? 2 * d : 0);
+    const int nchunks = cdiv(n, JC);
+    const long strideT = (long)n * ldb;
+    double* rT = w.take<double>((size_t)nu * strideT);
+    double* T1 = w.take<double>((size_t)nf * strideT);
+    double* T2 = want_grad ? w.take<double>((size_t)nf * strideT) : nullptr;
+    double* partial = w.take<double>((size_t)K * nchunks * Q * ldb);
+
+    SB_TRY(cross_cov_t(nu, n, d, B, theta, thetanew, hypcov, rT, ldb, strideT, stream));
+    {                                           // T1 = Linv r'            (n x B per factor)
+        GemmArgs g{};
+        g.M = n; g.N = B; g.K = n;
+        g.A = Linv; g.lda = ldl; g.strideA = strideL; g.a_kc = true;
+        g.B = rT; g.ldb = ldb; g.strideB = strideT; g.idxB = fu; g.b_kc = false;
+        g.C = T1; g.ldc = ldb; g.strideC = strideT;
+        g.alpha = 1.0; g.beta = 0.0; g.flags = GEMM_A_LOWER;
+        SB_TRY(launch_dgemm(g, nf, -1, stream));
+    }
+    if (want_grad) {                            // T2 = Linv' T1 = Rinv r'
+        GemmArgs g{};
+        g.M = n; g.N = B; g.K = n;
+        g.A = Linv; g.lda = ldl; g.strideA = strideL; g.a_kc = false;
+        g.B = T1; g.ldb = ldb; g.strideB = strideT; g.b_kc = false;
+        g.C = T2; g.ldc = ldb; g.strideC = strideT;
+        g.alpha = 1.0; g.beta = 0.0; g.flags = GEMM_A_UPPER;
+        SB_TRY(launch_dgemm(g, nf, -1, stream));
+    }
+    {
+        dim3 grid(cdiv(B, 32), nchunks, K);
+        predict_partial_kernel<<<grid, 256, 0, stream>>>(n, d, B, theta, thetanew, hypcov, fidx, fu, pw, rT, ldb, strideT,
+                                                         T1, T2, strideT, want_grad, partial, nchunks, Q);
+        SB_LAUNCH_CHECK();
+        dim3 grid2(cdiv(B, 128), K);
+        predict_reduce_kernel<<<grid2, 128, 0, stream>>>(K, d, B, ldb, nchunks, Q, partial, nug, sig2, want_grad,
+                                                         (B == 1 && d == 1) ? 1 : 0, predvecs, predvars, dpv, dpvar);
+        SB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+int pc_backproject(int m, int K, int B, int d, const double* phi, const double* offset, const double* extravar,
+                   const double* predvecs, const double* predvars, const double* dpv, const double* dpvar,
+                   double* mean, double* var, double* covxhalf, double* mean_grad, double* covxhalf_grad,
+                   cudaStream_t stream) {
+    SB_CHECK_ARG(m > 0 && K > 0 && B > 0, "pc_backproject: empty problem");
+    SB_CHECK_ARG(m <= 65535, "pc_backproject: m=%d exceeds grid.y", m);
+    {
+        dim3 grid(cdiv(B, 128), m);
+        backproject_meanvar_kernel<<<grid, 128, 0, stream>>>(m, K, B, phi, offset, extravar, predvecs, predvars, mean, var);
+        SB_LAUNCH_CHECK();
+    }
+    if (covxhalf) {
+        long total = (long)m * B * K;
+        backproject_covxhalf_kernel<<<cdiv(total, 256), 256, 0, stream>>>(m, K, B, phi, predvars, covxhalf);
+        SB_LAUNCH_CHECK();
+    }
+    if (mean_grad) {
+        SB_CHECK_ARG(dpv != nullptr, "pc_backproject: dpv is NULL");
+        long total = (long)m * B * d;
+        backproject_meangrad_kernel<<<cdiv(total, 256), 256, 0, stream>>>(m, K, B, d, phi, dpv, mean_grad);
+        SB_LAUNCH_CHECK();
+    }
+    if (covxhalf_grad) {
+        SB_CHECK_ARG(dpvar != nullptr, "pc_backproject: dpvar is NULL");
+        long total = (long)m * B * K * d;
+        backproject_covxgrad_kernel<<<cdiv(total, 256), 256, 0, stream>>>(m, K, B, d, phi, predvars, dpvar, covxhalf_grad);
+        SB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // namespace sb

@@ -1,0 +1,42 @@
+// GP-level entry points (see gp.cu / woodbury.cu); the C ABI in capi.cu forwards to these.
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+size_t gp_nll_grad_workspace(int batch, int n, int d, int want_grad);
+int gp_nll_grad(int batch, int n, int d, const double* theta, long strideTheta, const double* g, long strideG,
+                const double* gvar, long strideGvar, const double* hyp, const double* regmean, const double* regstd,
+                double s0, int want_grad, double* nll, double* grad, int* info, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream);
+
+size_t gp_factorize_workspace(int batch, int n);
+int gp_factorize(int batch, int n, int d, const double* theta, long strideTheta, const double* g, long strideG,
+                 const double* gvar, long strideGvar, const double* hyp, double s0, double* Linv, long ldl,
+                 long strideL, double* pw, double* sig2, double* logdet_half, int* info, void* workspace,
+                 size_t workspace_bytes, cudaStream_t stream);
+
+// pw (K,n), sig2 (K) for PC scores g (K,n) through factors Linv[fidx[j]]; ytmp: (K,n) scratch
+int gp_weights(int K, int n, const double* Linv, long ldl, long strideL, const int* fidx, const double* g, double s0,
+               double* pw, double* sig2, double* ytmp, cudaStream_t stream);
+
+size_t gp_predict_workspace(int K, int nf, int nu, int n, int d, int B, int want_grad);
+int gp_predict(int K, int nf, int nu, int n, int d, int B, const double* theta, const double* thetanew,
+               const double* hypcov, const int* fu, const int* fidx, const double* nug, const double* sig2,
+               const double* Linv, long ldl, long strideL, const double* pw, int want_grad, double* predvecs,
+               double* predvars, double* dpv, double* dpvar, void* workspace, size_t workspace_bytes,
+               cudaStream_t stream);
+
+int pc_backproject(int m, int K, int B, int d, const double* phi, const double* offset, const double* extravar,
+                   const double* predvecs, const double* predvars, const double* dpv, const double* dpvar,
+                   double* mean, double* var, double* covxhalf, double* mean_grad, double* covxhalf_grad,
+                   cudaStream_t stream);
+
+constexpr int WOODBURY_MAXK = 112;
+// sinv: (2, m) = 1/yvar and 1/(yvar+|extravar|);  G: (2, K, K) = Phi' diag(sinv_v) Phi;  fired: device int
+int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const double* predvars, const double* dpv,
+                    const double* dpvar, const double* phiT, const double* resid0, const double* extravar,
+                    const double* sinv, const double* G, int want_grad, double* ll, double* dll, int* fired,
+                    cudaStream_t stream);
+
+}  // namespace sb

@@ -1,0 +1,196 @@
+// Woodbury-form Gaussian log-likelihood (+ d/dtheta) for a whole batch of theta proposals in one
+// launch: the PC-space restatement of directbayeswoodbury.loglik / loglik_grad
+// (src/surmise/calibrationmethods/directbayeswoodbury.py:261-383).
+//
+//   v = predvars[b], pv = predvecs[b], D = diag(sqrt v), G = Phi' Sigma^-1 Phi (theta independent)
+//   r = (y - offset) - Phi pv   (kept in m-space: expanding r' Sigma^-1 r in k-space cancels badly)
+//   q = Phi' Sigma^-1 r,  A = I + D G D,  l = -1/2 log|A| - 1/2 (r' Sigma^-1 r - (Dq)' A^-1 (Dq))
+// One CTA per theta; work per theta O(m k + k^3 + d k^2); nothing of size m x B x k x d exists.
+// The batch-wide "extravar" trigger (dbw.py:277-284) is a pre-pass that ORs a device flag; the
+// main kernel then selects Sigma = yvar or yvar + |extravar| (both Gram matrices are precomputed).
+#include "gp.cuh"
+
+namespace sb {
+namespace {
+
+constexpr int WT = 128;
+
+__global__ void __launch_bounds__(WT) woodbury_trigger_kernel(int B, int K, int m, const double* __restrict__ predvars,
+                                                              const double* __restrict__ phiT,
+                                                              const double* __restrict__ extravar, int* fired) {
+    const int b = blockIdx.x;
+    extern __shared__ double sh[];
+    double* v = sh;
+    for (int a = threadIdx.x; a < K; a += WT) v[a] = predvars[(long)b * K + a];
+    __syncthreads();
+    bool hit = false;
+    for (int x = threadIdx.x; x < m; x += WT) {
+        double s = 0.0;
+        for (int a = 0; a < K; a++) {
+            double ph = phiT[(long)a * m + x];
+            s += v[a] * ph * ph;                                   // sum_k covxhalf^2
+        }
+        double var = extravar[x] + s;                               // emulator variance at (x, theta_b)
+        if (fabs(var / (1e-4 + (1.0 + 1e-4) * s)) > 1.0) hit = true;
+    }
+    if (__syncthreads_or(hit) && threadIdx.x == 0) atomicOr(fired, 1);
+}
+
+__global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m, int d,
+                                                             const double* __restrict__ predvecs,
+                                                             const double* __restrict__ predvars,
+                                                             const double* __restrict__ dpv,
+                                                             const double* __restrict__ dpvar,
+                                                             const double* __restrict__ phiT,
+                                                             const double* __restrict__ resid0,
+                                                             const double* __restrict__ sinvb,
+                                                             const double* __restrict__ Gb, const int* fired,
+                                                             int want_grad, double* __restrict__ ll,
+                                                             double* __restrict__ dll) {
+    extern __shared__ double sh[];
+    double* Lm = sh;                    // K*K : A, then L, then Ainv
+    double* Xm = Lm + K * K;            // K*K : L^-1
+    double* w = Xm + K * K;             // m   : Sigma^-1 r
+    double* D = w + m;                  // K each below
+    double* pvv = D + K;
+    double* q = pvv + K;
+    double* Dq = q + K;
+    double* J3 = Dq + K;
+    double* Nv = J3 + K;
+    double* MJ3 = Nv + K;
+    double* red = MJ3 + K;              // 32
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int variant = (*fired) ? 1 : 0;
+    const double* sinv = sinvb + (long)variant * m;
+    const double* G = Gb + (long)variant * K * K;
+
+    for (int a = tid; a < K; a += WT) {
+        D[a] = sqrt(predvars[(long)b * K + a]);
+        pvv[a] = predvecs[(long)b * K + a];
+    }
+    __syncthreads();
+    double t1 = 0.0;
+    for (int x = tid; x < m; x += WT) {
+        double r = resid0[x];
+        for (int a = 0; a < K; a++) r -= phiT[(long)a * m + x] * pvv[a];
+        double wx = sinv[x] * r;
+        w[x] = wx;
+        t1 += r * wx;
+    }
+    const double term1 = block_sum(t1, red);                       // r' Sigma^-1 r   (also publishes w)
+    for (int a = warp; a < K; a += WT / 32) {
+        double s = 0.0;
+        for (int x = lane; x < m; x += 32) s += phiT[(long)a * m + x] * w[x];
+        s = warp_sum(s);
+        if (lane == 0) {
+            q[a] = s;
+            Dq[a] = D[a] * s;
+        }
+    }
+    for (int idx = tid; idx < K * K; idx += WT) {
+        int i = idx / K, j = idx % K;
+        Lm[idx] = D[i] * G[idx] * D[j] + (i == j ? 1.0 : 0.0);
+        Xm[idx] = 0.0;
+    }
+    // Cholesky of A (k x k), lower, in shared memory
+    for (int j = 0; j < K; j++) {
+        __syncthreads();
+        double ljj = sqrt(Lm[j * K + j]);
+        __syncthreads();
+        for (int i = j + tid; i < K; i += WT) Lm[i * K + j] = (i == j) ? ljj : Lm[i * K + j] / ljj;
+        __syncthreads();
+        int rem = K - j - 1;
+        for (int idx = tid; idx < rem * rem; idx += WT) {
+            int i = j + 1 + idx / rem, c = j + 1 + idx % rem;
+            if (c <= i) Lm[i * K + c] -= Lm[i * K + j] * Lm[c * K + j];
+        }
+    }
+    __syncthreads();
+    double ldh = 0.0;
+    for (int a = tid; a < K; a += WT) ldh += log(Lm[a * K + a]);
+    const double logdet_half = block_sum(ldh, red);
+    // X = L^-1: each thread owns one column (no cross-thread dependence)
+    for (int c = tid; c < K; c += WT) {
+        Xm[c * K + c] = 1.0 / Lm[c * K + c];
+        for (int i = c + 1; i < K; i++) {
+            double s = 0.0;
+            for (int j = c; j < i; j++) s += Lm[i * K + j] * Xm[j * K + c];
+            Xm[i * K + c] = -s / Lm[i * K + i];
+        }
+    }
+    __syncthreads();
+    // Ainv = X' X  (full symmetric) into Lm
+    for (int idx = tid; idx < K * K; idx += WT) {
+        int a = idx / K, c = idx % K;
+        int lo = a > c ? a : c;
+        double s = 0.0;
+        for (int i = lo; i < K; i++) s += Xm[i * K + a] * Xm[i * K + c];
+        Lm[idx] = s;
+    }
+    __syncthreads();
+    double qd = 0.0;
+    for (int a = tid; a < K; a += WT) {
+        double s = 0.0;
+        for (int c = 0; c < K; c++) s += Lm[a * K + c] * Dq[c];
+        J3[a] = s;
+        qd += Dq[a] * s;
+    }
+    const double quad = block_sum(qd, red);                        // (Dq)' A^-1 (Dq)
+    if (tid == 0) ll[b] = -logdet_half - 0.5 * (term1 - quad);     // dbw.py:303-304
+    if (!want_grad) return;
+
+    for (int a = tid; a < K; a += WT) {
+        double sN = 0.0, sM = 0.0;
+        for (int c = 0; c < K; c++) {
+            double mac = G[a * K + c] * D[c];                      // (G D)_ac
+            sN += mac * Lm[c * K + a];
+            sM += mac * J3[c];
+        }
+        Nv[a] = sN;
+        MJ3[a] = sM;
+    }
+    __syncthreads();
+    for (int i = 0; i < d; i++) {
+        double val = 0.0;
+        for (int a = tid; a < K; a += WT) {
+            double dpa = dpv[((long)b * K + a) * d + i];
+            double dD = 0.5 * dpvar[((long)b * K + a) * d + i] / D[a];
+            double gd = 0.0;
+            for (int c = 0; c < K; c++) gd += G[a * K + c] * dpv[((long)b * K + c) * d + i];
+            double dJ2 = -D[a] * gd + dD * q[a];
+            // -1/2 dterm3 - 1/2 (dterm1 - dterm2), term by term (dbw.py:344-381 in k-space)
+            val += -dD * Nv[a] + q[a] * dpa + dJ2 * J3[a] - dD * J3[a] * MJ3[a];
+        }
+        double s = block_sum(val, red);
+        if (tid == 0) dll[(long)b * d + i] = s;
+    }
+}
+
+}  // namespace
+
+int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const double* predvars, const double* dpv,
+                    const double* dpvar, const double* phiT, const double* resid0, const double* extravar,
+                    const double* sinv, const double* G, int want_grad, double* ll, double* dll, int* fired,
+                    cudaStream_t stream) {
+    SB_CHECK_ARG(B > 0 && m > 0, "woodbury: empty batch");
+    SB_CHECK_ARG(K >= 1 && K <= WOODBURY_MAXK, "woodbury: k=%d outside [1,%d]", K, WOODBURY_MAXK);
+    SB_CHECK_ARG(!want_grad || (dpv && dpvar && dll), "woodbury: gradient buffers are NULL");
+    size_t smem = (size_t)(2 * K * K + m + 7 * K + 32) * sizeof(double);
+    SB_CHECK_ARG(smem <= 227 * 1024, "woodbury: k=%d, m=%d need %zu B of shared memory", K, m, smem);
+    static bool configured[64] = {false};
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !configured[dev]) {
+        SB_CUDA(cudaFuncSetAttribute(woodbury_loglik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured[dev] = true;
+    }
+    SB_CUDA(cudaMemsetAsync(fired, 0, sizeof(int), stream));
+    woodbury_trigger_kernel<<<B, WT, K * sizeof(double), stream>>>(B, K, m, predvars, phiT, extravar, fired);
+    SB_LAUNCH_CHECK();
+    woodbury_loglik_kernel<<<B, WT, smem, stream>>>(B, K, m, d, predvecs, predvars, dpv, dpvar, phiT, resid0, sinv, G,
+                                                    fired, want_grad, ll, dll);
+    SB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace sb

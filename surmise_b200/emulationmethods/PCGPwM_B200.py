@@ -1,0 +1,411 @@
+"""PCGPwM_B200 -- surmise emulation method: PCGP with missingness on one B200 (fp64, sm_100a).
+
+Drop-in sibling of surmise/emulationmethods/PCGPwM.py behind the same plugin contract
+(`fit(fitinfo, x, theta, f, **args)`, `predict(predinfo, fitinfo, x, theta, **args)`,
+surmise/emulation.py:150-153): `emulator(x, theta, f, method='PCGPwM_B200')` after
+`surmise_b200.register()`.
+
+What runs where
+  host (numpy)  : standardisation / imputation / PCA (_pca.py), the share-or-own bookkeeping of
+                  __fitGPs/__fitGP1d and scipy's L-BFGS-B driver -- the reference's own control flow;
+  device (CUDA) : every covariance build, every likelihood+gradient evaluation, the full-n
+                  factorisations, predict and back-projection (surmise_b200/csrc).
+
+Differences from the reference that a user can observe (all documented in DESIGN.md):
+  * one triangular factor Linv (Linv' Linv = R^-1) per distinct (hyper-parameters, gvar) pair is kept
+    on the device instead of R, Rinv and Vh per PC (PCGPwM.py:817-846) -- 1/3 the memory or less;
+  * the likelihood is evaluated through a Cholesky factorisation instead of eigh+abs (PCGPwM.py:858);
+    where the reference's R is not positive definite (rounding noise in unscaled_pcstdvar) the
+    evaluation reports breakdown and the optimiser treats the point as infeasible;
+  * the full-n factorisation is done once after the three sweeps, batched over PCs, instead of after
+    every __fitGP1d call (the intermediate ones are never read by the reference either).
+"""
+import warnings
+from pprint import pformat
+
+import numpy as np
+import scipy.optimize as spo
+
+from .. import _pca
+
+SIG2_OF_CONST = 0.01        # PCGPwM.py:705 / 719
+_INFEASIBLE = 1e30          # value handed to L-BFGS-B when the factorisation breaks down
+
+
+def _ops():
+    from .. import ops
+    return ops
+
+
+# ------------------------------------------------------------------------------------------------
+# fit
+# ------------------------------------------------------------------------------------------------
+def fit(fitinfo, x, theta, f, epsilonPC=0.001, epsilonImpute=10e-6, lognugmean=-10, lognugLB=-20,
+        varconstant=None, dampalpha=0.3, eta=10, standardpcinfo=None, verbose=0, nhyptrain=None,
+        **kwargs):
+    """Same arguments as PCGPwM.fit (PCGPwM.py:12-137) plus
+    nhyptrain : None (reference rule min(20 d, n), PCGPwM.py:744), an int, or 'all'.
+    """
+    ops = _ops()
+    ops._torch()                                   # fail loudly without CUDA before any work
+    f = np.asarray(f, dtype=np.float64).T          # (n, m)
+    theta = np.asarray(theta, dtype=np.float64)
+    fitinfo['epsilonImpute'] = epsilonImpute
+    fitinfo['epsilonPC'] = epsilonPC
+    fitinfo['dampalpha'] = dampalpha
+    fitinfo['eta'] = eta
+    fitinfo['theta'] = theta
+    fitinfo['f'] = f
+    fitinfo['x'] = x
+
+    if standardpcinfo is None:
+        spc, mof, mofrows = _pca.standardize(f, epsilonPC, epsilonImpute)
+    else:
+        spc = _pca.complete_pcinfo(standardpcinfo, f)
+        mof = None if np.all(np.isfinite(f)) else ~np.isfinite(f)
+        mofrows = None if mof is None else np.where(mof.any(axis=1))[0]
+    fitinfo['mof'], fitinfo['mofrows'] = mof, mofrows
+    fitinfo['standardpcinfo'] = spc
+    if 'U' in spc:
+        U, S = spc['U'], spc['S']
+    else:
+        U, S, _vt = np.linalg.svd(spc['fs'].T, full_matrices=False)
+    fitinfo.update(_pca.principal_components(spc['fs'], U, S, mof, mofrows, epsilonPC, epsilonImpute))
+    numpcs = fitinfo['pc'].shape[1]
+    if verbose > 0:
+        print(fitinfo.get('method', 'PCGPwM_B200'), 'considering ', numpcs, 'PCs')
+
+    logvarc = np.log(varconstant) if varconstant is not None else None
+    fitter = _GPFitter(fitinfo, theta, lognugmean, lognugLB, logvarc, nhyptrain)
+    emulist = fitter.run(previous=fitinfo.get('emulist'))
+    fitinfo['varc_status'] = 'fixed' if varconstant is not None else 'optimized'
+    fitinfo['logvarc'] = np.array([e['hypvarconst'] for e in emulist])
+    fitinfo['pcstdvar'] = np.exp(fitinfo['logvarc']) * fitinfo['unscaled_pcstdvar']
+    fitinfo['emulist'] = emulist
+    fitinfo['_b200'] = fitter.device_state(emulist, spc, fitinfo['pcti'])
+    fitinfo['param_desc'] = _param_desc(fitinfo)
+    return
+
+
+def hyper_prior(theta, lognugmean, lognugLB, logvarc):
+    """Regulariser mean / box / std for [gamma_0..gamma_d, h_v, h_nu] (PCGPwM.py:728-742)."""
+    d = theta.shape[1]
+    base = 0.5 * np.log(d) + np.log(np.std(theta, 0))
+    vmid, vlo, vhi = (4, -8, 8) if logvarc is None else (logvarc, logvarc - 0.5, logvarc + 0.5)
+    mean = np.concatenate([base, [0, vmid, lognugmean]])
+    lo = np.concatenate([base - 4, [-12, vlo, lognugLB]])
+    hi = np.concatenate([base + 4, [2, vhi, -8]])
+    std = (hi - lo) / 8
+    std[-3] = 2
+    std[-1] = 4
+    return mean, lo, hi, std
+
+
+class _GPFitter:
+    """Hyper-parameter search for all PCs with device-side likelihoods (PCGPwM.py:678-847)."""
+
+    def __init__(self, fitinfo, theta, lognugmean, lognugLB, logvarc, nhyptrain):
+        self.ops = _ops()
+        torch = self.ops._torch()
+        self.torch = torch
+        self.theta = theta
+        self.n, self.d = theta.shape
+        self.pc = fitinfo['pc']
+        # damped per-row variance of the imputed PCs: min(eta, v / (1-v)^alpha)   (PCGPwM.py:755)
+        v = fitinfo['unscaled_pcstdvar']
+        self.gvar = np.minimum(fitinfo['eta'], v / ((1 - v) ** fitinfo['dampalpha']))
+        self.mean, self.lo, self.hi, self.std = hyper_prior(theta, lognugmean, lognugLB, logvarc)
+        self.p = self.mean.shape[0]
+        self.share_bar = 1.25 * (self.p + 5 * np.sqrt(self.p))       # PCGPwM.py:776-777, 808-809
+        if nhyptrain is None:
+            self.nh = min(20 * self.d, self.n)
+        elif nhyptrain == 'all':
+            self.nh = self.n
+        else:
+            self.nh = int(min(max(int(nhyptrain), 2), self.n))
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self.theta_dev = torch.from_numpy(np.ascontiguousarray(theta)).to(dev)
+        self.pc_dev = torch.from_numpy(np.ascontiguousarray(self.pc.T)).to(dev)        # (k, n)
+        self.gvar_dev = torch.from_numpy(np.ascontiguousarray(self.gvar.T)).to(dev)    # (k, n)
+        self.mean_dev = torch.from_numpy(self.mean).to(dev)
+        self.std_dev = torch.from_numpy(self.std).to(dev)
+        self.nevals = 0
+
+    # -- one PC ---------------------------------------------------------------------------------
+    def _subsample(self, j):
+        """Rows used for the hyper-parameter search; consumes np.random like PCGPwM.py:744-750."""
+        if self.n > self.nh:
+            rows = np.random.choice(self.n, self.nh, replace=False)
+            idx = self.torch.from_numpy(rows).to(self.theta_dev.device)
+            data = self.ops.GPData(self.theta_dev[idx], self.pc_dev[j][idx], self.gvar_dev[j][idx])
+        else:
+            rows = np.arange(self.n)
+            data = self.ops.GPData(self.theta_dev, self.pc_dev[j], self.gvar_dev[j])
+        return rows, data
+
+    def _nll(self, data, hyps, want_grad):
+        self.nevals += len(hyps)
+        val, grad, info = self.ops.gp_nll_grad(data, np.asarray(hyps), self.mean_dev, self.std_dev,
+                                               SIG2_OF_CONST, want_grad)
+        bad = (info != 0) | ~np.isfinite(val)
+        val = np.where(bad, _INFEASIBLE, val)
+        if grad is not None:
+            grad = np.where(bad[:, None], 0.0, grad)
+        return val, grad
+
+    def fit_one(self, j, cand, cand_ids):
+        """__fitGP1d without its full-n stage.  Returns (hyp, hypind or -1, subsample rows)."""
+        rows, data = self._subsample(j)
+        hyp = 1 * self.mean
+        lead = -1
+        # candidate scan (PCGPwM.py:761-769): prior mean first, then every leader's hyper-parameters
+        trial = [self.mean] if cand is None else [self.mean] + [c for c in cand]
+        vals, _ = self._nll(data, trial, want_grad=False)
+        L0 = vals[0]
+        for c in range(1, len(trial)):
+            if vals[c] < L0:
+                hyp, L0, lead = trial[c], 1 * vals[c], cand_ids[c - 1]
+        skip = False
+        if lead > -0.5 and cand.ndim > 1:                           # PCGPwM.py:771-781
+            _, dL = self._nll(data, [hyp], want_grad=True)
+            nc = cand.shape[0]
+            scal = np.std(cand, 0) * nc / (1 + nc) + self.std / (1 + nc)
+            skip = np.sum((dL[0] * scal) ** 2) < self.share_bar
+        if not skip:                                                # PCGPwM.py:783-805
+            def scaled(v):
+                val, grad = self._nll(data, [self.mean + v * self.std], want_grad=True)
+                return float(val[0]), grad[0] * self.std
+            res = spo.minimize(scaled, (hyp - self.mean) / self.std, method='L-BFGS-B', jac=True,
+                               options={'gtol': 0.1},
+                               bounds=spo.Bounds((self.lo - self.mean) / self.std, (self.hi - self.mean) / self.std))
+            hypn = self.mean + res.x * self.std
+            likdiff = L0 - res.fun                                  # res.fun == nll(hypn): same kernel, same input
+        else:
+            likdiff = 0
+        if lead > -0.5 and (2 * likdiff) < self.share_bar:           # PCGPwM.py:808-833
+            return hyp, lead, rows
+        return hypn, -1, rows
+
+    # -- all PCs --------------------------------------------------------------------------------
+    def run(self, previous=None):
+        """Three Gauss-Seidel sweeps (PCGPwM.py:678-722) followed by ONE batched full-n factorisation."""
+        k = self.pc.shape[1]
+        hypinds = -1 * np.ones(k)
+        starts = None
+        if previous is not None:                                     # warm start on refit (680-685)
+            starts = np.zeros((k, previous[0]['hyp'].shape[0]))
+            for j in range(min(k, len(previous))):
+                starts[j] = previous[j]['hyp']
+                hypinds[j] = previous[j]['hypind']
+            if starts.shape[1] != self.p:
+                starts, hypinds = None, -1 * np.ones(k)
+        own = np.arange(k)
+        hyps = [None] * k
+        rows_used = [None] * k
+        for _sweep in range(3):
+            for j in range(k):
+                if np.sum(hypinds == own) > 0.5:
+                    leaders = np.where(hypinds == own)[0]
+                    hyp, hi, rows = self.fit_one(j, starts[leaders], leaders)
+                else:
+                    hyp, hi, rows = self.fit_one(j, None, None)
+                    starts = np.zeros((k, self.p))
+                hi = min(j, hi)
+                starts[j] = hyp
+                hypinds[j] = j if hi < -0.5 else hi
+                hyps[j], rows_used[j] = hyp, rows
+        return self._finalise(np.array(hyps), hypinds.astype(int), rows_used)
+
+    def _finalise(self, hyps, hypinds, rows_used):
+        """Full-data factorisations (PCGPwM.py:810-846), one per distinct (hyp, gvar), in one batch."""
+        ops, torch = self.ops, self.torch
+        k = hyps.shape[0]
+        keys, fidx, members = {}, np.zeros(k, dtype=np.int32), []
+        for j in range(k):
+            key = (hyps[j].tobytes(), self.gvar[:, j].tobytes())
+            if key not in keys:
+                keys[key] = len(members)
+                members.append(j)
+            fidx[j] = keys[key]
+        members = np.array(members)
+        Linv, clamped_f = self._factor_batch(members, hyps)
+        # pw and sig2 depend on the scores g_j, which differ between PCs sharing a factor
+        fidx_dev = torch.from_numpy(fidx).to(self.theta_dev.device)
+        pw, sig2 = ops.gp_weights(Linv, fidx_dev, self.pc_dev, SIG2_OF_CONST)
+        nug = np.exp(hyps[:, -1]) / (1 + np.exp(hyps[:, -1]))        # PCGPwM.py:813
+        pw_h, sig2_h = pw.cpu().numpy(), sig2.cpu().numpy()
+        emulist = []
+        for j in range(k):
+            rows = rows_used[j]
+            emulist.append({'hyp': hyps[j], 'hypcov': hyps[j][:-2], 'hypvarconst': hyps[j][-2], 'hypind': int(hypinds[j]),
+                            'nug': nug[j], 'sig2': sig2_h[j], 'pw': pw_h[j], 'sig2ofconst': SIG2_OF_CONST,
+                            'theta': self.theta[rows], 'g': self.pc[rows, j], 'gvar': self.gvar[rows, j],
+                            'hypregmean': self.mean, 'hypregLB': self.lo, 'hypregUB': self.hi, 'hypregstd': self.std,
+                            'gvar_clamped': bool(clamped_f[fidx[j]])})
+        self._Linv, self._fidx, self._members, self._pw, self._sig2 = Linv, fidx, members, pw, sig2
+        return emulist
+
+    def _factor_batch(self, members, hyps):
+        """Linv for each distinct problem; returns (Linv (nf,n,ldl), clamped flags (nf,))."""
+        ops, torch = self.ops, self.torch
+        idx = torch.from_numpy(members).to(self.theta_dev.device)
+        gv = self.gvar_dev[idx]
+        data = ops.GPData(self.theta_dev, self.pc_dev[idx], gv)
+        Linv, _pw, _s2, _ld, info = ops.gp_factorize(data, hyps[members], SIG2_OF_CONST)
+        clamped = np.zeros(len(members), dtype=bool)
+        bad = np.where(info != 0)[0]
+        if bad.size:
+            # R not positive definite: inside the hyper-parameter box that only happens through rounding
+            # noise (negative entries) in unscaled_pcstdvar; clamp those at their mathematical lower
+            # bound 0 and refactor the affected problems.
+            warnings.warn('PCGPwM_B200: covariance of %d component(s) not positive definite at the fitted '
+                          'hyper-parameters; negative imputation variances clamped to 0.' % bad.size)
+            bad_dev = torch.from_numpy(bad).to(idx.device)
+            data_b = ops.GPData(self.theta_dev, self.pc_dev[idx[bad_dev]], torch.clamp(gv[bad_dev], min=0.0))
+            Lb, _a, _b, _c, info_b = ops.gp_factorize(data_b, hyps[members[bad]], SIG2_OF_CONST)
+            if np.any(info_b != 0):
+                raise ValueError('PCGPwM_B200: covariance matrix not positive definite (info=%s)' % info_b)
+            Linv[bad_dev] = Lb
+            clamped[bad] = True
+        return Linv, clamped
+
+    def device_state(self, emulist, spc, pcti):
+        """Everything predict needs, as device tensors (kept in fitinfo['_b200'])."""
+        torch = self.torch
+        dev = self.theta_dev.device
+        k = len(emulist)
+        hypcov = np.array([e['hypcov'] for e in emulist])
+        # distinct covariance hyper-parameter sets (cross-covariances are shared between factors)
+        ukeys, fu = {}, np.zeros(len(self._members), dtype=np.int32)
+        ulist = []
+        for fi, j in enumerate(self._members):
+            key = hypcov[j].tobytes()
+            if key not in ukeys:
+                ukeys[key] = len(ulist)
+                ulist.append(hypcov[j])
+            fu[fi] = ukeys[key]
+        phi = pcti * spc['scale'][:, None]                           # PCGPwM.py:275
+        t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
+        return {'theta': self.theta_dev, 'Linv': self._Linv, 'pw': self._pw, 'sig2': self._sig2,
+                'nug': t(np.array([e['nug'] for e in emulist])), 'hypcov': t(np.array(ulist)),
+                'fu': t(fu, torch.int32), 'fidx': t(self._fidx, torch.int32),
+                'phi': t(phi), 'offset': t(spc['offset']), 'extravar': t(spc['extravar']),
+                'nevals': self.nevals}
+
+
+def import_state(theta, pc, gvar_damped, hyps, hypinds, pcti, spc):
+    """Build the device state from given hyper-parameters (no optimisation): used to load a
+    reference-fitted emulator (emulist[k]['hyp'], PCGPwM.py:817-846) for like-for-like prediction."""
+    fi = {'pc': np.asarray(pc), 'unscaled_pcstdvar': np.zeros_like(pc), 'eta': 10, 'dampalpha': 0.3}
+    fitter = _GPFitter(fi, np.asarray(theta, dtype=np.float64), -10, -20, None, None)
+    fitter.gvar = np.asarray(gvar_damped, dtype=np.float64)
+    fitter.gvar_dev = fitter.torch.from_numpy(np.ascontiguousarray(fitter.gvar.T)).to(fitter.theta_dev.device)
+    rows = [np.arange(fitter.n)] * pc.shape[1]
+    emulist = fitter._finalise(np.asarray(hyps, dtype=np.float64), np.asarray(hypinds).astype(int), rows)
+    return emulist, fitter.device_state(emulist, spc, pcti)
+
+
+# ------------------------------------------------------------------------------------------------
+# predict
+# ------------------------------------------------------------------------------------------------
+def match_rows(x, xfit):
+    """Rows of the fit-time x that each requested x row equals (PCGPwM.py:197-214).
+
+    Returns (xind, xnewind): prediction row xnewind[i] is fit row xind[i]; unmatched rows are absent.
+    """
+    if x is None:
+        idx = np.arange(xfit.shape[0])
+        return idx, idx
+    try:
+        if x.shape == xfit.shape and (np.all(np.equal(x, xfit)) or np.allclose(x, xfit)):
+            idx = np.arange(x.shape[0])
+            return idx, idx
+    except Exception:
+        pass
+    match = np.ones((x.shape[0], xfit.shape[0]), dtype=bool)
+    for c in range(x.shape[1]):
+        try:
+            match &= np.isclose(x[:, c][:, None].astype(float), xfit[:, c].astype(float))
+        except Exception:
+            match &= np.equal(x[:, c][:, None], xfit[:, c])
+    pairs = np.argwhere(match)
+    return pairs[:, 1], pairs[:, 0]
+
+
+def predict_pcspace(fitinfo, theta, return_grad=False, chunk=4096):
+    """Device tensors predvecs, predvars (B,k) [+ gradients (B,k,d)] for theta (B,d) numpy/tensor."""
+    ops = _ops()
+    torch = ops._torch()
+    st = fitinfo['_b200']
+    tn = ops._f64(torch, np.atleast_2d(theta) if not isinstance(theta, torch.Tensor) else theta)
+    B = tn.shape[0]
+    if B <= chunk:
+        return ops.gp_predict(st, tn, return_grad)
+    parts = [ops.gp_predict(st, tn[s:s + chunk], return_grad) for s in range(0, B, chunk)]
+    return tuple(None if parts[0][i] is None else torch.cat([p[i] for p in parts], 0) for i in range(4))
+
+
+def predict(predinfo, fitinfo, x, theta, **kwargs):
+    """Same contract and output shapes as PCGPwM.predict (PCGPwM.py:140-328)."""
+    ops = _ops()
+    torch = ops._torch()
+    return_grad = kwargs.get('return_grad', False) is True
+    return_covx = not (kwargs.get('return_covx', True) is False)
+    st = fitinfo['_b200']
+    theta = np.asarray(theta, dtype=np.float64)
+    if theta.ndim < 2:
+        theta = theta.reshape(1, -1)
+    B, d = theta.shape
+    xind, xnewind = match_rows(x, fitinfo['x'])
+    nx = fitinfo['x'].shape[0] if x is None else x.shape[0]
+
+    pv, pvar, dpv, dpvar = predict_pcspace(fitinfo, theta, return_grad)
+    sel = torch.from_numpy(np.asarray(xind, dtype=np.int64)).to(pv.device)
+    phi = st['phi'][sel].contiguous()
+    mean, var, cxh, mg, cg = ops.pc_backproject(phi, st['offset'][sel].contiguous(), st['extravar'][sel].contiguous(),
+                                                pv, pvar, dpv, dpvar, want_covx=return_covx)
+    K = pv.shape[1]
+
+    def scatter(t, tail):
+        out = np.full((nx,) + tail, np.nan)
+        out[xnewind] = t.cpu().numpy()
+        return out
+
+    predinfo['mean'] = scatter(mean, (B,))
+    predinfo['var'] = scatter(var, (B,))
+    predinfo['extravar'] = st['extravar'][sel].cpu().numpy()
+    predinfo['predvars'] = pvar.cpu().numpy()
+    predinfo['predvecs'] = pv.cpu().numpy()
+    predinfo['phi'] = phi.cpu().numpy()
+    predinfo['return_covx'] = return_covx
+    predinfo['return_grad'] = return_grad
+    if return_covx:
+        predinfo['covxhalf'] = scatter(cxh, (B, K))
+    if return_grad:
+        predinfo['mean_gradtheta'] = scatter(mg, (B, d))
+        predinfo['predvars_gradtheta'] = dpvar.cpu().numpy()
+        predinfo['predvecs_gradtheta'] = dpv.cpu().numpy()
+        if return_covx:
+            if not np.array_equal(xnewind, xind):
+                raise ValueError('Check shuffling of x indices within predictions.')   # PCGPwM.py:318-320
+            predinfo['covxhalf_gradtheta'] = cg.cpu().numpy()
+    return
+
+
+def _param_desc(fitinfo):
+    """Human-readable summary used by emulator.__repr__ (PCGPwM.py:938-964)."""
+    el = fitinfo['emulist']
+    k = len(el)
+    scales = 1 / (1 + np.exp(np.array([el[j]['hyp'][-2] for j in range(k)])))
+    lengthscales = np.array([el[j]['hyp'][:-3] for j in range(k)])
+    nuggets = np.array([el[j]['nug'] for j in range(k)])
+    return ('\taverage emulation residual variance (from principal components):\t{:.3E}\n'
+            '\tnumber of GP components:\t{:d}\n'
+            '\tGP parameters, following Gramacy (ch.5, 2022) notations:\n'
+            '\t\tscales (in log): \t{:s}\n'
+            '\t\tlengthscales (in log):\n\t\t\t{:s}\n'
+            '\t\tnuggets (in log):\t{:s}\n').format(
+        fitinfo['standardpcinfo']['extravar'].mean(), k,
+        pformat(['{:.3f}'.format(np.log(v)) for v in scales]),
+        pformat(lengthscales).replace('\n', '\n\t\t\t'),
+        pformat(['{:.3f}'.format(np.log(v)) for v in nuggets]))

@@ -1,0 +1,292 @@
+"""Device-tensor level wrappers over the C ABI (torch supplies memory and streams only).
+
+All tensors are float64 CUDA tensors (int32 where noted), contiguous.  Every function checks that
+it is handed CUDA memory: there is no CPU code path.
+"""
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check
+
+_workspaces = {}
+
+
+def _torch():
+    return _lib.require_cuda()
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream(torch):
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f64(torch, a, device=None):
+    """numpy / tensor -> contiguous float64 CUDA tensor."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+    t = t.to(device=device or torch.device('cuda', torch.cuda.current_device()), dtype=torch.float64)
+    return t.contiguous()
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.SurmiseB200Error('surmise_b200 ops need CUDA tensors (no CPU fallback)')
+
+
+def workspace(nbytes):
+    """Grow-only per-device scratch buffer (the library itself never allocates)."""
+    torch = _torch()
+    dev = torch.cuda.current_device()
+    ws = _workspaces.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        ws = None
+        _workspaces.pop(dev, None)
+        ws = torch.empty(int(nbytes * 1.1) + 1024, dtype=torch.uint8, device=torch.device('cuda', dev))
+        _workspaces[dev] = ws
+    return ws
+
+
+def release_workspaces():
+    _workspaces.clear()
+
+
+# ----------------------------------------------------------------------------------------------
+def covmat_device(x1, x2, gammav, grad_mode=0):
+    """R (n1,n2) [, dR planes (D,n1,n2)] on device.  Replaces matern_covmat.covmat (pyx:27-64)."""
+    torch = _torch()
+    _need_cuda(x1, x2, gammav)
+    n1, d = x1.shape
+    n2 = x2.shape[0]
+    R = torch.empty((n1, n2), dtype=torch.float64, device=x1.device)
+    dR = None
+    if grad_mode:
+        planes = d + 1 if grad_mode == 1 else d
+        dR = torch.empty((planes, n1, n2), dtype=torch.float64, device=x1.device)
+    check(lib.sb200_matern_covmat(_ptr(x1), n1, _ptr(x2), n2, d, _ptr(gammav), _ptr(R), n2, _ptr(dR), grad_mode,
+                                  _stream(torch)), 'sb200_matern_covmat')
+    return R, dR
+
+
+def covmat(x1, x2, gammav, return_gradhyp=False, return_gradx1=False):
+    """numpy-in / numpy-out drop-in for surmise.emulationsupport.matern_covmat.covmat."""
+    torch = _torch()
+    gam = np.asarray(gammav, dtype=np.float64)
+    d = gam.shape[0] - 1
+    a = np.asarray(x1, dtype=np.float64)
+    b = np.asarray(x2, dtype=np.float64)
+    a = a.reshape(1, d) if a.ndim < 2 else a          # pyx:29-32
+    b = b.reshape(1, d) if b.ndim < 2 else b
+    mode = 1 if return_gradhyp else (2 if return_gradx1 else 0)
+    R, dR = covmat_device(_f64(torch, a), _f64(torch, b), _f64(torch, gam), mode)
+    if mode:
+        return R.cpu().numpy(), dR.permute(1, 2, 0).cpu().numpy()
+    return R.cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------------
+class GPData:
+    """Device-resident (theta, g, gvar) of one or several GP problems sharing n and d.
+
+    theta: (n,d) shared or (nb,n,d); g: (n) or (nb,n); gvar: same shape as g or None.
+    """
+
+    def __init__(self, theta, g, gvar=None):
+        torch = _torch()
+        self.theta = _f64(torch, theta)
+        self.g = _f64(torch, g)
+        self.gvar = None if gvar is None else _f64(torch, gvar)
+        self.n, self.d = self.theta.shape[-2], self.theta.shape[-1]
+        self.stride_theta = 0 if self.theta.dim() == 2 else self.n * self.d
+        self.stride_g = 0 if self.g.dim() == 1 else self.n
+        self.stride_gvar = 0 if (self.gvar is None or self.gvar.dim() == 1) else self.n
+        self.nb_fixed = None
+        if self.theta.dim() == 3:
+            self.nb_fixed = self.theta.shape[0]
+        if self.g.dim() == 2:
+            self.nb_fixed = self.g.shape[0]
+
+
+def gp_nll_grad(data, hyp, regmean, regstd, sig2ofconst=0.01, want_grad=True):
+    """Batched PCGPwM.__negloglik (+ __negloglikgrad) (PCGPwM.py:850-907).
+
+    hyp: (nb, d+3) numpy or tensor.  Returns numpy (nll (nb,), grad (nb,p) or None, info (nb,)).
+    """
+    torch = _torch()
+    hyp_t = _f64(torch, np.atleast_2d(hyp) if not isinstance(hyp, torch.Tensor) else hyp)
+    nb, p = hyp_t.shape
+    n, d = data.n, data.d
+    if p != d + 3:
+        raise ValueError('hyp must have d+3 = %d columns' % (d + 3))
+    if data.nb_fixed is not None and data.nb_fixed != nb:
+        raise ValueError('batch mismatch between data (%d) and hyp (%d)' % (data.nb_fixed, nb))
+    rm, rs = _f64(torch, regmean), _f64(torch, regstd)
+    dev = hyp_t.device
+    nll = torch.empty(nb, dtype=torch.float64, device=dev)
+    grad = torch.empty((nb, p), dtype=torch.float64, device=dev) if want_grad else None
+    info = torch.empty(nb, dtype=torch.int32, device=dev)
+    nbytes = lib.sb200_gp_nll_grad_workspace(nb, n, d, int(want_grad))
+    ws = workspace(nbytes)
+    check(lib.sb200_gp_nll_grad(nb, n, d, _ptr(data.theta), data.stride_theta, _ptr(data.g), data.stride_g,
+                                _ptr(data.gvar), data.stride_gvar, _ptr(hyp_t),
+                                _ptr(rm), _ptr(rs), float(sig2ofconst), int(want_grad), _ptr(nll), _ptr(grad),
+                                _ptr(info), _ptr(ws), ws.numel(), _stream(torch)), 'sb200_gp_nll_grad')
+    if want_grad:
+        packed = torch.cat([nll[:, None], grad, info.to(torch.float64)[:, None]], dim=1).cpu().numpy()
+        return packed[:, 0], packed[:, 1:1 + p], packed[:, -1].astype(np.int64)
+    packed = torch.stack([nll, info.to(torch.float64)], dim=1).cpu().numpy()
+    return packed[:, 0], None, packed[:, 1].astype(np.int64)
+
+
+def gp_factorize(data, hyp, sig2ofconst=0.01):
+    """Full-data stage of __fitGP1d for a batch (PCGPwM.py:810-846).
+
+    Returns device tensors Linv (nb,n,ldl), pw (nb,n), sig2 (nb,), logdet_half (nb,) and numpy info.
+    """
+    torch = _torch()
+    hyp_t = _f64(torch, np.atleast_2d(hyp) if not isinstance(hyp, torch.Tensor) else hyp)
+    nb = hyp_t.shape[0]
+    n, d = data.n, data.d
+    dev = hyp_t.device
+    ldl = (n + 7) // 8 * 8
+    Linv = torch.empty((nb, n, ldl), dtype=torch.float64, device=dev)
+    pw = torch.empty((nb, n), dtype=torch.float64, device=dev)
+    sig2 = torch.empty(nb, dtype=torch.float64, device=dev)
+    ldh = torch.empty(nb, dtype=torch.float64, device=dev)
+    info = torch.empty(nb, dtype=torch.int32, device=dev)
+    nbytes = lib.sb200_gp_factorize_workspace(nb, n)
+    ws = workspace(nbytes)
+    check(lib.sb200_gp_factorize(nb, n, d, _ptr(data.theta), data.stride_theta, _ptr(data.g), data.stride_g,
+                                 _ptr(data.gvar), data.stride_gvar, _ptr(hyp_t),
+                                 float(sig2ofconst), _ptr(Linv), ldl, n * ldl, _ptr(pw), _ptr(sig2), _ptr(ldh),
+                                 _ptr(info), _ptr(ws), ws.numel(), _stream(torch)), 'sb200_gp_factorize')
+    return Linv, pw, sig2, ldh, info.cpu().numpy()
+
+
+def gp_weights(Linv, fidx, g, sig2ofconst=0.01):
+    """pw (k,n), sig2 (k) for PC scores g (k,n) through the shared factors Linv[fidx[j]] (PCGPwM.py:823-846)."""
+    torch = _torch()
+    _need_cuda(Linv, fidx, g)
+    K, n = g.shape
+    ldl = Linv.shape[2]
+    pw = torch.empty((K, n), dtype=torch.float64, device=g.device)
+    sig2 = torch.empty(K, dtype=torch.float64, device=g.device)
+    ytmp = torch.empty((K, n), dtype=torch.float64, device=g.device)
+    check(lib.sb200_gp_weights(K, n, _ptr(Linv), ldl, n * ldl, _ptr(fidx), _ptr(g.contiguous()), float(sig2ofconst),
+                               _ptr(pw), _ptr(sig2), _ptr(ytmp), _stream(torch)), 'sb200_gp_weights')
+    return pw, sig2
+
+
+def gp_predict(state, thetanew, want_grad=False):
+    """PC-space prediction (PCGPwM.py:219-270) from a device state dict (see emulation module).
+
+    Returns device tensors predvecs, predvars (B,k) and, if want_grad, gradients (B,k,d).
+    """
+    torch = _torch()
+    tn = _f64(torch, thetanew)
+    B, d = tn.shape
+    K = state['pw'].shape[0]
+    nf, n, ldl = state['Linv'].shape
+    nu = state['hypcov'].shape[0]
+    dev = tn.device
+    pv = torch.empty((B, K), dtype=torch.float64, device=dev)
+    pvar = torch.empty((B, K), dtype=torch.float64, device=dev)
+    dpv = torch.empty((B, K, d), dtype=torch.float64, device=dev) if want_grad else None
+    dpvar = torch.empty((B, K, d), dtype=torch.float64, device=dev) if want_grad else None
+    nbytes = lib.sb200_gp_predict_workspace(K, nf, nu, n, d, B, int(want_grad))
+    ws = workspace(nbytes)
+    check(lib.sb200_gp_predict(K, nf, nu, n, d, B, _ptr(state['theta']), _ptr(tn), _ptr(state['hypcov']),
+                               _ptr(state['fu']), _ptr(state['fidx']), _ptr(state['nug']), _ptr(state['sig2']),
+                               _ptr(state['Linv']), ldl, n * ldl, _ptr(state['pw']), int(want_grad), _ptr(pv),
+                               _ptr(pvar), _ptr(dpv), _ptr(dpvar), _ptr(ws), ws.numel(), _stream(torch)),
+          'sb200_gp_predict')
+    return pv, pvar, dpv, dpvar
+
+
+def pc_backproject(phi, offset, extravar, pv, pvar, dpv=None, dpvar=None, want_covx=True):
+    """mean, var (m,B) [, covxhalf (m,B,k), mean_grad (m,B,d), covxhalf_grad (m,B,k,d)] (PCGPwM.py:273-327)."""
+    torch = _torch()
+    _need_cuda(phi, offset, extravar, pv, pvar)
+    m, K = phi.shape
+    B = pv.shape[0]
+    d = dpv.shape[2] if dpv is not None else 1
+    dev = pv.device
+    mean = torch.empty((m, B), dtype=torch.float64, device=dev)
+    var = torch.empty((m, B), dtype=torch.float64, device=dev)
+    cxh = torch.empty((m, B, K), dtype=torch.float64, device=dev) if want_covx else None
+    mg = torch.empty((m, B, d), dtype=torch.float64, device=dev) if dpv is not None else None
+    cg = torch.empty((m, B, K, d), dtype=torch.float64, device=dev) if (dpvar is not None and want_covx) else None
+    check(lib.sb200_pc_backproject(m, K, B, d, _ptr(phi), _ptr(offset), _ptr(extravar), _ptr(pv), _ptr(pvar),
+                                   _ptr(dpv), _ptr(dpvar), _ptr(mean), _ptr(var), _ptr(cxh), _ptr(mg), _ptr(cg),
+                                   _stream(torch)), 'sb200_pc_backproject')
+    return mean, var, cxh, mg, cg
+
+
+def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None):
+    """Batched directbayeswoodbury log-likelihood (+ gradient) (dbw.py:261-383).
+
+    consts: dict of device tensors phiT (k,m), resid0 (m), extravar (m), sinv (2,m), G (2,k,k).
+    Returns device tensors ll (B,), dll (B,d) or None, fired (int32 scalar tensor).
+    """
+    torch = _torch()
+    _need_cuda(pv, pvar, consts['phiT'])
+    B, K = pv.shape
+    m = consts['phiT'].shape[1]
+    want_grad = dpv is not None
+    d = dpv.shape[2] if want_grad else 1
+    dev = pv.device
+    ll = torch.empty(B, dtype=torch.float64, device=dev)
+    dll = torch.empty((B, d), dtype=torch.float64, device=dev) if want_grad else None
+    fired = torch.empty(1, dtype=torch.int32, device=dev)
+    check(lib.sb200_woodbury_loglik(B, K, m, d, _ptr(pv), _ptr(pvar), _ptr(dpv), _ptr(dpvar), _ptr(consts['phiT']),
+                                    _ptr(consts['resid0']), _ptr(consts['extravar']), _ptr(consts['sinv']),
+                                    _ptr(consts['G']), int(want_grad), _ptr(ll), _ptr(dll), _ptr(fired),
+                                    _stream(torch)), 'sb200_woodbury_loglik')
+    return ll, dll, fired
+
+
+# ----------------------------------------------------------------------------------------------
+# building blocks (exported by the C ABI for testing / reuse)
+def dgemm(A, B, C, a_kc, b_kc, M, N, K, alpha=1.0, beta=0.0, flags=0, tile=-1, batch=1, strides=(0, 0, 0),
+          lds=None):
+    torch = _torch()
+    _need_cuda(A, B, C)
+    lda, ldb, ldc = lds
+    check(lib.sb200_dgemm(int(a_kc), int(b_kc), M, N, K, float(alpha), _ptr(A), lda, strides[0], _ptr(B), ldb,
+                          strides[1], float(beta), _ptr(C), ldc, strides[2], batch, flags, tile, _stream(torch)),
+          'sb200_dgemm')
+
+
+def potrf_batched(A, n, mrows):
+    """A: (batch, mrows, lda) in place; returns (Linv with diagonal blocks only, info numpy)."""
+    torch = _torch()
+    _need_cuda(A)
+    batch, _, lda = A.shape
+    Linv = torch.empty((batch, n, lda), dtype=torch.float64, device=A.device)
+    info = torch.empty(batch, dtype=torch.int32, device=A.device)
+    check(lib.sb200_potrf_batched(batch, n, mrows, _ptr(A), lda, A.stride(0), _ptr(Linv), lda, n * lda, _ptr(info),
+                                  _stream(torch)), 'sb200_potrf_batched')
+    return Linv, info
+
+
+def trtri_batched(L, Linv, n):
+    torch = _torch()
+    batch = L.shape[0]
+    te = lib.sb200_trtri_tmp_elems(n)
+    tmp = torch.empty((batch, max(te, 1)), dtype=torch.float64, device=L.device)
+    check(lib.sb200_trtri_batched(batch, n, _ptr(L), L.shape[2], L.stride(0), _ptr(Linv), Linv.shape[2],
+                                  Linv.stride(0), _ptr(tmp), te, _stream(torch)), 'sb200_trtri_batched')
+
+
+def lauum_batched(Linv, n):
+    torch = _torch()
+    batch, _, ldl = Linv.shape
+    Cm = torch.zeros((batch, n, ldl), dtype=torch.float64, device=Linv.device)
+    check(lib.sb200_lauum_batched(batch, n, _ptr(Linv), ldl, Linv.stride(0), _ptr(Cm), ldl, Cm.stride(0),
+                                  _stream(torch)), 'sb200_lauum_batched')
+    return Cm

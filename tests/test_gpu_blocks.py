@@ -1,0 +1,159 @@
+"""GPU: the dense building blocks (DMMA GEMM, batched Cholesky / inverse) against numpy."""
+import numpy as np
+import pytest
+
+from gpu_util import rel, report, dev
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from surmise_b200 import ops as o
+    o._torch()
+    return o
+
+
+def _operand(rng, rows, cols, kc, ld_pad):
+    """Logical (rows x K) operand stored k-contiguous (rows, K) or row-contiguous (K, rows)."""
+    M = rng.normal(size=(rows, cols))
+    store = M if kc else M.T
+    ld = store.shape[1] + ld_pad
+    buf = np.zeros((store.shape[0], ld))
+    buf[:, :store.shape[1]] = store
+    return M, buf, ld
+
+
+@pytest.mark.parametrize('a_kc', [True, False])
+@pytest.mark.parametrize('b_kc', [True, False])
+@pytest.mark.parametrize('shape', [(128, 128, 64), (200, 77, 133), (33, 264, 95), (257, 64, 16), (5, 3, 1)])
+@pytest.mark.parametrize('tile', [0, 1])
+def test_dgemm_layouts(ops, a_kc, b_kc, shape, tile):
+    import torch
+    rng = np.random.default_rng(1)
+    M, N, K = shape
+    for pad in (0, 3):                      # pad=3 -> odd leading dimension -> 8-byte cp.async path
+        A, Abuf, lda = _operand(rng, M, K, a_kc, pad)
+        B, Bbuf, ldb = _operand(rng, N, K, b_kc, pad)
+        C0 = rng.normal(size=(M, N + pad))
+        Cd = dev(C0.copy())
+        ops.dgemm(dev(Abuf), dev(Bbuf), Cd, a_kc, b_kc, M, N, K, alpha=-0.7, beta=1.3, tile=tile,
+                  lds=(lda, ldb, N + pad))
+        torch.cuda.synchronize()
+        want = C0.copy()
+        want[:, :N] = -0.7 * A @ B.T + 1.3 * C0[:, :N]
+        err = rel(Cd.cpu().numpy(), want)
+        report('dgemm', akc=a_kc, bkc=b_kc, M=M, N=N, K=K, tile=tile, pad=pad, err=err)
+        assert err < 1e-13
+
+
+@pytest.mark.parametrize('flag,which', [(1, 'A_LOWER'), (2, 'A_UPPER'), (4, 'B_LOWER'), (8, 'B_UPPER'), (16, 'C_LOWER')])
+def test_dgemm_triangular_flags(ops, flag, which):
+    import torch
+    rng = np.random.default_rng(2)
+    n = 300
+    A = rng.normal(size=(n, n))
+    B = rng.normal(size=(n, n))
+    if which == 'A_LOWER':
+        A = np.tril(A)
+    if which == 'A_UPPER':
+        A = np.triu(A)
+    if which == 'B_LOWER':
+        B = np.tril(B)
+    if which == 'B_UPPER':
+        B = np.triu(B)
+    for a_kc in (True, False):
+        for b_kc in (True, False):
+            Cd = dev(np.zeros((n, n)))
+            ops.dgemm(dev(A if a_kc else A.T.copy()), dev(B if b_kc else B.T.copy()), Cd, a_kc, b_kc, n, n, n,
+                      flags=flag, lds=(n, n, n))
+            torch.cuda.synchronize()
+            got, want = Cd.cpu().numpy(), A @ B.T
+            if which == 'C_LOWER':
+                got, want = np.tril(got), np.tril(want)
+            err = rel(got, want)
+            report('dgemm_flag', flag=flag, akc=a_kc, bkc=b_kc, err=err)
+            assert err < 1e-13
+
+
+def test_dgemm_batched_strided(ops):
+    import torch
+    rng = np.random.default_rng(3)
+    nb, M, N, K = 5, 150, 140, 90
+    A = rng.normal(size=(nb, M, K))
+    B = rng.normal(size=(N, K))                       # shared operand: stride 0
+    Cd = dev(np.zeros((nb, M, N)))
+    ops.dgemm(dev(A), dev(B), Cd, True, True, M, N, K, batch=nb, strides=(M * K, 0, M * N), lds=(K, K, N))
+    torch.cuda.synchronize()
+    assert rel(Cd.cpu().numpy(), A @ B.T) < 1e-13
+
+
+def _spd(rng, n, cond_boost=1e-3):
+    X = rng.normal(size=(n, n + 8))
+    return X @ X.T / n + cond_boost * np.eye(n)
+
+
+@pytest.mark.parametrize('n,extra', [(40, 1), (64, 0), (65, 1), (130, 2), (200, 1), (515, 1), (1030, 1)])
+def test_potrf_trtri_lauum(ops, n, extra):
+    import torch
+    rng = np.random.default_rng(n)
+    nb = 3
+    lda = (n + 7) // 8 * 8
+    mats = [_spd(rng, n) for _ in range(nb)]
+    rhs = rng.normal(size=(nb, extra, n))
+    buf = np.zeros((nb, n + extra, lda))
+    for z in range(nb):
+        buf[z, :n, :n] = np.tril(mats[z]) + np.triu(np.full((n, n), 777.0), 1)   # garbage above the diagonal
+        buf[z, n:, :n] = rhs[z]
+    Ad = dev(buf)
+    Linv, info = ops.potrf_batched(Ad, n, n + extra)
+    ops.trtri_batched(Ad, Linv, n)
+    Rinv = ops.lauum_batched(Linv, n)
+    torch.cuda.synchronize()
+    assert np.all(info.cpu().numpy() == 0)
+    out = Ad.cpu().numpy()
+    Li = Linv.cpu().numpy()
+    Ri = Rinv.cpu().numpy()
+    for z in range(nb):
+        L = np.linalg.cholesky(mats[z])
+        e_l = rel(np.tril(out[z, :n, :n]), L)
+        assert np.all(np.triu(out[z, :n, :n], 1) == 777.0)          # strict upper triangle never touched
+        e_y = rel(out[z, n:, :n], np.linalg.solve(L, rhs[z].T).T) if extra else 0.0
+        Linv_ref = np.linalg.inv(L)
+        e_i = rel(Li[z, :, :n], Linv_ref)
+        assert np.all(np.triu(Li[z, :, :n], 1) == 0.0)
+        e_r = rel(np.tril(Ri[z, :, :n]), np.tril(Linv_ref.T @ Linv_ref))
+        report('chol', n=n, z=z, L=e_l, y=e_y, Linv=e_i, Rinv=e_r, cond=np.linalg.cond(mats[z]))
+        assert e_l < 1e-11 and e_y < 1e-10 and e_i < 1e-9 and e_r < 1e-8
+
+
+def test_potrf_reports_indefinite(ops):
+    import torch
+    rng = np.random.default_rng(5)
+    n = 150
+    A = _spd(rng, n)
+    A[100, 100] = -5.0
+    buf = np.zeros((1, n, 152))
+    buf[0, :, :n] = np.tril(A)
+    _, info = ops.potrf_batched(dev(buf), n, n)
+    torch.cuda.synchronize()
+    assert int(info.cpu().numpy()[0]) == 101
+
+
+def test_large_factorisation_properties(ops):
+    """Size-independent checks at a BASELINE-size order: L L' = A, Linv L = I."""
+    import torch
+    n = 2000
+    g = torch.Generator(device='cuda').manual_seed(0)
+    X = torch.randn((n, n + 16), dtype=torch.float64, device='cuda', generator=g)
+    A = X @ X.T / n + 1e-3 * torch.eye(n, dtype=torch.float64, device='cuda')
+    buf = torch.tril(A).reshape(1, n, n).clone()
+    Linv, info = ops.potrf_batched(buf, n, n)
+    ops.trtri_batched(buf, Linv, n)
+    torch.cuda.synchronize()
+    assert int(info.cpu()[0]) == 0
+    L = torch.tril(buf[0])
+    e1 = float(((L @ L.T - A).abs().max() / A.abs().max()).cpu())
+    e2 = float(((Linv[0] @ L - torch.eye(n, dtype=torch.float64, device='cuda')).abs().max()).cpu())
+    report('chol_large', n=n, LLt=e1, LinvL=e2)
+    assert e1 < 1e-13 and e2 < 1e-9

@@ -1,0 +1,255 @@
+"""GPU parity tests proper: the CUDA hot path (through the C ABI) against the reference's golden
+vectors (tests/golden/, generated from bandframework/surmise itself) and against the numpy oracle
+on seeded inputs.  Tolerances: BASELINE.json north_star -- NLL/gradient 1e-9, predictive mean /
+variance 1e-6, log-likelihood per theta 1e-9 (relative), widened only where cond(R) * eps exceeds
+the bar (the reference's own eigh-vs-Cholesky agreement is bounded by that product)."""
+import numpy as np
+import pytest
+
+from gpu_util import rel, report, dev
+from oracle import pcgpwm_oracle as po
+from oracle import woodbury_oracle as wo
+
+pytestmark = pytest.mark.gpu
+EPS = 2.2e-16
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from surmise_b200 import ops as o
+    o._torch()
+    return o
+
+
+# ---------------------------------------------------------------------------------- covmat (K1-K3)
+@pytest.mark.parametrize('tag', ['a', 'b', 'c'])
+def test_covmat_golden(ops, golden, tag):
+    import surmise_b200
+    g = golden('covmat')
+    x1, x2, gam = g[f'{tag}_x1'], g[f'{tag}_x2'], g[f'{tag}_gam']
+    R = surmise_b200.covmat(x1, x2, gam)
+    _, dRh = surmise_b200.covmat(x1, x2, gam, return_gradhyp=True)
+    _, dRx = surmise_b200.covmat(x1, x2, gam, return_gradx1=True)
+    e = (rel(R, g[f'{tag}_R']), rel(dRh, g[f'{tag}_dRhyp']), rel(dRx, g[f'{tag}_dRx1']))
+    report('covmat_golden_' + tag, R=e[0], dRhyp=e[1], dRx1=e[2])
+    assert max(e) < 1e-13
+    assert dRh.shape == g[f'{tag}_dRhyp'].shape and dRx.shape == g[f'{tag}_dRx1'].shape
+
+
+def test_covmat_1d_and_ragged(ops, golden):
+    import surmise_b200
+    g = golden('covmat')
+    assert rel(surmise_b200.covmat(g['e_x1'], g['e_x2'], g['e_gam']), g['e_R']) < 1e-13
+    rng = np.random.default_rng(4)
+    for n1, n2, d in [(1, 1, 1), (33, 65, 16), (257, 31, 5), (1000, 999, 10)]:
+        x1, x2, gam = rng.uniform(size=(n1, d)), rng.uniform(size=(n2, d)), rng.normal(size=d + 1)
+        want, dwant = po.matern_covmat(x1, x2, gam, 'hyp')
+        got, dgot = surmise_b200.covmat(x1, x2, gam, return_gradhyp=True)
+        assert rel(got, want) < 1e-13 and rel(dgot, dwant) < 1e-13
+    with pytest.raises(Exception):
+        surmise_b200.covmat(rng.uniform(size=(4, 17)), rng.uniform(size=(4, 17)), np.zeros(18))   # d > 16
+
+
+# ---------------------------------------------------------------------------------- NLL + gradient (K4, K5)
+@pytest.mark.parametrize('tag', ['a', 'b', 'c'])
+def test_nll_grad_golden(ops, golden, tag):
+    g = golden('nll')
+    data = ops.GPData(g[f'{tag}_theta'], g[f'{tag}_g'], g[f'{tag}_gvar'])
+    hyps = g[f'{tag}_hyps']
+    n = g[f'{tag}_g'].shape[0]
+    nll, grad, info = ops.gp_nll_grad(data, hyps, g[f'{tag}_mean'], g[f'{tag}_std'], 0.01, True)
+    nll0, _, info0 = ops.gp_nll_grad(data, hyps, g[f'{tag}_mean'], g[f'{tag}_std'], 0.01, False)
+    assert np.all(info == 0) and np.all(info0 == 0)
+    assert np.array_equal(nll, nll0)                       # value-only path is the same arithmetic
+    for i in range(hyps.shape[0]):
+        tol = max(1e-9, 20 * EPS * g[f'{tag}_cond'][i])
+        e_v = abs(nll[i] - g[f'{tag}_nll'][i]) / (abs(g[f'{tag}_nll'][i]) + n)
+        e_g = rel(grad[i], g[f'{tag}_grad'][i])
+        report('nll_golden_' + tag, i=i, nll=e_v, grad=e_g, cond=g[f'{tag}_cond'][i])
+        assert e_v < tol and e_g < 10 * tol
+
+
+@pytest.mark.parametrize('n,d,nb', [(160, 8, 7), (200, 10, 3), (61, 3, 4), (700, 8, 2)])
+def test_nll_grad_vs_oracle_batched(ops, n, d, nb):
+    rng = np.random.default_rng(n + d)
+    theta = rng.uniform(size=(n, d))
+    g = np.sin(theta @ rng.normal(size=d)) + 0.05 * rng.normal(size=n)
+    gvar = rng.uniform(size=n) * (rng.uniform(size=n) < 0.2) * 0.3
+    mean, LB, UB, std = po.hyper_regulariser(theta, -10, -20)
+    hyps = np.array([mean] + [LB + rng.uniform(0.3, 0.7, size=mean.shape) * (UB - LB) for _ in range(nb - 1)])
+    hyps[:, -1] = np.maximum(hyps[:, -1], -12)             # keep cond(R) where 1e-9 is attainable
+    info = {'theta': theta, 'g': g, 'gvar': gvar, 'sig2ofconst': 0.01, 'hypregmean': mean, 'hypregstd': std}
+    nll, grad, code = ops.gp_nll_grad(ops.GPData(theta, g, gvar), hyps, mean, std, 0.01, True)
+    assert np.all(code == 0)
+    for i in range(nb):
+        v = po.negloglik_eigh(hyps[i], info)
+        dv = po.negloglikgrad_eigh(hyps[i], info)
+        cond = np.linalg.cond(po.assemble_gp_matrix(theta, hyps[i], gvar)[0])
+        tol = max(1e-9, 20 * EPS * cond)
+        e_v, e_g = abs(nll[i] - v) / (abs(v) + n), rel(grad[i], dv)
+        report('nll_oracle', n=n, d=d, i=i, nll=e_v, grad=e_g, cond=cond)
+        assert e_v < tol and e_g < 10 * tol
+
+
+def test_nll_per_problem_data_and_breakdown(ops):
+    """Different (g, gvar) per problem; an indefinite R must come back as info > 0, not a crash."""
+    rng = np.random.default_rng(9)
+    n, d, nb = 90, 4, 3
+    theta = rng.uniform(size=(n, d))
+    G = rng.normal(size=(nb, n))
+    GV = np.abs(rng.normal(size=(nb, n))) * 0.1
+    GV[2, 5] = -50.0                                       # forces a negative pivot
+    mean, LB, UB, std = po.hyper_regulariser(theta, -10, -20)
+    hyps = np.tile(mean, (nb, 1))
+    nll, grad, code = ops.gp_nll_grad(ops.GPData(theta, G, GV), hyps, mean, std, 0.01, True)
+    assert code[0] == 0 and code[1] == 0 and code[2] > 0
+    for i in range(2):
+        info = {'theta': theta, 'g': G[i], 'gvar': GV[i], 'sig2ofconst': 0.01, 'hypregmean': mean, 'hypregstd': std}
+        assert abs(nll[i] - po.negloglik_eigh(hyps[i], info)) < 1e-9 * n
+        assert rel(grad[i], po.negloglikgrad_eigh(hyps[i], info)) < 1e-8
+
+
+# ---------------------------------------------------------------------------------- factorise + predict (K6-K9)
+def _load_state(golden_npz):
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    g = golden_npz
+    gv = po.damp_gvar(g['st_unscaled_pcstdvar'], 10, 0.3)
+    spc = {'offset': g['st_offset'], 'scale': g['st_scale'], 'extravar': g['st_extravar']}
+    emulist, state = M.import_state(g['st_theta'], g['st_pc'], gv, g['st_hyp'], g['st_hypind'], g['st_pcti'], spc)
+    fitinfo = {'_b200': state, 'emulist': emulist, 'x': g['in_x'], 'theta': g['st_theta'], 'pcti': g['st_pcti'],
+               'standardpcinfo': spc}
+    return M, fitinfo
+
+
+@pytest.mark.parametrize('tag', ['c1', 'misspd', 'trig', 'd1'])
+def test_factorise_and_predict_golden(ops, golden, tag):
+    g = golden('emu_' + tag)
+    M, fitinfo = _load_state(g)
+    cond = float(g['st_condR'].max())
+    tol = max(1e-9, 100 * EPS * cond)
+    pw = np.array([e['pw'] for e in fitinfo['emulist']]).T
+    sig2 = np.array([e['sig2'] for e in fitinfo['emulist']])
+    e_pw, e_s2 = rel(pw, g['st_pw']), rel(sig2, g['st_sig2'])
+    pred = {}
+    M.predict(pred, fitinfo, g['in_x'], g['thetanew'], return_grad=True)
+    errs = dict(pw=e_pw, sig2=e_s2, predvecs=rel(pred['predvecs'], g['predvecs']),
+                predvars=float(np.max(np.abs(pred['predvars'] - g['predvars']) / g['predvars'])),
+                dpv=rel(pred['predvecs_gradtheta'], g['predvecs_grad']),
+                dpvar=rel(pred['predvars_gradtheta'], g['predvars_grad']),
+                mean=rel(pred['mean'], g['mean']), var=rel(pred['var'], g['var']),
+                dmean=rel(pred['mean_gradtheta'], g['mean_grad']),
+                cxh=rel(pred['covxhalf'][:, :2, :], g['covxhalf_sample']),
+                dcxh=rel(pred['covxhalf_gradtheta'][:, :2, :, :], g['covxhalf_grad_sample']))
+    report('predict_golden_' + tag, cond=cond, **errs)
+    assert errs['sig2'] < tol and errs['pw'] < 100 * tol
+    # BASELINE bar: fitted predictive mean / variance within 1e-6 relative
+    assert errs['mean'] < max(1e-6, tol) and errs['var'] < max(1e-6, 10 * tol)
+    assert errs['predvecs'] < 10 * tol and errs['predvars'] < 100 * tol
+    assert errs['dpv'] < 100 * tol and errs['dpvar'] < 100 * tol and errs['dmean'] < 100 * tol
+    assert errs['cxh'] < 100 * tol and errs['dcxh'] < 100 * tol
+    assert pred['mean'].shape == g['mean'].shape and pred['covxhalf'].shape[2] == g['st_hyp'].shape[0]
+    # no-gradient call gives the same mean/variance
+    pred2 = {}
+    M.predict(pred2, fitinfo, g['in_x'], g['thetanew'])
+    assert rel(pred2['mean'], pred['mean']) < 1e-12 and rel(pred2['var'], pred['var']) < 1e-12
+    # at the design points the variance is a cancellation: looser, reported
+    pd = {}
+    M.predict(pd, fitinfo, g['in_x'], g['st_theta'][:8])
+    report('predict_design_' + tag, predvecs=rel(pd['predvecs'], g['design_predvecs']),
+           predvars_abs=float(np.max(np.abs(pd['predvars'] - g['design_predvars']))))
+    assert rel(pd['predvecs'], g['design_predvecs']) < max(1e-6, 100 * tol)
+
+
+def test_predict_row_subset_and_edge_shapes(ops, golden):
+    g = golden('emu_c1')
+    M, fitinfo = _load_state(g)
+    x = g['in_x']
+    rows = np.array([7, 3, 20])
+    xs = np.vstack([x[rows], [[12345.0]]])                  # last row matches nothing -> NaN (PCGPwM.py:273-280)
+    pred = {}
+    M.predict(pred, fitinfo, xs, g['thetanew'][:5])
+    assert pred['mean'].shape == (4, 5)
+    assert np.all(np.isnan(pred['mean'][3])) and np.all(np.isfinite(pred['mean'][:3]))
+    assert rel(pred['mean'][:3], g['mean'][rows][:, :5]) < 1e-6
+    one = {}
+    M.predict(one, fitinfo, x, g['thetanew'][0], return_grad=True)      # 1-D theta (B = 1)
+    assert one['mean'].shape == (x.shape[0], 1) and one['covxhalf_gradtheta'].shape[1] == 1
+    assert rel(one['mean'][:, 0], g['mean'][:, 0]) < 1e-6
+
+
+# ---------------------------------------------------------------------------------- Woodbury log-lik (K10, K11)
+class _Emu:
+    """Just enough of surmise's emulator object for the calibration plugin (._info, .predict)."""
+
+    def __init__(self, method, fitinfo):
+        self.method, self._info = method, fitinfo
+
+
+@pytest.mark.parametrize('tag', ['c1', 'misspd', 'trig', 'd1'])
+def test_woodbury_loglik_golden(ops, golden, tag):
+    from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
+    g = golden('emu_' + tag)
+    M, fitinfo = _load_state(g)
+    emu = _Emu(M, fitinfo)
+    cal = {'yvar': g['yvar']}
+    ll = C.loglik(cal, emu, g['thetanew'], g['y'], g['in_x'])
+    ll2, dll = C.loglik_grad(cal, emu, g['thetanew'], g['y'], g['in_x'])
+    _, _, fired = C.loglik_device(cal, emu, g['thetanew'], g['y'], g['in_x'])
+    cond = float(g['st_condR'].max())
+    tol = max(1e-9, 100 * EPS * cond)
+    e_l = float(np.max(np.abs(ll - g['loglik']) / np.abs(g['loglik'])))
+    e_d = rel(dll, g['dloglik'])
+    report('loglik_golden_' + tag, ll=e_l, dll=e_d, fired=int(fired.cpu()[0]), cond=cond)
+    assert bool(int(fired.cpu()[0])) == bool(g['fired'])
+    assert ll.shape == g['loglik'].shape and dll.shape == g['dloglik'].shape
+    assert np.allclose(ll, ll2, rtol=1e-12, atol=0)
+    assert e_l < 10 * tol and e_d < 100 * tol
+
+
+def test_woodbury_kernel_isolated(ops, golden):
+    """Feed the reference's own PC-space predictions to the kernel: 1e-9 per theta, no GP error."""
+    for tag in ['c1', 'trig', 'd1']:
+        g = golden('emu_' + tag)
+        phi = g['st_pcti'] * g['st_scale'][:, None]
+        yv = g['yvar']
+        ev = g['st_extravar']
+        sinv = np.stack([1 / yv, 1 / (yv + np.abs(ev))])
+        G = np.stack([phi.T @ (phi * s[:, None]) for s in sinv])
+        consts = {'phiT': dev(phi.T.copy()), 'resid0': dev(g['y'] - g['st_offset']), 'extravar': dev(ev),
+                  'sinv': dev(sinv), 'G': dev(G)}
+        ll, dll, fired = ops.woodbury_loglik(consts, dev(g['predvecs']), dev(g['predvars']),
+                                             dev(g['predvecs_grad']), dev(g['predvars_grad']))
+        e_l = float(np.max(np.abs(ll.cpu().numpy()[:, None] - g['loglik']) / np.abs(g['loglik'])))
+        e_d = rel(dll.cpu().numpy(), g['dloglik'])
+        report('woodbury_isolated_' + tag, ll=e_l, dll=e_d)
+        assert bool(int(fired.cpu()[0])) == bool(g['fired'])
+        assert e_l < 1e-9 and e_d < 1e-8
+
+
+def test_logpost_closure_contract(ops, golden):
+    """Shapes / -inf handling of the closure handed to samplers (dbw.py:100-129)."""
+    from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
+    g = golden('emu_c1')
+    M, fitinfo = _load_state(g)
+    emu = _Emu(M, fitinfo)
+
+    class prior:
+        @staticmethod
+        def lpdf(theta):
+            inside = np.all((theta >= 0) & (theta <= 1), axis=1)
+            return np.where(inside, 0.0, -np.inf).reshape(-1, 1)
+
+        @staticmethod
+        def rnd(n):
+            return np.random.default_rng(0).uniform(size=(n, 3))
+    cal = {'yvar': g['yvar'], 'thetaprior': prior}
+    logpost, draw = C.make_logpost(cal, emu, g['in_x'], g['y'])
+    th = g['thetanew'].copy()
+    th[1, 0] = 1.5                                          # outside the prior support
+    lp, dlp = logpost(th)
+    assert lp.shape == (th.shape[0], 1) and dlp.shape == th.shape
+    assert np.isneginf(lp[1, 0]) and np.all(np.isfinite(np.delete(lp[:, 0], 1)))
+    lp2 = logpost(th, return_grad=False)
+    assert np.allclose(np.delete(lp2[:, 0], 1), np.delete(lp[:, 0], 1), rtol=1e-12)
+    assert np.allclose(np.delete(lp[:, 0], 1), np.delete(g['loglik'][:, 0], 1), rtol=1e-7)
+    assert draw(10).shape == (10, 3)
