@@ -9,12 +9,26 @@ OUT = os.path.join(ROOT, 'surmise_b200', 'lib', 'libsurmise_b200.so')
 SOURCES = ['capi.cu', 'dgemm.cu', 'chol.cu', 'covmat.cu', 'gp.cu', 'woodbury.cu']
 
 
+STAMP = OUT + '.srchash'
+
+
+def source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(ROOT, 'include', 'surmise_b200.h')]
+    for p in deps:
+        h.update(os.path.basename(p).encode())
+        with open(p, 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(OUT):
+    """Content hash, not mtime: the snapshot shipped to the GPU box does not keep timestamps."""
+    if not (os.path.exists(OUT) and os.path.exists(STAMP)):
         return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, 'include', 'surmise_b200.h')]
-    return any(os.path.getmtime(p) > t for p in deps)
+    with open(STAMP) as fh:
+        return fh.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -28,6 +42,8 @@ def build(force=False, verbose=False):
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')
     subprocess.check_call(cmd)
+    with open(STAMP, 'w') as fh:
+        fh.write(source_hash())
     return OUT
 
 

@@ -13,6 +13,8 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    import build as _build          # keep libsurmise_b200.so in step with csrc/ (content hash; nvcc cross-compiles)
+    _build.build()
 
 
 @pytest.fixture(scope='session')
