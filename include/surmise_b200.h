@@ -28,6 +28,13 @@ extern "C" {
 int sb200_version(void);
 const char* sb200_last_error(void);
 
+/* Instrumentation used by bench.py: number of kernels this library has launched in the process so far, and an
+ * optional per-launch CUDA-event timing of the DMMA GEMM (enable, run, collect -> launches, summed ms, summed
+ * algorithmic flop = 2 M N K with exact triangular ranges). */
+long sb200_launch_count(void);
+void sb200_gemm_profile_enable(int on);
+int sb200_gemm_profile_collect(double* total_ms, double* total_flops);
+
 /* Replaces surmise.emulationsupport.matern_covmat.covmat (emulationsupport/matern_covmat.pyx:27-64,
  * map4 at :13-24).  R[i][j] (n1 x n2, leading dimension ldr) is the separable Matern-3/2 correlation
  * between x1[i] and x2[j] (both (.,d) contiguous) for gammav (d+1).

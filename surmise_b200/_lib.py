@@ -25,6 +25,9 @@ _z = C.c_size_t
 SIGNATURES = {
     'sb200_version': (_i, []),
     'sb200_last_error': (C.c_char_p, []),
+    'sb200_launch_count': (_l, []),
+    'sb200_gemm_profile_enable': (None, [_i]),
+    'sb200_gemm_profile_collect': (_i, [_p, _p]),
     'sb200_matern_covmat': (_i, [_p, _i, _p, _i, _i, _p, _p, _l, _p, _i, _p]),
     'sb200_gp_nll_grad_workspace': (_z, [_i, _i, _i, _i]),
     'sb200_gp_nll_grad': (_i, [_i, _i, _i, _p, _l, _p, _l, _p, _l, _p, _p, _p, _d, _i, _p, _p, _p, _p, _z, _p]),

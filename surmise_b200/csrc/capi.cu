@@ -4,7 +4,10 @@
 #include "covmat.cuh"
 #include "dgemm.cuh"
 #include "gp.cuh"
+#include <atomic>
 #include <cstdarg>
+#include <mutex>
+#include <vector>
 
 namespace sb {
 static thread_local char g_err[512] = "";
@@ -14,6 +17,19 @@ void set_last_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct GemmSample { cudaEvent_t a, b; double flops; };
+static std::mutex g_prof_mu;
+static std::vector<GemmSample> g_prof;
+static std::atomic<bool> g_prof_on{false};
+bool gemm_profile_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+void gemm_profile_add(cudaEvent_t a, cudaEvent_t b, double flops) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(GemmSample{a, b, flops});
+}
 }  // namespace sb
 
 using namespace sb;
@@ -22,6 +38,32 @@ using namespace sb;
 extern "C" {
 
 int sb200_version(void) { return 100; }
+
+long sb200_launch_count(void) { return sb::g_launches.load(); }
+
+void sb200_gemm_profile_enable(int on) { sb::g_prof_on.store(on != 0); }
+
+// Synchronises the recorded events, returns the number of DMMA GEMM launches booked since the last call and
+// their summed device time (ms) and algorithmic flop; clears the record.
+int sb200_gemm_profile_collect(double* total_ms, double* total_flops) {
+    std::lock_guard<std::mutex> lk(sb::g_prof_mu);
+    double ms = 0.0, fl = 0.0;
+    int n = 0;
+    for (auto& smp : sb::g_prof) {
+        float t = 0.f;
+        if (cudaEventSynchronize(smp.b) == cudaSuccess && cudaEventElapsedTime(&t, smp.a, smp.b) == cudaSuccess) {
+            ms += t;
+            fl += smp.flops;
+            n++;
+        }
+        cudaEventDestroy(smp.a);
+        cudaEventDestroy(smp.b);
+    }
+    sb::g_prof.clear();
+    if (total_ms) *total_ms = ms;
+    if (total_flops) *total_flops = fl;
+    return n;
+}
 const char* sb200_last_error(void) { return sb::g_err; }
 
 int sb200_matern_covmat(const double* x1, int n1, const double* x2, int n2, int d, const double* gammav,

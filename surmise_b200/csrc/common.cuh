@@ -13,6 +13,12 @@ namespace sb {
 
 // ---- error plumbing: every C-ABI entry point returns 0, <0 (bad argument) or >0 (cudaError_t) ----
 void set_last_error(const char* fmt, ...);
+void count_launch();
+
+// optional per-launch timing of the DMMA GEMM (bench.py's roofline leg): when enabled, launch_dgemm brackets
+// each launch with CUDA events on its stream and books the launch's algorithmic flop count
+bool gemm_profile_enabled();
+void gemm_profile_add(cudaEvent_t start, cudaEvent_t stop, double flops);
 
 #define SB_CHECK_ARG(cond, ...)                         \
     do {                                                \
@@ -32,7 +38,12 @@ void set_last_error(const char* fmt, ...);
         }                                                                               \
     } while (0)
 
-#define SB_LAUNCH_CHECK() SB_CUDA(cudaGetLastError())
+// every kernel launch in the library is followed by this: counts launches (sb200_launch_count)
+#define SB_LAUNCH_CHECK()              \
+    do {                               \
+        sb::count_launch();            \
+        SB_CUDA(cudaGetLastError());   \
+    } while (0)
 
 #define SB_TRY(expr)            \
     do {                        \

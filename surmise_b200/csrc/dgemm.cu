@@ -8,6 +8,9 @@
 //   row-contiguous operand: [k][row + pad 4] -> (4t + g) mod 16 distinct per half-warp
 // Algorithmic work: 2*M*N*Keff flop where Keff is the (possibly triangular) k-range per tile.
 #include "dgemm.cuh"
+#include <algorithm>
+using std::min;
+using std::max;
 
 namespace sb {
 namespace {
@@ -199,6 +202,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
     }
 }
 
+// 2*M*N*K with the exact element-wise triangular k-ranges (tile independent): the algorithmic flop of one problem
+double algorithmic_flops(const GemmArgs& g, int, int) {
+    double fl = 0.0;
+    for (int m = 0; m < g.M; m++) {
+        // count (n, k) pairs with nonzero products for this row
+        // k-range from A: [alo, ahi); from B (depends on n): handled per case below
+        long alo = (g.flags & GEMM_A_UPPER) ? m : 0;
+        long ahi = (g.flags & GEMM_A_LOWER) ? (long)min(g.K, m + 1) : g.K;
+        long nmax = (g.flags & GEMM_C_LOWER) ? (long)min(g.N, m + 1) : g.N;
+        if (ahi <= alo || nmax <= 0) continue;
+        if (!(g.flags & (GEMM_B_LOWER | GEMM_B_UPPER))) {
+            fl += 2.0 * (double)(ahi - alo) * (double)nmax;
+        } else {
+            for (long n = 0; n < nmax; n++) {
+                long lo = alo, hi = ahi;
+                if (g.flags & GEMM_B_UPPER) lo = lo > n ? lo : n;
+                if (g.flags & GEMM_B_LOWER) hi = hi < n + 1 ? hi : n + 1;
+                if (hi > lo) fl += 2.0 * (double)(hi - lo);
+            }
+        }
+    }
+    return fl;
+}
+
 template <int BM, int BN, int WM, int WN, bool AKC, bool BKC>
 int launch_one(const GemmArgs& g, int batch, cudaStream_t stream) {
     constexpr size_t smem = (size_t)STAGES * (BK * (BM + 4) + BK * (BN + 4)) * sizeof(double);
@@ -211,6 +238,17 @@ int launch_one(const GemmArgs& g, int batch, cudaStream_t stream) {
         configured[dev] = true;
     }
     dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), batch);
+    if (gemm_profile_enabled()) {
+        cudaEvent_t e0, e1;
+        SB_CUDA(cudaEventCreate(&e0));
+        SB_CUDA(cudaEventCreate(&e1));
+        SB_CUDA(cudaEventRecord(e0, stream));
+        kern<<<grid, NTHREADS, smem, stream>>>(g);
+        SB_CUDA(cudaEventRecord(e1, stream));
+        gemm_profile_add(e0, e1, algorithmic_flops(g, BM, BN) * batch);
+        SB_LAUNCH_CHECK();
+        return 0;
+    }
     kern<<<grid, NTHREADS, smem, stream>>>(g);
     SB_LAUNCH_CHECK();
     return 0;

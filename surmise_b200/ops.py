@@ -112,10 +112,11 @@ class GPData:
             self.nb_fixed = self.g.shape[0]
 
 
-def gp_nll_grad(data, hyp, regmean, regstd, sig2ofconst=0.01, want_grad=True):
+def gp_nll_grad(data, hyp, regmean, regstd, sig2ofconst=0.01, want_grad=True, return_device=False):
     """Batched PCGPwM.__negloglik (+ __negloglikgrad) (PCGPwM.py:850-907).
 
-    hyp: (nb, d+3) numpy or tensor.  Returns numpy (nll (nb,), grad (nb,p) or None, info (nb,)).
+    hyp: (nb, d+3) numpy or tensor.  Returns numpy (nll (nb,), grad (nb,p) or None, info (nb,)), or with
+    return_device=True one device tensor (nb, p+2) = [nll | grad | info] without synchronising.
     """
     torch = _torch()
     hyp_t = _f64(torch, np.atleast_2d(hyp) if not isinstance(hyp, torch.Tensor) else hyp)
@@ -136,6 +137,9 @@ def gp_nll_grad(data, hyp, regmean, regstd, sig2ofconst=0.01, want_grad=True):
                                 _ptr(data.gvar), data.stride_gvar, _ptr(hyp_t),
                                 _ptr(rm), _ptr(rs), float(sig2ofconst), int(want_grad), _ptr(nll), _ptr(grad),
                                 _ptr(info), _ptr(ws), ws.numel(), _stream(torch)), 'sb200_gp_nll_grad')
+    if return_device:
+        cols = [nll[:, None]] + ([grad] if want_grad else []) + [info.to(torch.float64)[:, None]]
+        return torch.cat(cols, dim=1)
     if want_grad:
         packed = torch.cat([nll[:, None], grad, info.to(torch.float64)[:, None]], dim=1).cpu().numpy()
         return packed[:, 0], packed[:, 1:1 + p], packed[:, -1].astype(np.int64)
