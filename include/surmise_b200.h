@@ -94,18 +94,23 @@ int sb200_pc_backproject(int m, int k, int B, int d, const double* phi, const do
  * 309-383) for a whole batch of theta in one launch, in principal-component space.
  *   phiT (k,m); resid0 (m) = y - offset; extravar (m); sinv (2,m) = 1/yvar, 1/(yvar+|extravar|);
  *   G (2,k,k) = Phi' diag(sinv[v]) Phi.  Outputs ll (B), dll (B,d; if want_grad) and *fired (device int):
- *   1 when the batch-wide unmodelled-variance test (dbw.py:277-284) selected the second variant. */
+ *   1 when the batch-wide unmodelled-variance test (dbw.py:277-284) selected the second variant.
+ *   variant < 0: run that test over this batch; 0 / 1: use the given variant (a theta population sharded over
+ *   several GPUs evaluates sb200_woodbury_trigger per shard, OR-reduces the flags and passes the result). */
 int sb200_woodbury_loglik(int B, int k, int m, int d, const double* predvecs, const double* predvars,
                           const double* predvecs_grad, const double* predvars_grad, const double* phiT,
                           const double* resid0, const double* extravar, const double* sinv, const double* G,
-                          int want_grad, double* ll, double* dll, int* fired, void* stream);
+                          int want_grad, int variant, double* ll, double* dll, int* fired, void* stream);
+int sb200_woodbury_trigger(int B, int k, int m, const double* predvars, const double* phiT, const double* extravar,
+                           int* fired, void* stream);
 
 /* Building blocks, exported for testing and reuse (no reference counterpart: the reference calls LAPACK).
  * sb200_dgemm: C[m][n] = alpha sum_k Aop[m][k] Bop[n][k] + beta C[m][n] on the FP64 tensor cores (DMMA);
  *   a_kc != 0: Aop[m][k] = A[m*lda+k] else A[k*lda+m]; same for B.  flags: 1 A lower, 2 A upper,
  *   4 B lower, 8 B upper (triangular operands must hold zeros in the empty triangle), 16 lower-C only.
  * sb200_potrf_batched: in-place lower Cholesky of `batch` matrices (rows n..mrows-1 are solved as
- *   right-hand sides X <- X L^-T); Linv receives the inverted diagonal blocks and is zeroed elsewhere.
+ *   right-hand sides X <- X L^-T); Linv receives the inverted diagonal blocks and is zeroed elsewhere;
+ *   `info` must hold 2*batch ints (first half = result, second half = scratch).
  * sb200_trtri_batched: completes Linv = L^-1 from the output of sb200_potrf_batched.
  * sb200_lauum_batched: lower triangle of C = Linv' Linv. */
 int sb200_dgemm(int a_kc, int b_kc, int M, int N, int K, double alpha, const double* A, long lda, long stride_a,

@@ -76,18 +76,62 @@ def loglik_device(fitinfo, emu, theta, y, x, return_grad=False, chunk=4096):
     return ops.woodbury_loglik(consts, pv, pvar, dpv, dpvar)
 
 
+def _packed(fitinfo, emu, theta, y, x, return_grad):
+    """numpy (B, 1) or (B, 1+d) from one fused device evaluation and one D2H copy."""
+    ops = _ops()
+    torch = ops._torch()
+    ll, dll, _ = loglik_device(fitinfo, emu, theta, y, x, return_grad=return_grad)
+    if return_grad:
+        return torch.cat([ll[:, None], dll], dim=1).cpu().numpy()
+    return ll.cpu().numpy().reshape(-1, 1)
+
+
+def _evaluate(fitinfo, emu, theta, y, x, return_grad):
+    """Optionally shard the theta population over the torch.distributed ranks (fitinfo['shard_theta']).
+
+    Every rank must then call with the same theta (samplers run replicated with identical seeds); each rank
+    evaluates its slice, the batch-wide unmodelled-variance flag (dbw.py:277-284) is OR-reduced so that it is
+    still decided over the whole population, and the (B, 1+d) table is all-gathered (NCCL).
+    """
+    if fitinfo.get('shard_theta'):
+        from .. import _dist
+        comm = _dist.Comm()
+        if comm.world > 1:
+            return _evaluate_sharded(fitinfo, emu, np.atleast_2d(theta), y, x, return_grad, comm)
+    return _packed(fitinfo, emu, theta, y, x, return_grad)
+
+
+def _evaluate_sharded(fitinfo, emu, theta, y, x, return_grad, comm):
+    from .. import _dist
+    ops = _ops()
+    torch = ops._torch()
+    consts = woodbury_constants(fitinfo, emu, x, y)
+    info = _device_state(emu)
+    sizes, starts = _dist.block_partition(theta.shape[0], comm.world)
+    lo, hi = int(starts[comm.rank]), int(starts[comm.rank + 1])
+    dev = consts['phiT'].device
+    fired = torch.zeros(1, dtype=torch.int32, device=dev)
+    pred = None
+    if hi > lo:
+        pred = _emu_method.predict_pcspace(info, theta[lo:hi], return_grad)
+        fired = ops.woodbury_trigger(consts, pred[1])
+    comm.dist.all_reduce(fired, op=comm.dist.ReduceOp.MAX)
+    width = 1 + (theta.shape[1] if return_grad else 0)
+    local = np.zeros((0, width))
+    if pred is not None:
+        ll, dll, _ = ops.woodbury_loglik(consts, *pred, variant=int(fired.item()))
+        local = (torch.cat([ll[:, None], dll], dim=1) if return_grad else ll[:, None]).cpu().numpy()
+    return comm.allgather_rows(local, sizes)
+
+
 def loglik(fitinfo, emu, theta, y, x):
     """(B,1) log-likelihoods; same contract as directbayeswoodbury.loglik (dbw.py:261-306)."""
-    ll, _, _ = loglik_device(fitinfo, emu, theta, y, x, return_grad=False)
-    return ll.cpu().numpy().reshape(-1, 1)
+    return _evaluate(fitinfo, emu, theta, y, x, False)
 
 
 def loglik_grad(fitinfo, emu, theta, y, x):
     """(B,1), (B,d); same contract as directbayeswoodbury.loglik_grad (dbw.py:309-383)."""
-    ops = _ops()
-    torch = ops._torch()
-    ll, dll, _ = loglik_device(fitinfo, emu, theta, y, x, return_grad=True)
-    packed = torch.cat([ll[:, None], dll], dim=1).cpu().numpy()              # one D2H copy per call
+    packed = _evaluate(fitinfo, emu, theta, y, x, True)
     return packed[:, :1].copy(), packed[:, 1:].copy()
 
 
@@ -140,6 +184,8 @@ def make_logpost(fitinfo, emu, x, y):
 def fit(fitinfo, emu, x, y, **bayeswoodbury_args):
     """Posterior sampling with surmise's own sampler plugins (dbw.py:7-163)."""
     from surmise.utilities import sampler            # the reference's dispatcher, used unmodified
+    if 'shard_theta' in bayeswoodbury_args:          # our option, not a sampler option
+        fitinfo['shard_theta'] = bool(bayeswoodbury_args.pop('shard_theta'))
     woodbury_constants(fitinfo, emu, x, y)
     logpost, draw_func = make_logpost(fitinfo, emu, x, y)
     sampler_obj = sampler(logpost_func=logpost, draw_func=draw_func, **bayeswoodbury_args)

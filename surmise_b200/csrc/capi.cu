@@ -128,11 +128,17 @@ int sb200_pc_backproject(int m, int k, int B, int d, const double* phi, const do
 int sb200_woodbury_loglik(int B, int k, int m, int d, const double* predvecs, const double* predvars,
                           const double* predvecs_grad, const double* predvars_grad, const double* phiT,
                           const double* resid0, const double* extravar, const double* sinv, const double* G,
-                          int want_grad, double* ll, double* dll, int* fired, void* stream) {
+                          int want_grad, int variant, double* ll, double* dll, int* fired, void* stream) {
     SB_CHECK_ARG(predvecs && predvars && phiT && resid0 && extravar && sinv && G && ll && fired,
                  "woodbury_loglik: NULL pointer");
     return woodbury_loglik(B, k, m, d, predvecs, predvars, predvecs_grad, predvars_grad, phiT, resid0, extravar, sinv,
-                           G, want_grad, ll, dll, fired, ST(stream));
+                           G, want_grad, variant, ll, dll, fired, ST(stream));
+}
+
+int sb200_woodbury_trigger(int B, int k, int m, const double* predvars, const double* phiT, const double* extravar,
+                           int* fired, void* stream) {
+    SB_CHECK_ARG(predvars && phiT && extravar && fired, "woodbury_trigger: NULL pointer");
+    return woodbury_trigger(B, k, m, predvars, phiT, extravar, fired, ST(stream));
 }
 
 int sb200_dgemm(int a_kc, int b_kc, int M, int N, int K, double alpha, const double* A, long lda, long stride_a,
@@ -153,10 +159,11 @@ int sb200_potrf_batched(int batch, int n, int mrows, double* A, long lda, long s
                         long stride_linv, int* info, void* stream) {
     SB_CHECK_ARG(A && Linv && info, "potrf: NULL pointer");
     SB_CHECK_ARG(ldl >= n && stride_linv >= (long)n * ldl, "potrf: bad Linv layout");
-    SB_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, ST(stream)));
+    SB_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * 2 * batch, ST(stream)));      // [info | scratch counters]
     SB_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * ((size_t)(batch - 1) * stride_linv + (size_t)n * ldl), ST(stream)));
     CholBatch c{};
     c.batch = batch; c.n = n; c.mrows = mrows; c.A = A; c.lda = lda; c.strideA = stride_a; c.info = info;
+    c.counters = info + batch;
     c.Dinv = Linv; c.ldd = ldl; c.strideD = stride_linv; c.blockD = (long)CHOL_NB * ldl + CHOL_NB;
     return potrf_batched(c, ST(stream));
 }

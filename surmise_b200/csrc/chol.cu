@@ -11,81 +11,210 @@ namespace sb {
 namespace {
 
 constexpr int NB = CHOL_NB;
-constexpr int LDS_ = NB + 1;   // padded shared-memory leading dimension
 
-// One CTA per matrix: unblocked Cholesky of an nb x nb (nb <= 64) diagonal block held in shared
-// memory, followed by its explicit inverse.  Only the lower triangle of A is read or written.
-__global__ void __launch_bounds__(256) potrf_leaf_kernel(double* __restrict__ Abase, long lda, long strideA,
-                                                         double* __restrict__ Dbase, long ldd, long strideD, int nb,
-                                                         int j0, int* __restrict__ info) {
+// ------------------------------------------------------------------------------------------------
+// Panel kernel: factor one 64-wide diagonal block AND solve the rows below it, in one launch.
+//   grid = (row tiles of 128 below the block (at least 1), batch), 256 threads.
+// Every CTA redundantly factors the 64x64 block (64^3/3 flop, ~6 us) and inverts it, so the panel solve
+// needs no second launch and no grid-wide dependency; the CTA that loaded the block last writes L, L^-1 back.
+//   phase 1: block -> registers (16x16 thread grid, 4x4 elements each), right-looking Cholesky with one
+//            __syncthreads per column (double-buffered column broadcast through shared memory);
+//   phase 2: X = L^-1 by forward substitution, 4 threads per column, rows interleaved, x_j by warp shuffle;
+//   phase 3: P <- P X' for this CTA's 128 rows on the FP64 tensor cores (DMMA) out of shared memory.
+constexpr int PT = 128;          // rows per CTA in the panel solve
+constexpr int SLD = NB + 4;      // shared leading dimension: (4 g + t) mod 16 distinct -> conflict-free LDS.64
+
+__device__ __forceinline__ void cp_async8_plain(double* smem, const double* gmem, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(valid ? 8 : 0) : "memory");
+}
+
+__global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ Abase, long lda, long strideA,
+                                                          double* __restrict__ Dbase, long ldd, long strideD, int nb,
+                                                          int j0, int below, int* __restrict__ info,
+                                                          int* __restrict__ counters) {
     extern __shared__ double sm[];
-    double* S = sm;                    // [NB][LDS_]
-    double* X = sm + NB * LDS_;        // [NB][LDS_]
-    double* diag = X + NB * LDS_;      // [NB]
-    const int tid = threadIdx.x, z = blockIdx.x;
-    double* A = Abase + (long)z * strideA;
-    double* D = Dbase + (long)z * strideD;
+    double* S = sm;                       // [NB][SLD]  block, then L
+    double* X = S + NB * SLD;             // [NB][SLD]  L^-1
+    double* T = X + NB * SLD;             // [PT][SLD]  this CTA's rows of the panel
+    double* colbuf = T + PT * SLD;        // [2][NB]
+    double* invd = colbuf + 2 * NB;       // [NB]
+    const int tid = threadIdx.x, z = blockIdx.y;
+    double* A = Abase + (long)z * strideA;          // points at the diagonal block (j0, j0)
+    const int r0 = blockIdx.x * PT;                 // first panel row (relative to the row just below the block)
+    const int rows_here = min(PT, below - r0);      // <= 0 when there is nothing below
 
-    for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
-        int i = idx / nb, j = idx % nb;
-        S[i * LDS_ + j] = (j <= i) ? A[(long)i * lda + j] : 0.0;
-        X[i * LDS_ + j] = 0.0;
+    // asynchronous stage of the panel rows (overlaps the factorisation)
+    if (rows_here > 0) {
+        const double* P = A + (long)(nb + r0) * lda;
+        for (int idx = tid; idx < PT * NB; idx += 256) {
+            int r = idx >> 6, c = idx & 63;
+            bool ok = (r < rows_here) && (c < nb);
+            cp_async8_plain(T + r * SLD + c, ok ? P + (long)r * lda + c : A, ok);
+        }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+
+    // ---- phase 1: Cholesky of the (identity padded) 64 x 64 block, register resident
+    const int ti = tid >> 4, tc = tid & 15;
+    double a[4][4];
+#pragma unroll
+    for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+            int i = ti + 16 * ii, c = tc + 16 * cc;
+            double v = 0.0;
+            if (i < nb && c <= i) v = A[(long)i * lda + c];
+            else if (i >= nb && c == i) v = 1.0;
+            a[ii][cc] = v;
+        }
+    // The block is factored in place by whichever CTA of this matrix loaded it LAST (all CTAs compute the
+    // same L), so no CTA can still be reading A's block when it is overwritten.  No spinning: a counter.
+    __shared__ int s_writer;
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        int old = atomicAdd(&counters[z], 1);
+        s_writer = (old == (int)gridDim.x - 1);
+        if (s_writer) counters[z] = 0;               // everyone has arrived: re-arm for the next launch
+        __threadfence();
     }
     int bad_at = 0;
-    const int ti = tid >> 4, tc = tid & 15;
-    for (int j = 0; j < nb; j++) {
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        const int jb = j >> 4, jr = j & 15;
+        double* cb = colbuf + (j & 1) * NB;
+        if (tc == jr) {
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) cb[ti + 16 * ii] = a[ii][jb];
+        }
         __syncthreads();
-        double ajj = S[j * LDS_ + j];
+        double ajj = cb[j];
         bool bad = !(ajj > 0.0);
         if (bad && bad_at == 0) bad_at = j0 + j + 1;
         double ljj = sqrt(bad ? 1.0 : ajj);
         double inv = 1.0 / ljj;
-        if (tid == j) diag[j] = ljj;
-        if (tid > j && tid < nb) S[tid * LDS_ + j] *= inv;
-        __syncthreads();
-        for (int i = j + 1 + ti; i < nb; i += 16) {
-            double lij = S[i * LDS_ + j];
-            for (int c = j + 1 + tc; c <= i; c += 16) S[i * LDS_ + c] -= lij * S[c * LDS_ + j];
+        double li[4], lc[4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ii++) li[ii] = cb[ti + 16 * ii] * inv;
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) lc[cc] = cb[tc + 16 * cc] * inv;
+#pragma unroll
+        for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++)
+                if (ii >= jb && cc >= jb && cc <= ii) {
+                    int i = ti + 16 * ii, c = tc + 16 * cc;
+                    if (i > j && c > j && c <= i) a[ii][cc] -= li[ii] * lc[cc];
+                }
+        if (tc == jr) {
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) {
+                int i = ti + 16 * ii;
+                if (i > j) a[ii][jb] = li[ii];
+                else if (i == j) a[ii][jb] = ljj;
+            }
+        }
+        if (ti == jr && tc == jr) invd[j] = inv;
+    }
+#pragma unroll
+    for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+            int i = ti + 16 * ii, c = tc + 16 * cc;
+            S[i * SLD + c] = (c <= i) ? a[ii][cc] : 0.0;
+            X[i * SLD + c] = 0.0;
+        }
+    __syncthreads();
+    const bool writer = s_writer != 0;
+    if (writer && tid == 0 && bad_at != 0 && info[z] == 0) info[z] = bad_at;
+
+    // ---- phase 2: X = L^-1; thread (c, q) owns rows q, q+4, ... of column c
+    {
+        const int c = tid >> 2, q = tid & 3, lane = tid & 31;
+        double bcol[16];
+#pragma unroll
+        for (int r = 0; r < 16; r++) bcol[r] = (q + 4 * r == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            const int jq = j & 3, jr = j >> 2;
+            double xj = __shfl_sync(0xffffffffu, bcol[jr] * invd[j], (lane & ~3) | jq);
+            if (q == jq) X[j * SLD + c] = xj;
+#pragma unroll
+            for (int r = 0; r < 16; r++)
+                if (r >= jr) {
+                    int i = q + 4 * r;
+                    if (i > j) bcol[r] -= S[i * SLD + j] * xj;
+                }
         }
     }
-    __syncthreads();
-    if (tid < nb) S[tid * LDS_ + tid] = diag[tid];
-    if (tid == 0 && bad_at != 0 && info[z] == 0) info[z] = bad_at;
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
 
-    // X = L^-1 by forward substitution, 4 threads per column sharing the dot product
-    const int c = tid >> 2, q = tid & 3;
-    for (int i = 0; i < nb; i++) {
-        double s = 0.0;
-        if (c < i && c < nb)
-            for (int j = c + q; j < i; j += 4) s += S[i * LDS_ + j] * X[j * LDS_ + c];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (q == 0 && c < nb) {
-            if (c == i) X[i * LDS_ + c] = 1.0 / diag[i];
-            else if (c < i) X[i * LDS_ + c] = -s / diag[i];
+    if (writer) {
+        double* D = Dbase + (long)z * strideD;
+        for (int idx = tid; idx < nb * nb; idx += 256) {
+            int i = idx / nb, c = idx % nb;
+            if (c <= i) A[(long)i * lda + c] = S[i * SLD + c];
+            D[(long)i * ldd + c] = X[i * SLD + c];
         }
-        __syncthreads();
     }
-    for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
-        int i = idx / nb, j = idx % nb;
-        if (j <= i) A[(long)i * lda + j] = S[i * LDS_ + j];
-        D[(long)i * ldd + j] = X[i * LDS_ + j];
+    if (rows_here <= 0) return;
+
+    // ---- phase 3: P <- P X'  (DMMA from shared memory); warp w owns rows 16w .. 16w+15
+    {
+        const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+        const int m0 = warp * 16;
+        double acc[2][8][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+#pragma unroll
+        for (int k4 = 0; k4 < NB / 4; k4++) {
+            double av[2];
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) av[mi] = T[(m0 + 8 * mi + g) * SLD + 4 * k4 + t];
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++)
+                if (4 * k4 <= 8 * ni + 7) {                      // X[n][k] == 0 for k > n
+                    double bv = X[(8 * ni + g) * SLD + 4 * k4 + t];
+#pragma unroll
+                    for (int mi = 0; mi < 2; mi++)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                     : "+d"(acc[mi][ni][0]), "+d"(acc[mi][ni][1])
+                                     : "d"(av[mi]), "d"(bv));
+                }
+        }
+        double* P = A + (long)(nb + r0) * lda;
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+            int r = m0 + 8 * mi + g;
+            if (r >= rows_here) continue;
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++) {
+                int c = 8 * ni + 2 * t;
+                if (c < nb) P[(long)r * lda + c] = acc[mi][ni][0];
+                if (c + 1 < nb) P[(long)r * lda + c + 1] = acc[mi][ni][1];
+            }
+        }
     }
 }
 
-int leaf(const CholBatch& c, int j0, int nb, cudaStream_t stream) {
-    constexpr size_t smem = (size_t)(2 * NB * LDS_ + NB) * sizeof(double);
+int panel(const CholBatch& c, int j0, int nb, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)(2 * NB * SLD + PT * SLD + 3 * NB) * sizeof(double);
     static bool configured[64] = {false};
     int dev = 0;
     SB_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !configured[dev]) {
-        SB_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = true;
     }
-    potrf_leaf_kernel<<<c.batch, 256, smem, stream>>>(c.A + (long)j0 * c.lda + j0, c.lda, c.strideA,
-                                                     c.Dinv + (long)(j0 / NB) * c.blockD, c.ldd, c.strideD, nb, j0,
-                                                     c.info);
+    int below = c.mrows - (j0 + nb);
+    dim3 grid(below > 0 ? cdiv(below, PT) : 1, c.batch);
+    potrf_panel_kernel<<<grid, 256, smem, stream>>>(c.A + (long)j0 * c.lda + j0, c.lda, c.strideA,
+                                                    c.Dinv + (long)(j0 / NB) * c.blockD, c.ldd, c.strideD, nb, j0,
+                                                    below, c.info, c.counters);
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -96,20 +225,7 @@ int split_point(int nn) {      // multiple of NB closest to nn/2 from above
 }
 
 int potrf_rec(const CholBatch& c, int j0, int nn, cudaStream_t stream) {
-    if (nn <= NB) {
-        SB_TRY(leaf(c, j0, nn, stream));
-        int below = c.mrows - (j0 + nn);
-        if (below > 0) {                       // panel solve, in place:  P <- P * Dinv'
-            GemmArgs g{};
-            g.M = below; g.N = nn; g.K = nn;
-            g.A = c.A + (long)(j0 + nn) * c.lda + j0; g.lda = c.lda; g.strideA = c.strideA; g.a_kc = true;
-            g.B = c.Dinv + (long)(j0 / NB) * c.blockD; g.ldb = c.ldd; g.strideB = c.strideD; g.b_kc = true;
-            g.C = c.A + (long)(j0 + nn) * c.lda + j0; g.ldc = c.lda; g.strideC = c.strideA;
-            g.alpha = 1.0; g.beta = 0.0; g.flags = GEMM_B_LOWER;
-            SB_TRY(launch_dgemm(g, c.batch, 1, stream));
-        }
-        return 0;
-    }
+    if (nn <= NB) return panel(c, j0, nn, stream);      // factor the block and solve every row below it
     int n1 = split_point(nn), n2 = nn - n1;
     SB_TRY(potrf_rec(c, j0, n1, stream));
     {                                          // rows [j0+n1, mrows) x cols [j0+n1, j0+nn) -= P Pc'
@@ -210,6 +326,7 @@ size_t trtri_tmp_elems(int n) {
 int potrf_batched(const CholBatch& c, cudaStream_t stream) {
     SB_CHECK_ARG(c.n > 0 && c.mrows >= c.n && c.batch > 0, "potrf: bad shape n=%d mrows=%d batch=%d", c.n, c.mrows, c.batch);
     SB_CHECK_ARG(c.lda >= c.n, "potrf: lda %ld < n %d", c.lda, c.n);
+    SB_CHECK_ARG(c.counters != nullptr, "potrf: counters is NULL");
     return potrf_rec(c, 0, c.n, stream);
 }
 

@@ -17,6 +17,7 @@ struct CholBatch {
     long ldd;         //   Dinv + z*strideD + b*blockD, leading dimension ldd, zeros above the diagonal
     long strideD, blockD;
     int* info;        // (batch) 0 = ok, j>0 = leading minor j not positive (LAPACK convention)
+    int* counters;    // (batch) zero-initialised scratch: arrival counters of the panel kernel (left at zero)
 };
 
 // A <- L (in place), Dinv filled, extra rows <- rows * L^-T.   ~ n^3/3 + (mrows-n) n^2 flop per matrix

@@ -139,7 +139,18 @@ __global__ void __launch_bounds__(256) gp_assemble_kernel(int n, int d, const do
     }
 }
 
-// one CTA per 32x32 tile of the lower triangle; partial[z][tile][0..p)
+// one CTA per 64x64 tile of the lower triangle (16 pairs per thread); partial[z][tile][0..p)
+constexpr int GT = 64;
+
+__device__ __forceinline__ void stage_scaled_n(double* dst, const double* __restrict__ X, int row0, int nrows, int d,
+                                               const double* ell, int rows) {
+    for (int idx = threadIdx.x; idx < rows * d; idx += blockDim.x) {
+        int r = idx / d, k = idx % d;
+        int gr = row0 + r;
+        dst[r * XLD + k] = (gr < nrows) ? X[(long)gr * d + k] / ell[k] : 0.0;
+    }
+}
+
 __global__ void __launch_bounds__(256) gp_grad_contract_kernel(int n, int d, const double* __restrict__ thetab,
                                                                long strideTheta, const double* __restrict__ gvarb,
                                                                long strideGvar, const double* __restrict__ hypb,
@@ -154,9 +165,9 @@ __global__ void __launch_bounds__(256) gp_grad_contract_kernel(int n, int d, con
     while ((long)(ti + 1) * (ti + 2) / 2 <= t) ti++;
     while ((long)ti * (ti + 1) / 2 > t) ti--;
     const int tj = t - ti * (ti + 1) / 2;
-    const int i0 = ti * TS, j0 = tj * TS;
+    const int i0 = ti * GT, j0 = tj * GT;
 
-    __shared__ double xa[TS * XLD], xb[TS * XLD], red[32];
+    __shared__ double xa[GT * XLD], xb[GT * XLD], red[MAXP][8];
     __shared__ GpConsts gc;
     const double* theta = thetab + (long)z * strideTheta;
     const double* hyp = hypb + (long)z * (d + 3);
@@ -164,8 +175,8 @@ __global__ void __launch_bounds__(256) gp_grad_contract_kernel(int n, int d, con
     const double* alpha = alphab + (long)z * strideAlpha;
     load_gp_consts(&gc, hyp, d);
     __syncthreads();
-    stage_scaled(xa, theta, i0, n, d, gc.ell);
-    stage_scaled(xb, theta, j0, n, d, gc.ell);
+    stage_scaled_n(xa, theta, i0, n, d, gc.ell, GT);
+    stage_scaled_n(xb, theta, j0, n, d, gc.ell, GT);
     __syncthreads();
     const double cq = 0.5 * n / ((n + s0) * sig2hat[z]);           // PCGPwM.py:898-902
     const double omn = 1.0 - gc.nu;
@@ -173,13 +184,15 @@ __global__ void __launch_bounds__(256) gp_grad_contract_kernel(int n, int d, con
 #pragma unroll
     for (int k = 0; k < MAXD; k++) acc[k] = 0.0;
 
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int j = j0 + tx;
     if (j < n) {
         const double aj = alpha[j];
-        for (int r = ty; r < TS; r += 8) {
+        const double* b = xb + tx * XLD;
+        for (int r = ty; r < GT; r += 4) {
             int i = i0 + r;
-            if (i >= n || j > i) continue;
+            if (i >= n) break;
+            if (j > i) continue;
             double w = 0.5 * Rinv[(long)i * ldr + j] - cq * alpha[i] * aj;
             if (i == j) {                                          // only d/dh_v lives on the diagonal
                 if (gvarb) acc_v += w * gc.ev * gvarb[(long)z * strideGvar + i];
@@ -187,34 +200,48 @@ __global__ void __launch_bounds__(256) gp_grad_contract_kernel(int n, int d, con
             }
             w *= 2.0;                                              // (a,b) and (b,a)
             const double* a = xa + r * XLD;
-            const double* b = xb + tx * XLD;
-            double rp = rpre_pair(a, b, d, gc.c);
-            double wr = w * omn * rp;
+            double prod = gc.c, ssum = 0.0, wsum[MAXD];
 #pragma unroll
             for (int k = 0; k < MAXD; k++)
                 if (k < d) {
                     double S = fabs(a[k] - b[k]);
-                    acc[k] += wr * (S * S) / (1.0 + S);            // (1-nu) dR0/dgamma_k
+                    double op = 1.0 + S;
+                    prod *= op;
+                    ssum -= S;
+                    wsum[k] = (S * S) / op;                        // dR0/dgamma_k / R_pre
                 }
+            double rp = prod * exp(ssum);
+            double wr = w * omn * rp;
+#pragma unroll
+            for (int k = 0; k < MAXD; k++)
+                if (k < d) acc[k] += wr * wsum[k];                 // (1-nu) dR0/dgamma_k
             acc_g += w * omn * gc.onemc * (gc.c - rp);             // (1-nu) dR0/dgamma_d
             acc_n -= w * gc.nu * omn * (rp + gc.onemc);            // nu (1-nu) (I - R0), PCGPwM.py:878
         }
     }
-    const int p = d + 3;
-    double* out = partial + ((long)z * ntiles + t) * MAXP;
+    // warp shuffles, then one pass through shared memory (fixed order)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < MAXD; k++)
         if (k < d) {
-            double s = block_sum(acc[k], red);
-            if (threadIdx.x == 0) out[k] = s;
+            double sv = warp_sum(acc[k]);
+            if (lane == 0) red[k][warp] = sv;
         }
-    double sg = block_sum(acc_g, red), sv = block_sum(acc_v, red), sn = block_sum(acc_n, red);
-    if (threadIdx.x == 0) {
-        out[d] = sg;
-        out[d + 1] = sv;
-        out[d + 2] = sn;
+    {
+        double sg = warp_sum(acc_g), sv = warp_sum(acc_v), sn = warp_sum(acc_n);
+        if (lane == 0) {
+            red[d][warp] = sg;
+            red[d + 1][warp] = sv;
+            red[d + 2][warp] = sn;
+        }
     }
-    (void)p;
+    __syncthreads();
+    if (threadIdx.x < d + 3) {
+        double sv = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < 8; wv++) sv += red[threadIdx.x][wv];
+        partial[((long)z * ntiles + t) * MAXP + threadIdx.x] = sv;
+    }
 }
 
 // one warp per hyper-parameter: fixed-order strided sum over the tile partials, then the prior term
@@ -262,7 +289,7 @@ __global__ void __launch_bounds__(256) cross_cov_t_kernel(int n, int d, int B, c
 }  // namespace
 
 int grad_contract_tiles(int n) {
-    long t = cdiv(n, TS);
+    long t = cdiv(n, GT);
     return (int)(t * (t + 1) / 2);
 }
 

@@ -17,7 +17,6 @@ namespace {
 
 constexpr int BK = 16;
 constexpr int STAGES = 3;
-constexpr int NTHREADS = 256;
 
 __device__ __forceinline__ void cp_async16(double* smem, const double* gmem, int src_bytes) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -41,7 +40,7 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
 
 // Stage one BMN x BK operand tile.  Elements outside [0,MN) x [kbase,k_hi) are zero-filled by
 // cp.async's src-size mechanism, so ragged M/N/K and triangular k-ranges need no special code.
-template <int BMN, bool KC>
+template <int BMN, bool KC, int NTHREADS>
 __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ G, long ld, int mn0, int MN,
                                           int kbase, int k_hi, bool vec16, int tid) {
     const double* dummy = (const double*)((uintptr_t)G & ~(uintptr_t)15);
@@ -83,12 +82,12 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
 }
 
 template <int BM, int BN, int WM, int WN, bool AKC, bool BKC>
-__global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) dgemm_dmma_kernel(GemmArgs p) {
     constexpr int A_TILE = BK * (BM + 4);
     constexpr int B_TILE = BK * (BN + 4);
     constexpr int WARPS_N = BN / WN;
     constexpr int WARPS_M = BM / WM;
-    static_assert(WARPS_M * WARPS_N * 32 == NTHREADS, "warp grid must cover the CTA tile");
+    constexpr int NTHREADS = WARPS_M * WARPS_N * 32;
     constexpr int MI = WM / 8, NI = WN / 8;
 
     extern __shared__ __align__(16) double smem[];
@@ -125,8 +124,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
         if (s < ktiles) {
-            load_tile<BM, AKC>(As + s * A_TILE, A, p.lda, m0, p.M, k_lo + s * BK, k_hi, a16, tid);
-            load_tile<BN, BKC>(Bs + s * B_TILE, B, p.ldb, n0, p.N, k_lo + s * BK, k_hi, b16, tid);
+            load_tile<BM, AKC, NTHREADS>(As + s * A_TILE, A, p.lda, m0, p.M, k_lo + s * BK, k_hi, a16, tid);
+            load_tile<BN, BKC, NTHREADS>(Bs + s * B_TILE, B, p.ldb, n0, p.N, k_lo + s * BK, k_hi, b16, tid);
         }
         cp_async_commit();
     }
@@ -142,8 +141,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
             int nx = kt + STAGES - 1;
             if (nx < ktiles) {
                 int slot = nx % STAGES;
-                load_tile<BM, AKC>(As + slot * A_TILE, A, p.lda, m0, p.M, k_lo + nx * BK, k_hi, a16, tid);
-                load_tile<BN, BKC>(Bs + slot * B_TILE, B, p.ldb, n0, p.N, k_lo + nx * BK, k_hi, b16, tid);
+                load_tile<BM, AKC, NTHREADS>(As + slot * A_TILE, A, p.lda, m0, p.M, k_lo + nx * BK, k_hi, a16, tid);
+                load_tile<BN, BKC, NTHREADS>(Bs + slot * B_TILE, B, p.ldb, n0, p.N, k_lo + nx * BK, k_hi, b16, tid);
             }
             cp_async_commit();
         }
@@ -237,6 +236,7 @@ int launch_one(const GemmArgs& g, int batch, cudaStream_t stream) {
         SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = true;
     }
+    constexpr int NTHREADS = (BM / WM) * (BN / WN) * 32;
     dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), batch);
     if (gemm_profile_enabled()) {
         cudaEvent_t e0, e1;
@@ -272,6 +272,8 @@ int launch_dgemm(const GemmArgs& g, int batch, int tile, cudaStream_t stream) {
     SB_CHECK_ARG(cdiv(g.M, 128) <= 65535, "dgemm: M %d too large", g.M);
     if (tile < 0) tile = (round_up(g.N, 64) < round_up(g.N, 128)) ? 1 : 0;
     if (tile == 1) return launch_layout<128, 64, 32, 32>(g, batch, stream);
+    if (tile == 2) return launch_layout<128, 128, 32, 32>(g, batch, stream);     // 16 warps
+    if (tile == 3) return launch_layout<128, 64, 32, 16>(g, batch, stream);      // 16 warps, narrow
     return launch_layout<128, 128, 64, 32>(g, batch, stream);
 }
 

@@ -36,7 +36,9 @@ constexpr int WOODBURY_MAXK = 112;
 // sinv: (2, m) = 1/yvar and 1/(yvar+|extravar|);  G: (2, K, K) = Phi' diag(sinv_v) Phi;  fired: device int
 int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const double* predvars, const double* dpv,
                     const double* dpvar, const double* phiT, const double* resid0, const double* extravar,
-                    const double* sinv, const double* G, int want_grad, double* ll, double* dll, int* fired,
-                    cudaStream_t stream);
+                    const double* sinv, const double* G, int want_grad, int variant, double* ll, double* dll,
+                    int* fired, cudaStream_t stream);
+int woodbury_trigger(int B, int K, int m, const double* predvars, const double* phiT, const double* extravar,
+                     int* fired, cudaStream_t stream);
 
 }  // namespace sb

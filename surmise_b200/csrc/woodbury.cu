@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
                                                              const double* __restrict__ phiT,
                                                              const double* __restrict__ resid0,
                                                              const double* __restrict__ sinvb,
-                                                             const double* __restrict__ Gb, const int* fired,
-                                                             int want_grad, double* __restrict__ ll,
+                                                             const double* __restrict__ Gb, int* fired,
+                                                             int forced_variant, int want_grad, double* __restrict__ ll,
                                                              double* __restrict__ dll) {
     extern __shared__ double sh[];
     double* Lm = sh;                    // K*K : A, then L, then Ainv
@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
     double* MJ3 = Nv + K;
     double* red = MJ3 + K;              // 32
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int variant = (*fired) ? 1 : 0;
+    const int variant = forced_variant >= 0 ? forced_variant : ((*fired) ? 1 : 0);
+    if (forced_variant >= 0 && blockIdx.x == 0 && threadIdx.x == 0) *fired = forced_variant;
     const double* sinv = sinvb + (long)variant * m;
     const double* G = Gb + (long)variant * K * K;
 
@@ -170,8 +171,8 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
 
 int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const double* predvars, const double* dpv,
                     const double* dpvar, const double* phiT, const double* resid0, const double* extravar,
-                    const double* sinv, const double* G, int want_grad, double* ll, double* dll, int* fired,
-                    cudaStream_t stream) {
+                    const double* sinv, const double* G, int want_grad, int variant, double* ll, double* dll,
+                    int* fired, cudaStream_t stream) {
     SB_CHECK_ARG(B > 0 && m > 0, "woodbury: empty batch");
     SB_CHECK_ARG(K >= 1 && K <= WOODBURY_MAXK, "woodbury: k=%d outside [1,%d]", K, WOODBURY_MAXK);
     SB_CHECK_ARG(!want_grad || (dpv && dpvar && dll), "woodbury: gradient buffers are NULL");
@@ -184,11 +185,22 @@ int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const do
         SB_CUDA(cudaFuncSetAttribute(woodbury_loglik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured[dev] = true;
     }
+    if (variant < 0) {
+        SB_CUDA(cudaMemsetAsync(fired, 0, sizeof(int), stream));
+        woodbury_trigger_kernel<<<B, WT, K * sizeof(double), stream>>>(B, K, m, predvars, phiT, extravar, fired);
+        SB_LAUNCH_CHECK();
+    }
+    woodbury_loglik_kernel<<<B, WT, smem, stream>>>(B, K, m, d, predvecs, predvars, dpv, dpvar, phiT, resid0, sinv, G,
+                                                    fired, variant > 0 ? 1 : variant, want_grad, ll, dll);
+    SB_LAUNCH_CHECK();
+    return 0;
+}
+
+int woodbury_trigger(int B, int K, int m, const double* predvars, const double* phiT, const double* extravar,
+                     int* fired, cudaStream_t stream) {
+    SB_CHECK_ARG(B > 0 && m > 0 && K >= 1, "woodbury_trigger: empty batch");
     SB_CUDA(cudaMemsetAsync(fired, 0, sizeof(int), stream));
     woodbury_trigger_kernel<<<B, WT, K * sizeof(double), stream>>>(B, K, m, predvars, phiT, extravar, fired);
-    SB_LAUNCH_CHECK();
-    woodbury_loglik_kernel<<<B, WT, smem, stream>>>(B, K, m, d, predvecs, predvars, dpv, dpvar, phiT, resid0, sinv, G,
-                                                    fired, want_grad, ll, dll);
     SB_LAUNCH_CHECK();
     return 0;
 }

@@ -42,9 +42,13 @@ def _ops():
 # ------------------------------------------------------------------------------------------------
 def fit(fitinfo, x, theta, f, epsilonPC=0.001, epsilonImpute=10e-6, lognugmean=-10, lognugLB=-20,
         varconstant=None, dampalpha=0.3, eta=10, standardpcinfo=None, verbose=0, nhyptrain=None,
-        **kwargs):
+        fit_mode='reference', **kwargs):
     """Same arguments as PCGPwM.fit (PCGPwM.py:12-137) plus
     nhyptrain : None (reference rule min(20 d, n), PCGPwM.py:744), an int, or 'all'.
+    fit_mode  : 'reference' -- the reference's sequential Gauss-Seidel sweeps (PCGPwM.py:691-721), one GPU;
+                'parallel'  -- Jacobi sweeps: every PC sees the previous sweep's leaders, PCs are sharded over
+                               the ranks of the initialised torch.distributed group (results do not depend on
+                               the number of ranks); see surmise_b200/_dist.py.
     """
     ops = _ops()
     ops._torch()                                   # fail loudly without CUDA before any work
@@ -77,7 +81,9 @@ def fit(fitinfo, x, theta, f, epsilonPC=0.001, epsilonImpute=10e-6, lognugmean=-
 
     logvarc = np.log(varconstant) if varconstant is not None else None
     fitter = _GPFitter(fitinfo, theta, lognugmean, lognugLB, logvarc, nhyptrain)
-    emulist = fitter.run(previous=fitinfo.get('emulist'))
+    if fit_mode not in ('reference', 'parallel'):
+        raise ValueError("fit_mode must be 'reference' or 'parallel'")
+    emulist = (fitter.run if fit_mode == 'reference' else fitter.run_parallel)(previous=fitinfo.get('emulist'))
     fitinfo['varc_status'] = 'fixed' if varconstant is not None else 'optimized'
     fitinfo['logvarc'] = np.array([e['hypvarconst'] for e in emulist])
     fitinfo['pcstdvar'] = np.exp(fitinfo['logvarc']) * fitinfo['unscaled_pcstdvar']
@@ -132,14 +138,19 @@ class _GPFitter:
         self.nevals = 0
 
     # -- one PC ---------------------------------------------------------------------------------
-    def _subsample(self, j):
-        """Rows used for the hyper-parameter search; consumes np.random like PCGPwM.py:744-750."""
+    def _draw_rows(self, j=None):
+        """Random rows for the hyper-parameter search; consumes np.random like PCGPwM.py:744-750."""
         if self.n > self.nh:
-            rows = np.random.choice(self.n, self.nh, replace=False)
-            idx = self.torch.from_numpy(rows).to(self.theta_dev.device)
+            return np.random.choice(self.n, self.nh, replace=False)
+        return np.arange(self.n)
+
+    def _subsample(self, j, rows=None):
+        if rows is None:
+            rows = self._draw_rows()
+        if self.n > self.nh:
+            idx = self.torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(self.theta_dev.device)
             data = self.ops.GPData(self.theta_dev[idx], self.pc_dev[j][idx], self.gvar_dev[j][idx])
         else:
-            rows = np.arange(self.n)
             data = self.ops.GPData(self.theta_dev, self.pc_dev[j], self.gvar_dev[j])
         return rows, data
 
@@ -153,9 +164,9 @@ class _GPFitter:
             grad = np.where(bad[:, None], 0.0, grad)
         return val, grad
 
-    def fit_one(self, j, cand, cand_ids):
+    def fit_one(self, j, cand, cand_ids, rows=None):
         """__fitGP1d without its full-n stage.  Returns (hyp, hypind or -1, subsample rows)."""
-        rows, data = self._subsample(j)
+        rows, data = self._subsample(j, rows)
         hyp = 1 * self.mean
         lead = -1
         # candidate scan (PCGPwM.py:761-769): prior mean first, then every leader's hyper-parameters
@@ -215,6 +226,23 @@ class _GPFitter:
                 hypinds[j] = j if hi < -0.5 else hi
                 hyps[j], rows_used[j] = hyp, rows
         return self._finalise(np.array(hyps), hypinds.astype(int), rows_used)
+
+    def run_parallel(self, previous=None):
+        """Jacobi sweeps with the PCs sharded over torch.distributed ranks (see _dist.jacobi_sweeps)."""
+        from .. import _dist
+        comm = _dist.Comm()
+        k = self.pc.shape[1]
+        start_hyps = start_inds = None
+        if previous is not None and previous[0]['hyp'].shape[0] == self.p and len(previous) >= k:
+            start_hyps = np.array([previous[j]['hyp'] for j in range(k)])
+            start_inds = np.array([previous[j]['hypind'] for j in range(k)])
+
+        def one(j, cand, cand_ids, rows):
+            hyp, hi, _ = self.fit_one(j, cand, cand_ids, rows)
+            return hyp, hi
+        hyps, hypinds, rows_used = _dist.jacobi_sweeps(one, k, self.p, comm, self._draw_rows,
+                                                       start_hyps=start_hyps, start_inds=start_inds)
+        return self._finalise(hyps, hypinds, rows_used)       # replicated on every rank (cheap next to the search)
 
     def _finalise(self, hyps, hypinds, rows_used):
         """Full-data factorisations (PCGPwM.py:810-846), one per distinct (hyp, gvar), in one batch."""

@@ -231,7 +231,18 @@ def pc_backproject(phi, offset, extravar, pv, pvar, dpv=None, dpvar=None, want_c
     return mean, var, cxh, mg, cg
 
 
-def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None):
+def woodbury_trigger(consts, pvar):
+    """Device int32 flag: does the unmodelled-variance test (dbw.py:277-279) fire for this batch?"""
+    torch = _torch()
+    _need_cuda(pvar, consts['phiT'])
+    B, K = pvar.shape
+    fired = torch.empty(1, dtype=torch.int32, device=pvar.device)
+    check(lib.sb200_woodbury_trigger(B, K, consts['phiT'].shape[1], _ptr(pvar), _ptr(consts['phiT']),
+                                     _ptr(consts['extravar']), _ptr(fired), _stream(torch)), 'sb200_woodbury_trigger')
+    return fired
+
+
+def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1):
     """Batched directbayeswoodbury log-likelihood (+ gradient) (dbw.py:261-383).
 
     consts: dict of device tensors phiT (k,m), resid0 (m), extravar (m), sinv (2,m), G (2,k,k).
@@ -249,7 +260,7 @@ def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None):
     fired = torch.empty(1, dtype=torch.int32, device=dev)
     check(lib.sb200_woodbury_loglik(B, K, m, d, _ptr(pv), _ptr(pvar), _ptr(dpv), _ptr(dpvar), _ptr(consts['phiT']),
                                     _ptr(consts['resid0']), _ptr(consts['extravar']), _ptr(consts['sinv']),
-                                    _ptr(consts['G']), int(want_grad), _ptr(ll), _ptr(dll), _ptr(fired),
+                                    _ptr(consts['G']), int(want_grad), int(variant), _ptr(ll), _ptr(dll), _ptr(fired),
                                     _stream(torch)), 'sb200_woodbury_loglik')
     return ll, dll, fired
 
@@ -272,10 +283,10 @@ def potrf_batched(A, n, mrows):
     _need_cuda(A)
     batch, _, lda = A.shape
     Linv = torch.empty((batch, n, lda), dtype=torch.float64, device=A.device)
-    info = torch.empty(batch, dtype=torch.int32, device=A.device)
+    info = torch.empty(2 * batch, dtype=torch.int32, device=A.device)      # [info | scratch]
     check(lib.sb200_potrf_batched(batch, n, mrows, _ptr(A), lda, A.stride(0), _ptr(Linv), lda, n * lda, _ptr(info),
                                   _stream(torch)), 'sb200_potrf_batched')
-    return Linv, info
+    return Linv, info[:batch]
 
 
 def trtri_batched(L, Linv, n):

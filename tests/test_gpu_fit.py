@@ -97,3 +97,117 @@ def test_user_supplied_basis_and_errors():
     fconst[0, :] = 1.0
     with pytest.raises(ValueError):
         _facade_fit(M, x, theta, fconst)
+
+
+def test_fit_parallel_mode_single_rank():
+    """fit_mode='parallel' (Jacobi sweeps, the shardable form) on one GPU: accurate and self-consistent."""
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    x, theta, f, truth = make_simulator(200, 3, 50, 8, seed=3)
+    np.random.seed(3)
+    fi = _facade_fit(M, x, theta, f, fit_mode='parallel')
+    tn = np.random.default_rng(0).uniform(0.05, 0.95, size=(40, 3))
+    p = {}
+    M.predict(p, fi, x, tn)
+    e_truth = float(np.sqrt(np.mean((p['mean'] - truth(tn)) ** 2)) / np.std(truth(tn)))
+    inds = [e['hypind'] for e in fi['emulist']]
+    report('fit_parallel', rmse_vs_truth=e_truth, leaders=len(set(inds)))
+    assert e_truth < 0.05
+    assert all(inds[j] <= j for j in range(len(inds)))
+    for j, e in enumerate(fi['emulist']):                          # sharing PCs carry their leader's hyper-parameters
+        assert np.array_equal(e['hyp'], fi['emulist'][e['hypind']]['hyp'])
+    with pytest.raises(ValueError):
+        _facade_fit(M, x, theta, f, fit_mode='nonsense')
+
+
+class _ShimPrediction:
+    def __init__(self, info):
+        self._info = info
+
+    def mean(self):
+        return self._info['mean']
+
+    def covxhalf(self):
+        return self._info['covxhalf']
+
+    def __call__(self):
+        return self.mean()
+
+
+class _ShimEmulator:
+    """The three things surmise's emulator object offers to a calibration method."""
+
+    def __init__(self, method, fitinfo, theta):
+        self.method, self._info, self._emulator__theta = method, fitinfo, theta
+
+    def predict(self, x=None, theta=None, args={}):
+        info = {}
+        self.method.predict(info, self._info, x, self._info['theta'] if theta is None else theta, **args)
+        return _ShimPrediction(info)
+
+
+def test_calibration_fit_through_sampler_contract(monkeypatch):
+    """directbayeswoodbury_B200.fit drives a sampler exactly as surmise.utilities.sampler would (dbw.py:149-162).
+    The GPU box has no surmise, so a stand-in `surmise.utilities.sampler` with the same constructor contract
+    (utilities.py:36-71) runs a plain random-walk Metropolis on the closure it is given."""
+    import sys
+    import types
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
+    from synth import make_observation
+
+    class sampler:
+        def __init__(self, logpost_func, draw_func, sampler='metropolis_hastings', numsamp=400, **opts):
+            rng = np.random.default_rng(0)
+            th = draw_func(64)
+            lp = logpost_func(th, return_grad=False)
+            cur, curlp = th[np.argmax(lp)].copy(), float(np.max(lp))
+            draws = []
+            for it in range(numsamp + 200):
+                prop = cur + 0.03 * rng.normal(size=cur.shape)
+                plp = float(logpost_func(prop[None, :], return_grad=False)[0, 0])
+                if np.log(rng.uniform()) < plp - curlp:
+                    cur, curlp = prop, plp
+                if it >= 200:
+                    draws.append(cur.copy())
+            self.sampler_info = {'theta': np.array(draws)}
+    if 'surmise' not in sys.modules:
+        pkg = types.ModuleType('surmise')
+        util = types.ModuleType('surmise.utilities')
+        util.sampler = sampler
+        pkg.utilities = util
+        monkeypatch.setitem(sys.modules, 'surmise', pkg)
+        monkeypatch.setitem(sys.modules, 'surmise.utilities', util)
+    else:
+        import surmise.utilities
+        monkeypatch.setattr(surmise.utilities, 'sampler', sampler)
+
+    x, theta, f, truth = make_simulator(150, 2, 25, 4, seed=21)
+    np.random.seed(21)
+    fi = _facade_fit(M, x, theta, f)
+    emu = _ShimEmulator(M, fi, theta)
+    theta_true, y, yvar = make_observation(truth, 2, seed=22)
+
+    class prior:
+        @staticmethod
+        def lpdf(th):
+            th = np.atleast_2d(th)
+            return np.where(np.all((th >= 0) & (th <= 1), axis=1), 0.0, -np.inf).reshape(-1, 1)
+
+        @staticmethod
+        def rnd(n):
+            return np.random.uniform(size=(n, 2))
+    cal = {'thetaprior': prior, 'yvar': yvar}
+    C.fit(cal, emu, x, y, sampler='metropolis_hastings', numsamp=400)
+    assert cal['thetarnd'].shape == (400, 2) and np.isfinite(cal['lpdfapproxnorm'])
+    err = np.abs(cal['thetarnd'].mean(0) - theta_true[0])
+    report('calibration_fit', err0=float(err[0]), err1=float(err[1]))
+    assert np.all(err < 0.1)                                        # posterior sits on the generating theta
+    lp = C.thetalpdf(cal, cal['thetarnd'][:5])
+    assert lp.shape == (5, 1) and np.all(np.isfinite(lp))
+    pred = {}
+    C.predict(pred, cal, emu, x)
+    assert pred['rnd'].shape == (400, x.shape[0]) and pred['mean'].shape == (x.shape[0],)
+    assert np.sqrt(np.mean((pred['mean'] - truth(theta_true)[:, 0]) ** 2)) < 0.2
+    assert C.thetarnd(cal, 7).shape == (7, 2)
+    with pytest.raises(ValueError):
+        C.loglik({}, emu, cal['thetarnd'][:2], y, x)                # yvar is mandatory (dbw.py:266-269)

@@ -1,0 +1,125 @@
+"""CPU: host-side logic, the C-ABI surface, and the no-fallback guarantees (no compute calls)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'surmise_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(sb200_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    import surmise_b200._lib as L
+    names = _declared_symbols()
+    assert len(names) >= 20
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(L.SIGNATURES) == names            # the ctypes table binds exactly the header's surface
+    assert L.lib.sb200_version() >= 100
+    assert L.lib.sb200_launch_count() == 0
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    import surmise_b200
+    from surmise_b200._lib import SurmiseB200Error
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    with pytest.raises(SurmiseB200Error):
+        surmise_b200.covmat(np.zeros((3, 2)), np.zeros((3, 2)), np.zeros(3))
+    with pytest.raises(SurmiseB200Error):
+        M.fit({}, np.arange(5.0)[:, None], np.random.rand(20, 2), np.random.rand(5, 20))
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'surmise_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M) or 'oracle/' in src:
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_pca_matches_reference_internals(golden):
+    """Batched imputation/PCA (_pca.py) vs the reference's per-row loops (PCGPwM.py:533-654).
+
+    The 40 ill-conditioned ridge iterations amplify summation-order differences (the reference's own
+    GEMM-vs-SYRK rounding moves fs by 2e-5), hence the tolerances."""
+    from surmise_b200 import _pca
+    g = golden('standardize')
+    spc, mof, mofrows = _pca.standardize(g['f'].T, 0.001, 10e-6)
+    assert np.allclose(spc['offset'], g['offset'], rtol=1e-13) and np.allclose(spc['scale'], g['scale'], rtol=1e-13)
+    pcs = _pca.principal_components(spc['fs'], spc['U'], spc['S'], mof, mofrows, 0.001, 10e-6)
+    assert pcs['pc'].shape == g['pc'].shape
+    assert np.max(np.abs(spc['fs'] - g['fs'])) < 1e-3
+    assert np.max(np.abs(spc['extravar'] - g['extravar'])) / np.max(g['extravar']) < 1e-3
+    sign = np.sign(np.sum(pcs['pc'] * g['pc'], 0))               # singular-vector sign is arbitrary
+    assert np.max(np.abs(pcs['pc'] * sign - g['pc'])) / np.max(np.abs(g['pc'])) < 1e-3
+    assert np.max(np.abs(pcs['unscaled_pcstdvar'] - g['unscaled_pcstdvar'])) < 1e-2
+
+
+def test_pca_complete_data_is_exact(golden):
+    from surmise_b200 import _pca
+    g = golden('emu_c1')
+    spc, mof, mofrows = _pca.standardize(g['in_f'].T, 0.001, 10e-6)
+    assert mof is None and mofrows is None
+    pcs = _pca.principal_components(spc['fs'], spc['U'], spc['S'], None, None, 0.001, 10e-6)
+    assert np.allclose(pcs['pc'], g['st_pc'], rtol=0, atol=1e-12)
+    assert np.allclose(pcs['pcti'], g['st_pcti'], rtol=0, atol=1e-12)
+    assert np.allclose(spc['extravar'], g['st_extravar'], rtol=1e-10, atol=1e-18)
+
+
+def test_hyper_prior_and_row_matching(golden):
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    from oracle import pcgpwm_oracle as po
+    g = golden('emu_c1')
+    got = M.hyper_prior(g['st_theta'], -10, -20, None)
+    want = po.hyper_regulariser(g['st_theta'], -10, -20)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    got = M.hyper_prior(g['st_theta'], -8, -16, np.log(0.5))
+    want = po.hyper_regulariser(g['st_theta'], -8, -16, np.log(0.5))
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    x = g['in_x']
+    assert np.array_equal(M.match_rows(x, x)[0], np.arange(x.shape[0]))
+    assert np.array_equal(M.match_rows(None, x)[0], np.arange(x.shape[0]))
+    xind, xnew = M.match_rows(np.vstack([x[[4, 2]], [[-1.0]]]), x)
+    assert list(xind) == [4, 2] and list(xnew) == [0, 1]
+    xo = np.array([['a', 1.0], ['b', 2.0], ['c', 3.0]], dtype=object)          # object x as in surmise's tests
+    xind, xnew = M.match_rows(xo[[2, 0]], xo)
+    assert list(xind) == [2, 0]
+
+
+def test_register_into_surmise_if_installed():
+    """With the real surmise importable (build container: PYTHONPATH=/tmp/ref/src) the plugin lookup works."""
+    surmise = pytest.importorskip('surmise')
+    import importlib
+    import surmise_b200
+    names = surmise_b200.register()
+    assert 'PCGPwM_B200' in names
+    m = importlib.import_module('surmise.emulationmethods.PCGPwM_B200')
+    assert hasattr(m, 'fit') and hasattr(m, 'predict')
+    c = importlib.import_module('surmise.calibrationmethods.directbayeswoodbury_B200')
+    for fn in ('fit', 'predict', 'thetarnd', 'thetalpdf', 'loglik', 'loglik_grad'):
+        assert hasattr(c, fn)
+    import torch
+    if not torch.cuda.is_available():
+        from surmise.emulation import emulator
+        x = np.arange(6.0)[:, None]
+        theta = np.random.default_rng(0).uniform(size=(30, 2))
+        f = np.sin(x + theta.sum(1))
+        with pytest.raises(Exception) as e:
+            emulator(x, theta, f, method='PCGPwM_B200')
+        assert 'CUDA' in str(e.value) or 'cuda' in str(e.value)
