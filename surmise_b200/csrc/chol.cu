@@ -31,8 +31,8 @@ __device__ __forceinline__ void cp_async8_plain(double* smem, const double* gmem
 
 __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ Abase, long lda, long strideA,
                                                           double* __restrict__ Dbase, long ldd, long strideD, int nb,
-                                                          int j0, int below, int* __restrict__ info,
-                                                          int* __restrict__ counters) {
+                                                          int j0, int below, int rows_per_cta,
+                                                          int* __restrict__ info, int* __restrict__ counters) {
     extern __shared__ double sm[];
     double* S = sm;                       // [NB][SLD]  block, then L
     double* X = S + NB * SLD;             // [NB][SLD]  L^-1
@@ -41,19 +41,21 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
     double* invd = colbuf + 2 * NB;       // [NB]
     const int tid = threadIdx.x, z = blockIdx.y;
     double* A = Abase + (long)z * strideA;          // points at the diagonal block (j0, j0)
-    const int r0 = blockIdx.x * PT;                 // first panel row (relative to the row just below the block)
-    const int rows_here = min(PT, below - r0);      // <= 0 when there is nothing below
+    const int cta_r0 = blockIdx.x * rows_per_cta;   // first panel row of this CTA (relative to the row below the block)
+    const int cta_rows = min(rows_per_cta, below - cta_r0);     // <= 0 when there is nothing below
 
-    // asynchronous stage of the panel rows (overlaps the factorisation)
-    if (rows_here > 0) {
+    // asynchronous stage of the first 128 panel rows (overlaps the factorisation)
+    auto stage_tile = [&](int r0) {
+        const int rows_here = min(PT, cta_r0 + cta_rows - r0);
         const double* P = A + (long)(nb + r0) * lda;
         for (int idx = tid; idx < PT * NB; idx += 256) {
             int r = idx >> 6, c = idx & 63;
             bool ok = (r < rows_here) && (c < nb);
             cp_async8_plain(T + r * SLD + c, ok ? P + (long)r * lda + c : A, ok);
         }
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    if (cta_rows > 0) stage_tile(cta_r0);
 
     // ---- phase 1: Cholesky of the (identity padded) 64 x 64 block, register resident
     const int ti = tid >> 4, tc = tid & 15;
@@ -80,42 +82,45 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
         __threadfence();
     }
     int bad_at = 0;
+    // Only the 16-column block index jb is unrolled (it selects registers); the column within the block is a
+    // real loop, so the code stays small (a fully unrolled 64-step version is instruction-fetch bound).
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-        const int jb = j >> 4, jr = j & 15;
-        double* cb = colbuf + (j & 1) * NB;
-        if (tc == jr) {
+    for (int jb = 0; jb < 4; jb++) {
+#pragma unroll 1
+        for (int jr = 0; jr < 16; jr++) {
+            const int j = jb * 16 + jr;
+            double* cb = colbuf + (j & 1) * NB;
+            if (tc == jr) {
 #pragma unroll
-            for (int ii = 0; ii < 4; ii++) cb[ti + 16 * ii] = a[ii][jb];
-        }
-        __syncthreads();
-        double ajj = cb[j];
-        bool bad = !(ajj > 0.0);
-        if (bad && bad_at == 0) bad_at = j0 + j + 1;
-        double ljj = sqrt(bad ? 1.0 : ajj);
-        double inv = 1.0 / ljj;
-        double li[4], lc[4];
-#pragma unroll
-        for (int ii = 0; ii < 4; ii++) li[ii] = cb[ti + 16 * ii] * inv;
-#pragma unroll
-        for (int cc = 0; cc < 4; cc++) lc[cc] = cb[tc + 16 * cc] * inv;
-#pragma unroll
-        for (int ii = 0; ii < 4; ii++)
-#pragma unroll
-            for (int cc = 0; cc < 4; cc++)
-                if (ii >= jb && cc >= jb && cc <= ii) {
-                    int i = ti + 16 * ii, c = tc + 16 * cc;
-                    if (i > j && c > j && c <= i) a[ii][cc] -= li[ii] * lc[cc];
-                }
-        if (tc == jr) {
-#pragma unroll
-            for (int ii = 0; ii < 4; ii++) {
-                int i = ti + 16 * ii;
-                if (i > j) a[ii][jb] = li[ii];
-                else if (i == j) a[ii][jb] = ljj;
+                for (int ii = 0; ii < 4; ii++) cb[ti + 16 * ii] = a[ii][jb];
             }
+            __syncthreads();
+            double ajj = cb[j];
+            bool bad = !(ajj > 0.0);
+            if (bad && bad_at == 0) bad_at = j0 + j + 1;
+            // one reciprocal square root instead of sqrt + divide on the per-column critical path
+            double inv = rsqrt(bad ? 1.0 : ajj);
+            double ljj = (bad ? 1.0 : ajj) * inv;
+            double li[4], lc[4];
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) li[ii] = (ti + 16 * ii > j) ? cb[ti + 16 * ii] * inv : 0.0;
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) lc[cc] = (tc + 16 * cc > j) ? cb[tc + 16 * cc] * inv : 0.0;
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+                for (int cc = 0; cc < 4; cc++)
+                    if (ii >= jb && cc >= jb && cc <= ii) a[ii][cc] -= li[ii] * lc[cc];   // zero factors mask i<=j, c<=j
+            if (tc == jr) {
+#pragma unroll
+                for (int ii = 0; ii < 4; ii++) {
+                    int i = ti + 16 * ii;
+                    if (i > j) a[ii][jb] = li[ii];
+                    else if (i == j) a[ii][jb] = ljj;
+                }
+            }
+            if (ti == jr && tc == jr) invd[j] = inv;
         }
-        if (ti == jr && tc == jr) invd[j] = inv;
     }
 #pragma unroll
     for (int ii = 0; ii < 4; ii++)
@@ -136,21 +141,23 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
 #pragma unroll
         for (int r = 0; r < 16; r++) bcol[r] = (q + 4 * r == c) ? 1.0 : 0.0;
 #pragma unroll
-        for (int j = 0; j < NB; j++) {
-            const int jq = j & 3, jr = j >> 2;
-            double xj = __shfl_sync(0xffffffffu, bcol[jr] * invd[j], (lane & ~3) | jq);
-            if (q == jq) X[j * SLD + c] = xj;
+        for (int jr = 0; jr < 16; jr++) {
+#pragma unroll 1
+            for (int jq = 0; jq < 4; jq++) {
+                const int j = jr * 4 + jq;
+                double xj = __shfl_sync(0xffffffffu, bcol[jr] * invd[j], (lane & ~3) | jq);
+                if (q == jq) X[j * SLD + c] = xj;
 #pragma unroll
-            for (int r = 0; r < 16; r++)
-                if (r >= jr) {
-                    int i = q + 4 * r;
-                    if (i > j) bcol[r] -= S[i * SLD + j] * xj;
-                }
+                for (int r = 0; r < 16; r++)
+                    if (r >= jr) {
+                        int i = q + 4 * r;
+                        double lij = (i > j) ? S[i * SLD + j] : 0.0;
+                        bcol[r] -= lij * xj;
+                    }
+            }
         }
     }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
-
     if (writer) {
         double* D = Dbase + (long)z * strideD;
         for (int idx = tid; idx < nb * nb; idx += 256) {
@@ -159,12 +166,15 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
             D[(long)i * ldd + c] = X[i * SLD + c];
         }
     }
-    if (rows_here <= 0) return;
+    if (cta_rows <= 0) return;
 
-    // ---- phase 3: P <- P X'  (DMMA from shared memory); warp w owns rows 16w .. 16w+15
-    {
-        const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-        const int m0 = warp * 16;
+    // ---- phase 3: P <- P X'  (DMMA from shared memory), 128 rows at a time; warp w owns rows 16w .. 16w+15
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int m0 = warp * 16;
+    for (int r0 = cta_r0; r0 < cta_r0 + cta_rows; r0 += PT) {
+        const int rows_here = min(PT, cta_r0 + cta_rows - r0);
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
         double acc[2][8][2];
 #pragma unroll
         for (int mi = 0; mi < 2; mi++)
@@ -186,6 +196,8 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
                                      : "d"(av[mi]), "d"(bv));
                 }
         }
+        __syncthreads();                                         // everyone is done reading T
+        if (r0 + PT < cta_r0 + cta_rows) stage_tile(r0 + PT);    // prefetch the next 128 rows while storing
         double* P = A + (long)(nb + r0) * lda;
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) {
@@ -211,10 +223,15 @@ int panel(const CholBatch& c, int j0, int nb, cudaStream_t stream) {
         configured[dev] = true;
     }
     int below = c.mrows - (j0 + nb);
-    dim3 grid(below > 0 ? cdiv(below, PT) : 1, c.batch);
+    // every CTA repeats the 64x64 factorisation, so keep the grid within one wave of the 148 SMs (1 CTA/SM):
+    // each CTA takes as many 128-row sub-tiles as that needs
+    int ctas_per_matrix = 148 / c.batch;
+    if (ctas_per_matrix < 1) ctas_per_matrix = 1;
+    int rows_per_cta = (int)round_up(cdiv(below > 0 ? below : 1, ctas_per_matrix), PT);
+    dim3 grid(below > 0 ? cdiv(below, rows_per_cta) : 1, c.batch);
     potrf_panel_kernel<<<grid, 256, smem, stream>>>(c.A + (long)j0 * c.lda + j0, c.lda, c.strideA,
                                                     c.Dinv + (long)(j0 / NB) * c.blockD, c.ldd, c.strideD, nb, j0,
-                                                    below, c.info, c.counters);
+                                                    below, rows_per_cta, c.info, c.counters);
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -247,29 +264,41 @@ struct TrtriCtx {
     double* tmp; long tmp_stride;
 };
 
-int trtri_rec(const TrtriCtx& t, int j0, int nn, cudaStream_t stream) {
-    if (nn <= NB) return 0;                    // diagonal blocks of X already hold Dinv
-    int n1 = split_point(nn), n2 = nn - n1;
-    SB_TRY(trtri_rec(t, j0, n1, stream));
-    SB_TRY(trtri_rec(t, j0 + n1, n2, stream));
-    long ldt = round_up(n1, 2);
-    {                                          // T = L21 * X11          (n2 x n1)
+// X21 = -X22 (L21 X11) for `pairs` adjacent (s, s2) block pairs starting at block offset j0, spaced 2s apart
+int trtri_merge(const TrtriCtx& t, int j0, int s, int s2, int pairs, cudaStream_t stream) {
+    const long step_i = (long)2 * s * (t.ldi + 1), step_x = (long)2 * s * (t.ldl + 1), step_t = (long)s * s;
+    {                                          // T = L21 * X11          (s2 x s per pair)
         GemmArgs g{};
-        g.M = n2; g.N = n1; g.K = n1;
-        g.A = t.L + (long)(j0 + n1) * t.ldi + j0; g.lda = t.ldi; g.strideA = t.strideLi; g.a_kc = true;
+        g.M = s2; g.N = s; g.K = s;
+        g.A = t.L + (long)(j0 + s) * t.ldi + j0; g.lda = t.ldi; g.strideA = t.strideLi; g.a_kc = true;
         g.B = t.X + (long)j0 * t.ldl + j0; g.ldb = t.ldl; g.strideB = t.strideL; g.b_kc = false;
-        g.C = t.tmp; g.ldc = ldt; g.strideC = t.tmp_stride;
+        g.C = t.tmp; g.ldc = s; g.strideC = t.tmp_stride;
         g.alpha = 1.0; g.beta = 0.0; g.flags = GEMM_B_UPPER;     // X11[k][n] == 0 for k < n
-        SB_TRY(launch_dgemm(g, t.batch, -1, stream));
+        g.inner_batch = t.batch; g.strideA2 = step_i; g.strideB2 = step_x; g.strideC2 = step_t;
+        SB_TRY(launch_dgemm(g, t.batch * pairs, -1, stream));
     }
     {                                          // X21 = -X22 * T
         GemmArgs g{};
-        g.M = n2; g.N = n1; g.K = n2;
-        g.A = t.X + (long)(j0 + n1) * t.ldl + (j0 + n1); g.lda = t.ldl; g.strideA = t.strideL; g.a_kc = true;
-        g.B = t.tmp; g.ldb = ldt; g.strideB = t.tmp_stride; g.b_kc = false;
-        g.C = t.X + (long)(j0 + n1) * t.ldl + j0; g.ldc = t.ldl; g.strideC = t.strideL;
+        g.M = s2; g.N = s; g.K = s2;
+        g.A = t.X + (long)(j0 + s) * t.ldl + (j0 + s); g.lda = t.ldl; g.strideA = t.strideL; g.a_kc = true;
+        g.B = t.tmp; g.ldb = s; g.strideB = t.tmp_stride; g.b_kc = false;
+        g.C = t.X + (long)(j0 + s) * t.ldl + j0; g.ldc = t.ldl; g.strideC = t.strideL;
         g.alpha = -1.0; g.beta = 0.0; g.flags = GEMM_A_LOWER;
-        SB_TRY(launch_dgemm(g, t.batch, -1, stream));
+        g.inner_batch = t.batch; g.strideA2 = step_x; g.strideB2 = step_t; g.strideC2 = step_x;
+        SB_TRY(launch_dgemm(g, t.batch * pairs, -1, stream));
+    }
+    return 0;
+}
+
+// Bottom-up: at level s all pairs of adjacent s-blocks are independent, so one (two-level batched) launch pair
+// handles every full pair of every matrix; a ragged last pair (right block shorter) gets its own launches.
+int trtri_levels(const TrtriCtx& t, int n, cudaStream_t stream) {
+    for (long s = NB; s < n; s *= 2) {
+        int full = (int)(n / (2 * s));                 // pairs with two complete s-blocks
+        long rest = n - (long)full * 2 * s;            // columns after the last full pair
+        SB_CHECK_ARG((long)t.batch * (full > 0 ? full : 1) <= 65535, "trtri: batch x pairs exceeds grid.z");
+        if (full > 0) SB_TRY(trtri_merge(t, 0, (int)s, (int)s, full, stream));
+        if (rest > s) SB_TRY(trtri_merge(t, (int)(full * 2 * s), (int)s, (int)(rest - s), 1, stream));
     }
     return 0;
 }
@@ -319,8 +348,9 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(int n, const double* __
 }  // namespace
 
 size_t trtri_tmp_elems(int n) {
-    long h = split_point(n);
-    return (size_t)(h * round_up(h, 2));
+    // level s uses full_pairs * s * s (+ rest * s for a ragged pair) <= n^2 / 4 (+ slack for block rounding)
+    long h = (long)n / 2 + NB;
+    return (size_t)(h * h);
 }
 
 int potrf_batched(const CholBatch& c, cudaStream_t stream) {
@@ -334,7 +364,7 @@ int trtri_batched(int batch, int n, const double* L, long ldl_in, long strideLin
                   long strideL, double* tmp, long tmp_stride, cudaStream_t stream) {
     SB_CHECK_ARG(n <= NB || (tmp != nullptr && (size_t)tmp_stride >= trtri_tmp_elems(n)), "trtri: temp too small");
     TrtriCtx t{batch, L, ldl_in, strideLin, Linv, ldl, strideL, tmp, tmp_stride};
-    return trtri_rec(t, 0, n, stream);
+    return trtri_levels(t, n, stream);
 }
 
 int lauum_batched(int batch, int n, const double* Linv, long ldl, long strideL, double* C, long ldc, long strideC,

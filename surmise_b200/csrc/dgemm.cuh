@@ -27,9 +27,13 @@ struct GemmArgs {
     double alpha, beta;
     bool a_kc, b_kc;
     int flags;
+    // optional second batch level: launch index z = z2 * inner_batch + z1; the strides above (and idxA/idxB)
+    // apply to z1, these to z2 (e.g. z1 = matrix of the batch, z2 = diagonal block pair within the matrix)
+    int inner_batch;
+    long strideA2, strideB2, strideC2;
 };
 
-// tile: 0 = 128x128 CTA tile, 1 = 128x64 (narrow N, e.g. panel solves), -1 = pick from N
+// tile: 0 = 128x128 CTA tile (1 CTA/SM), 1 = 128x64 (2 CTAs/SM), 2-4 experimental variants, -1 = default (1)
 int launch_dgemm(const GemmArgs& g, int batch, int tile, cudaStream_t stream);
 
 }  // namespace sb
