@@ -236,6 +236,10 @@ long lda_for(int n) { return round_up(n, 8); }
 
 }  // namespace
 
+// testing hook: route small problems through the blocked (multi-launch) path as well
+static bool g_force_blocked = false;
+void gp_force_blocked_path(int on) { g_force_blocked = on != 0; }
+
 // ------------------------------------------------------------------------------------------------
 size_t gp_nll_grad_workspace(int batch, int n, int d, int want_grad) {
     Workspace w(nullptr, 0);
@@ -262,6 +266,9 @@ int gp_nll_grad(int batch, int n, int d, const double* theta, long strideTheta, 
     SB_CHECK_ARG(d >= 1 && d <= MAXD, "gp_nll_grad: d=%d outside [1,%d]", d, MAXD);
     SB_CHECK_ARG(workspace_bytes >= gp_nll_grad_workspace(batch, n, d, want_grad), "gp_nll_grad: workspace too small");
     SB_CHECK_ARG(!want_grad || grad != nullptr, "gp_nll_grad: grad is NULL");
+    if (n <= gp_nll_small_max_n() && !g_force_blocked)
+        return gp_nll_grad_small(batch, n, d, theta, strideTheta, g, strideG, gvar, strideGvar, hyp, regmean, regstd,
+                                 s0, want_grad, nll, grad, info, stream);
     Workspace w(workspace, workspace_bytes);
     const long lda = lda_for(n);
     const long strideA = (long)(n + 1) * lda;

@@ -147,6 +147,15 @@ def gp_nll_grad(data, hyp, regmean, regstd, sig2ofconst=0.01, want_grad=True, re
     return packed[:, 0], None, packed[:, 1].astype(np.int64)
 
 
+def force_blocked_path(on):
+    """Testing hook: send n <= small_max_n() problems through the blocked multi-launch path too."""
+    lib.sb200_gp_force_blocked_path(int(bool(on)))
+
+
+def small_max_n():
+    return int(lib.sb200_gp_nll_small_max_n())
+
+
 def gp_factorize(data, hyp, sig2ofconst=0.01):
     """Full-data stage of __fitGP1d for a batch (PCGPwM.py:810-846).
 

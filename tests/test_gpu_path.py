@@ -91,6 +91,33 @@ def test_nll_grad_vs_oracle_batched(ops, n, d, nb):
         assert e_v < tol and e_g < 10 * tol
 
 
+@pytest.mark.parametrize('n,d', [(30, 2), (63, 3), (64, 5), (160, 8), (200, 10), (207, 16)])
+def test_nll_small_fused_kernel_equals_blocked_path(ops, n, d):
+    """The single-launch sweep kernel (n <= 207) and the blocked DMMA path are two routes to the same numbers."""
+    assert ops.small_max_n() == 207
+    rng = np.random.default_rng(n)
+    theta = rng.uniform(size=(n, d))
+    G = np.sin(theta @ rng.normal(size=(d, 3))).T + 0.05 * rng.normal(size=(3, n))
+    GV = rng.uniform(size=(3, n)) * (rng.uniform(size=(3, n)) < 0.2) * 0.3
+    mean, LB, UB, std = po.hyper_regulariser(theta, -10, -20)
+    hyps = np.array([mean, LB + 0.4 * (UB - LB), LB + 0.6 * (UB - LB)])
+    hyps[:, -1] = np.maximum(hyps[:, -1], -12)
+    data = ops.GPData(theta, G, GV)
+    a = ops.gp_nll_grad(data, hyps, mean, std, 0.01, True)
+    a0 = ops.gp_nll_grad(data, hyps, mean, std, 0.01, False)
+    ops.force_blocked_path(True)
+    try:
+        b = ops.gp_nll_grad(data, hyps, mean, std, 0.01, True)
+    finally:
+        ops.force_blocked_path(False)
+    assert np.all(a[2] == 0) and np.all(b[2] == 0)
+    assert np.array_equal(a[0], a0[0])
+    e_v = float(np.max(np.abs(a[0] - b[0]) / (np.abs(b[0]) + n)))
+    e_g = rel(a[1], b[1])
+    report('nll_small_vs_blocked', n=n, d=d, nll=e_v, grad=e_g)
+    assert e_v < 1e-10 and e_g < 1e-7
+
+
 def test_nll_per_problem_data_and_breakdown(ops):
     """Different (g, gvar) per problem; an indefinite R must come back as info > 0, not a crash."""
     rng = np.random.default_rng(9)
