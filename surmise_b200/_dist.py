@@ -63,7 +63,7 @@ def block_partition(count, world):
     return sizes, starts
 
 
-def jacobi_sweeps(fit_one, k, p, comm, draw_rows, sweeps=3, start_hyps=None, start_inds=None):
+def jacobi_sweeps(fit_one, k, p, comm, draw_rows, sweeps=3, start_hyps=None, start_inds=None, run_block=None):
     """Sharded variant of PCGPwM.__fitGPs (PCGPwM.py:678-722).
 
     The reference sweeps Gauss-Seidel (PC j sees the PCs fitted earlier in the same sweep); sharding PCs over
@@ -71,6 +71,8 @@ def jacobi_sweeps(fit_one, k, p, comm, draw_rows, sweeps=3, start_hyps=None, sta
     fit_one(j, cand (c,p) or None, cand_ids (c,) or None, rows) -> (hyp (p,), hypind or -1)
     draw_rows(j) -> the random sub-sample for PC j (drawn on rank 0 in PC order, broadcast, so the result
     does not depend on the number of ranks).
+    run_block(list of zero-argument callables) -> list of results: how this rank's PCs are executed; default is
+    one after the other, the GPU plugin passes a lock-step runner that batches their likelihood launches.
     Returns (hyps (k,p), hypinds (k,) int, rows list) identical on every rank.
     """
     sizes, starts = block_partition(k, comm.world)
@@ -92,8 +94,11 @@ def jacobi_sweeps(fit_one, k, p, comm, draw_rows, sweeps=3, start_hyps=None, sta
         leaders = np.where(hypinds == own)[0]
         cand = hyps[leaders] if leaders.size else None
         local = np.zeros((len(mine), p + 1))
+        lead_ids = leaders if leaders.size else None
+        jobs = [(lambda j=j: fit_one(j, cand, lead_ids, drawn[j])) for j in mine]
+        outs = run_block(jobs) if run_block is not None else [job() for job in jobs]
         for t, j in enumerate(mine):
-            hyp, hi = fit_one(j, cand, leaders if leaders.size else None, drawn[j])
+            hyp, hi = outs[t]
             hi = min(j, hi)
             local[t, :p] = hyp
             local[t, p] = j if hi < -0.5 else hi

@@ -1,0 +1,130 @@
+"""Device (torch CUDA) version of the standardisation / imputation / PCA stage of PCGPwM.
+
+Same mathematics as surmise's PCGPwM.__standardizef / __PCs (emulationmethods/PCGPwM.py:533-654) and as the
+host implementation in _pca.py; SURVEY.md section 8(f) row 2.  This stage is not one of the hand-written
+kernels of the hot path: it is expressed with torch.linalg on the device (library eigensolver / batched solve),
+because with missing data it otherwise dominates the whole fit (config C3: 287 s on the host, 41 SVDs of a
+1000 x 4000 matrix plus 160 k ridge systems).
+
+The reference takes the SVD of fs' (m x n) and only ever uses U and S.  Here U and S^2 come from the symmetric
+eigendecomposition of the m x m Gram matrix fs' fs, which is much cheaper and accurate for every component the
+method keeps (S^2 > epsilonPC; relative eigenvalue error ~ eps * S_max^2 / S_k^2 <= 1e-9).  Singular-vector signs
+are arbitrary in both; nothing downstream depends on them.
+"""
+import numpy as np
+
+
+def _torch():
+    from . import _lib
+    return _lib.require_cuda()
+
+
+def _left_singular(fs, torch):
+    """U (m, m) and S (m,) of fs' (descending), from eigh of the Gram matrix."""
+    lam, U = torch.linalg.eigh(fs.T @ fs)
+    lam = torch.flip(lam, [0])
+    U = torch.flip(U, [1])
+    return U, torch.sqrt(torch.clamp(lam, min=0.0)), lam
+
+
+_CHUNK_BYTES = 8 << 30      # bound on the temporaries of one row chunk (early imputation sweeps keep k ~ m PCs)
+
+
+def _row_chunks(nrows, m, k):
+    per_row = 8 * k * max(m, 3 * k)
+    step = max(1, min(nrows, _CHUNK_BYTES // max(per_row, 1)))
+    return [(s, min(s + step, nrows)) for s in range(0, nrows, step)]
+
+
+def _ridge_rows(basis, obs, cur, diag_add, torch, want_qih=False):
+    """Per row r: H = basis' diag(obs_r) basis, J = basis' (obs_r * cur_r), sol = (H + diag_add)^-1 J.
+
+    Returns vec = J - H sol  (nr, k) and, if want_qih, term3 = diag(H) - sum_a H_ab [(H + diag_add)^-1 H]_ab.
+    Rows are processed in chunks so the (chunk, k, k) temporaries stay below _CHUNK_BYTES."""
+    nr, m = obs.shape
+    k = basis.shape[1]
+    vec = torch.empty((nr, k), dtype=torch.float64, device=basis.device)
+    term3 = torch.empty((nr, k), dtype=torch.float64, device=basis.device) if want_qih else None
+    D = torch.diag(diag_add)
+    for lo, hi in _row_chunks(nr, m, k):
+        o = obs[lo:hi]
+        H = torch.matmul((basis.unsqueeze(0) * o.unsqueeze(2)).transpose(1, 2), basis)    # (c, k, k)
+        J = (o * cur[lo:hi]) @ basis
+        A = H + D
+        sol = torch.linalg.solve(A, J.unsqueeze(2)).squeeze(2)
+        vec[lo:hi] = J - torch.einsum('rab,rb->ra', H, sol)
+        if want_qih:
+            QiH = torch.linalg.solve(A, H)
+            term3[lo:hi] = torch.diagonal(H, dim1=1, dim2=2) - torch.einsum('rab,rab->rb', H, QiH)
+    return vec, term3
+
+
+def standardize(f, eps_pc, eps_impute, n_iter=40):
+    """f: (n, m) numpy with NaN/inf for missing.  Returns (standardpcinfo of numpy arrays, mof, mofrows)."""
+    torch = _torch()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    f_np = np.asarray(f, dtype=np.float64)
+    mof_np = ~np.isfinite(f_np)
+    any_missing = bool(mof_np.any())
+    # offset / scale exactly as the reference computes them (PCGPwM.py:553-557), on the host: O(n m)
+    offset_np = np.nanmean(f_np, axis=0)
+    scale_np = np.nanstd(f_np, axis=0) / np.sqrt(1 - np.isnan(f_np).mean(axis=0))
+    if np.any(scale_np == 0):
+        raise ValueError("You have a row that is non-varying.")
+    fs_np = (f_np - offset_np) / scale_np
+    mofrows_np = None
+    if any_missing:
+        mofrows_np = np.where(mof_np.any(axis=1))[0]
+        # initial fill +2, -2, +2, ... minus its mean, in row order within each column (PCGPwM.py:565-571)
+        rank = np.cumsum(mof_np, axis=0) - 1
+        alt = np.where(rank % 2 == 0, 2.0, -2.0)
+        cnt = mof_np.sum(axis=0)
+        col_mean = np.where(cnt > 0, (alt * mof_np).sum(axis=0) / np.maximum(cnt, 1), 0.0)
+        fs_np = np.where(mof_np, alt - col_mean, fs_np)
+    fs = torch.from_numpy(np.ascontiguousarray(fs_np)).to(dev)
+    if any_missing:
+        rows = torch.from_numpy(mofrows_np).to(dev)
+        miss = torch.from_numpy(mof_np[mofrows_np]).to(dev)
+        obs = (~miss).to(torch.float64)
+        for _ in range(n_iter):                                   # PCGPwM.py:573-587
+            U, _S, lam = _left_singular(fs, torch)
+            keep = (lam - eps_pc) > 0
+            Up = U[:, keep]
+            sp2 = lam[keep] - eps_pc
+            cur = fs[rows]
+            vec, _ = _ridge_rows(Up, obs, cur, eps_impute / sp2, torch)
+            filled = vec @ (Up * (sp2 / eps_impute)).T
+            fs[rows] = torch.where(miss, filled, cur)
+    U, S, lam = _left_singular(fs, torch)
+    Up = U[:, (lam - eps_pc) > 0]
+    resid = fs - (fs @ Up) @ Up.T
+    extravar = (resid ** 2).mean(0).cpu().numpy() * scale_np ** 2   # PCGPwM.py:594
+    info = {'offset': offset_np, 'scale': scale_np, 'fs': fs, 'U': U, 'S': S, 'extravar': extravar, '_lam': lam}
+    return info, (mof_np if any_missing else None), mofrows_np
+
+
+def principal_components(spc, mof, mofrows, eps_pc, eps_impute):
+    """PC loadings / scores / per-row imputation variance (PCGPwM.py:608-654) from a device standardpcinfo.
+
+    Returns a dict of numpy arrays and converts spc's device tensors to numpy in place."""
+    torch = _torch()
+    fs, U, lam = spc['fs'], spc['U'], spc.pop('_lam')
+    keep = (lam - eps_pc) > 0
+    basis = U[:, keep]
+    pcw = torch.sqrt(lam[keep] - eps_pc)
+    pcstdvar = torch.zeros((fs.shape[0], basis.shape[1]), dtype=torch.float64, device=fs.device)
+    if mof is not None:
+        rows = torch.from_numpy(mofrows).to(fs.device)
+        obs = torch.from_numpy(~mof[mofrows]).to(fs.device).to(torch.float64)
+        gain = pcw ** 2 / eps_impute + 1
+        vec, term3 = _ridge_rows(basis, obs, fs[rows], eps_impute / pcw ** 2, torch, want_qih=True)
+        fs[rows] = (gain * vec) @ basis.T
+        pcstdvar[rows] = 1 - gain * term3
+    effn = torch.sum(torch.clamp(1 - pcstdvar, 0, 1))
+    pct = basis * pcw / torch.sqrt(effn)
+    out = {'pcw': pcw, 'pcto': basis.clone(), 'pct': pct, 'pcti': basis * (torch.sqrt(effn) / pcw),
+           'pc': fs @ pct, 'unscaled_pcstdvar': pcstdvar}
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    for k in ('fs', 'U', 'S'):
+        spc[k] = spc[k].cpu().numpy()
+    return out

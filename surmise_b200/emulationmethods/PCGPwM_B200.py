@@ -42,13 +42,16 @@ def _ops():
 # ------------------------------------------------------------------------------------------------
 def fit(fitinfo, x, theta, f, epsilonPC=0.001, epsilonImpute=10e-6, lognugmean=-10, lognugLB=-20,
         varconstant=None, dampalpha=0.3, eta=10, standardpcinfo=None, verbose=0, nhyptrain=None,
-        fit_mode='reference', **kwargs):
+        fit_mode='reference', pca='device', **kwargs):
     """Same arguments as PCGPwM.fit (PCGPwM.py:12-137) plus
     nhyptrain : None (reference rule min(20 d, n), PCGPwM.py:744), an int, or 'all'.
     fit_mode  : 'reference' -- the reference's sequential Gauss-Seidel sweeps (PCGPwM.py:691-721), one GPU;
                 'parallel'  -- Jacobi sweeps: every PC sees the previous sweep's leaders, PCs are sharded over
                                the ranks of the initialised torch.distributed group (results do not depend on
                                the number of ranks); see surmise_b200/_dist.py.
+    pca       : 'device' (default) -- standardisation / imputation / PCA on the GPU (_pca_device.py: Gram-matrix
+                eigendecomposition and batched ridge solves); 'host' -- the numpy implementation (_pca.py), which
+                takes the SVD exactly as the reference does.
     """
     ops = _ops()
     ops._torch()                                   # fail loudly without CUDA before any work
@@ -62,19 +65,26 @@ def fit(fitinfo, x, theta, f, epsilonPC=0.001, epsilonImpute=10e-6, lognugmean=-
     fitinfo['f'] = f
     fitinfo['x'] = x
 
-    if standardpcinfo is None:
-        spc, mof, mofrows = _pca.standardize(f, epsilonPC, epsilonImpute)
+    if pca not in ('device', 'host'):
+        raise ValueError("pca must be 'device' or 'host'")
+    if standardpcinfo is None and pca == 'device':
+        from .. import _pca_device
+        spc, mof, mofrows = _pca_device.standardize(f, epsilonPC, epsilonImpute)
+        fitinfo.update(_pca_device.principal_components(spc, mof, mofrows, epsilonPC, epsilonImpute))
     else:
-        spc = _pca.complete_pcinfo(standardpcinfo, f)
-        mof = None if np.all(np.isfinite(f)) else ~np.isfinite(f)
-        mofrows = None if mof is None else np.where(mof.any(axis=1))[0]
+        if standardpcinfo is None:
+            spc, mof, mofrows = _pca.standardize(f, epsilonPC, epsilonImpute)
+        else:
+            spc = _pca.complete_pcinfo(standardpcinfo, f)
+            mof = None if np.all(np.isfinite(f)) else ~np.isfinite(f)
+            mofrows = None if mof is None else np.where(mof.any(axis=1))[0]
+        if 'U' in spc:
+            U, S = spc['U'], spc['S']
+        else:
+            U, S, _vt = np.linalg.svd(spc['fs'].T, full_matrices=False)
+        fitinfo.update(_pca.principal_components(spc['fs'], U, S, mof, mofrows, epsilonPC, epsilonImpute))
     fitinfo['mof'], fitinfo['mofrows'] = mof, mofrows
     fitinfo['standardpcinfo'] = spc
-    if 'U' in spc:
-        U, S = spc['U'], spc['S']
-    else:
-        U, S, _vt = np.linalg.svd(spc['fs'].T, full_matrices=False)
-    fitinfo.update(_pca.principal_components(spc['fs'], U, S, mof, mofrows, epsilonPC, epsilonImpute))
     numpcs = fitinfo['pc'].shape[1]
     if verbose > 0:
         print(fitinfo.get('method', 'PCGPwM_B200'), 'considering ', numpcs, 'PCs')
@@ -136,6 +146,7 @@ class _GPFitter:
         self.mean_dev = torch.from_numpy(self.mean).to(dev)
         self.std_dev = torch.from_numpy(self.std).to(dev)
         self.nevals = 0
+        self._lockstep = None
 
     # -- one PC ---------------------------------------------------------------------------------
     def _draw_rows(self, j=None):
@@ -156,8 +167,11 @@ class _GPFitter:
 
     def _nll(self, data, hyps, want_grad):
         self.nevals += len(hyps)
-        val, grad, info = self.ops.gp_nll_grad(data, np.asarray(hyps), self.mean_dev, self.std_dev,
-                                               SIG2_OF_CONST, want_grad)
+        if self._lockstep is not None:
+            val, grad, info = self._lockstep.evaluate(data, np.asarray(hyps), want_grad)
+        else:
+            val, grad, info = self.ops.gp_nll_grad(data, np.asarray(hyps), self.mean_dev, self.std_dev,
+                                                   SIG2_OF_CONST, want_grad)
         bad = (info != 0) | ~np.isfinite(val)
         val = np.where(bad, _INFEASIBLE, val)
         if grad is not None:
@@ -241,8 +255,42 @@ class _GPFitter:
             hyp, hi, _ = self.fit_one(j, cand, cand_ids, rows)
             return hyp, hi
         hyps, hypinds, rows_used = _dist.jacobi_sweeps(one, k, self.p, comm, self._draw_rows,
-                                                       start_hyps=start_hyps, start_inds=start_inds)
+                                                       start_hyps=start_hyps, start_inds=start_inds,
+                                                       run_block=self._run_block_lockstep if self.lockstep else None)
         return self._finalise(hyps, hypinds, rows_used)       # replicated on every rank (cheap next to the search)
+
+    lockstep = True      # batch the likelihood calls of this rank's PCs into one launch per optimiser step
+
+    def _run_block_lockstep(self, jobs):
+        """Run fit_one for several PCs concurrently (one Python thread each); their likelihood requests are
+        gathered and evaluated by ONE batched kernel launch whenever every live thread is waiting for a value.
+        Per-problem arithmetic is unchanged (one CTA per problem), so results equal the sequential run."""
+        import threading
+        dev = self.theta_dev.device
+        if len(jobs) <= 1:
+            return [fn() for fn in jobs]
+        self._lockstep = _LockstepEvaluator(self, len(jobs))
+        results, errors = [None] * len(jobs), []
+
+        def work(t, fn):
+            try:
+                self.torch.cuda.set_device(dev)
+                results[t] = fn()
+            except BaseException as exc:            # surface worker failures in the caller
+                errors.append(exc)
+            finally:
+                self._lockstep.retire()
+        threads = [threading.Thread(target=work, args=(t, fn)) for t, fn in enumerate(jobs)]
+        try:
+            for th in threads:
+                th.start()
+            for th in threads:
+                th.join()
+        finally:
+            self._lockstep = None
+        if errors:
+            raise errors[0]
+        return results
 
     def _finalise(self, hyps, hypinds, rows_used):
         """Full-data factorisations (PCGPwM.py:810-846), one per distinct (hyp, gvar), in one batch."""
@@ -319,6 +367,65 @@ class _GPFitter:
                 'fu': t(fu, torch.int32), 'fidx': t(self._fidx, torch.int32),
                 'phi': t(phi), 'offset': t(spc['offset']), 'extravar': t(spc['extravar']),
                 'nevals': self.nevals}
+
+
+class _LockstepEvaluator:
+    """Rendezvous of the per-PC optimiser threads: the thread that completes the set of waiting requests
+    launches them all at once (gp_nll_grad is batched over problems with per-problem data)."""
+
+    def __init__(self, fitter, nthreads):
+        import threading
+        self.f = fitter
+        self.cv = threading.Condition()
+        self.live = nthreads
+        self.pending = []
+
+    def evaluate(self, data, hyps, want_grad):
+        req = {'data': data, 'hyps': hyps, 'grad': bool(want_grad), 'out': None}
+        with self.cv:
+            self.pending.append(req)
+            if len(self.pending) >= self.live:
+                self._flush()
+            else:
+                while req['out'] is None:
+                    self.cv.wait()
+        out = req['out']
+        if isinstance(out, BaseException):
+            raise out
+        return out
+
+    def retire(self):
+        with self.cv:
+            self.live -= 1
+            if self.live > 0 and len(self.pending) >= self.live:
+                self._flush()
+
+    def _flush(self):
+        """Caller holds the lock.  One launch per gradient flag over all pending problems."""
+        f, torch = self.f, self.f.torch
+        reqs, self.pending = self.pending, []
+        try:
+            for flag in (False, True):
+                group = [r for r in reqs if r['grad'] == flag]
+                if not group:
+                    continue
+                counts = [r['hyps'].shape[0] for r in group]
+                theta = torch.cat([r['data'].theta.expand(c, -1, -1) if r['data'].theta.dim() == 2
+                                   else r['data'].theta for r, c in zip(group, counts)], 0)
+                g = torch.cat([r['data'].g.expand(c, -1) for r, c in zip(group, counts)], 0)
+                gv = torch.cat([r['data'].gvar.expand(c, -1) for r, c in zip(group, counts)], 0)
+                data = f.ops.GPData(theta, g, gv)
+                hyps = np.concatenate([r['hyps'] for r in group], 0)
+                val, grad, info = f.ops.gp_nll_grad(data, hyps, f.mean_dev, f.std_dev, SIG2_OF_CONST, flag)
+                lo = 0
+                for r, c in zip(group, counts):
+                    r['out'] = (val[lo:lo + c], None if grad is None else grad[lo:lo + c], info[lo:lo + c])
+                    lo += c
+        except BaseException as exc:
+            for r in reqs:
+                if r['out'] is None:
+                    r['out'] = exc
+        self.cv.notify_all()
 
 
 def import_state(theta, pc, gvar_damped, hyps, hypinds, pcti, spc):

@@ -211,3 +211,65 @@ def test_calibration_fit_through_sampler_contract(monkeypatch):
     assert C.thetarnd(cal, 7).shape == (7, 2)
     with pytest.raises(ValueError):
         C.loglik({}, emu, cal['thetarnd'][:2], y, x)                # yvar is mandatory (dbw.py:266-269)
+
+
+def test_lockstep_batching_equals_sequential_jacobi():
+    """Batching the per-PC optimisers' likelihood calls into one launch must not change any number."""
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    x, theta, f, truth = make_simulator(260, 3, 30, 6, seed=17)
+    outs = []
+    for lock in (True, False):
+        M._GPFitter.lockstep = lock
+        try:
+            np.random.seed(17)
+            fi = _facade_fit(M, x, theta, f, fit_mode='parallel')
+        finally:
+            M._GPFitter.lockstep = True
+        outs.append((np.array([e['hyp'] for e in fi['emulist']]), [e['hypind'] for e in fi['emulist']],
+                     fi['_b200']['nevals']))
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+    assert outs[0][2] == outs[1][2]
+
+
+def test_device_pca_matches_host_pca(golden):
+    """Imputation / PCA on the device (Gram eigh + batched solves) against the host implementation and, through it,
+    the reference internals (PCGPwM.py:533-654).  The 40 ridge iterations amplify rounding (the reference's own
+    GEMM-vs-SYRK choice moves fs by 2e-5), hence the tolerances; complete data is tight."""
+    from surmise_b200 import _pca, _pca_device
+    g = golden('standardize')
+    spc_d, mof, rows = _pca_device.standardize(g['f'].T, 0.001, 10e-6)
+    pcs_d = _pca_device.principal_components(spc_d, mof, rows, 0.001, 10e-6)
+    assert pcs_d['pc'].shape == g['pc'].shape
+    sign = np.sign(np.sum(pcs_d['pc'] * g['pc'], 0))
+    e_fs = float(np.max(np.abs(spc_d['fs'] - g['fs'])))
+    e_pc = float(np.max(np.abs(pcs_d['pc'] * sign - g['pc'])) / np.max(np.abs(g['pc'])))
+    e_ev = float(np.max(np.abs(spc_d['extravar'] - g['extravar'])) / np.max(g['extravar']))
+    e_sv = float(np.max(np.abs(pcs_d['unscaled_pcstdvar'] - g['unscaled_pcstdvar'])))
+    report('device_pca_missing', fs=e_fs, pc=e_pc, extravar=e_ev, pcstdvar=e_sv)
+    assert e_fs < 1e-3 and e_pc < 1e-3 and e_ev < 1e-3 and e_sv < 1e-2
+    c = golden('emu_c1')
+    spc_c, mof, rows = _pca_device.standardize(c['in_f'].T, 0.001, 10e-6)
+    assert mof is None
+    pcs_c = _pca_device.principal_components(spc_c, None, None, 0.001, 10e-6)
+    sign = np.sign(np.sum(pcs_c['pc'] * c['st_pc'], 0))
+    e_pc = float(np.max(np.abs(pcs_c['pc'] * sign - c['st_pc'])) / np.max(np.abs(c['st_pc'])))
+    e_ti = float(np.max(np.abs(pcs_c['pcti'] * sign - c['st_pcti'])) / np.max(np.abs(c['st_pcti'])))
+    e_ev = float(np.max(np.abs(spc_c['extravar'] - c['st_extravar'])) / np.max(c['st_extravar']))
+    report('device_pca_complete', pc=e_pc, pcti=e_ti, extravar=e_ev)
+    assert e_pc < 1e-9 and e_ti < 1e-9 and e_ev < 1e-6
+
+
+def test_fit_host_pca_option_agrees_with_device_pca():
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    x, theta, f, truth = make_simulator(150, 2, 30, 4, seed=7, missing=0.10)
+    tn = np.random.default_rng(1).uniform(0.1, 0.9, size=(20, 2))
+    means = []
+    for mode in ('device', 'host'):
+        np.random.seed(7)
+        fi = _facade_fit(M, x, theta, f, pca=mode)
+        p = {}
+        M.predict(p, fi, x, tn)
+        means.append(p['mean'])
+    assert rel(means[0], means[1]) < 1e-2
+    with pytest.raises(ValueError):
+        _facade_fit(M, x, theta, f, pca='nowhere')
