@@ -151,7 +151,7 @@ __device__ __forceinline__ void stage_scaled_n(double* dst, const double* __rest
     }
 }
 
-__global__ void __launch_bounds__(256) gp_grad_contract_kernel(int n, int d, const double* __restrict__ thetab,
+__global__ void __launch_bounds__(256, 2) gp_grad_contract_kernel(int n, int d, const double* __restrict__ thetab,
                                                                long strideTheta, const double* __restrict__ gvarb,
                                                                long strideGvar, const double* __restrict__ hypb,
                                                                const double* __restrict__ Rinvb, long ldr, long strideR,
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) gp_grad_contract_kernel(int n, int d, con
                     double op = 1.0 + S;
                     prod *= op;
                     ssum -= S;
-                    wsum[k] = (S * S) / op;                        // dR0/dgamma_k / R_pre
+                    wsum[k] = (S * S) * __drcp_rn(op);             // dR0/dgamma_k / R_pre
                 }
             double rp = prod * exp(ssum);
             double wr = w * omn * rp;
