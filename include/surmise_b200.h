@@ -128,6 +128,7 @@ int sb200_dgemm(int a_kc, int b_kc, int M, int N, int K, double alpha, const dou
 int sb200_potrf_batched(int batch, int n, int mrows, double* A, long lda, long stride_a, double* Linv, long ldl,
                         long stride_linv, int* info, void* stream);
 size_t sb200_trtri_tmp_elems(int n);
+void sb200_debug_panel_stamps(long long* device_ptr);   /* instrumentation: clock64 stamps of the panel kernel's phases */
 int sb200_trtri_batched(int batch, int n, const double* L, long lda, long stride_a, double* Linv, long ldl,
                         long stride_linv, double* tmp, size_t tmp_elems_per_matrix, void* stream);
 int sb200_lauum_batched(int batch, int n, const double* Linv, long ldl, long stride_linv, double* C, long ldc,

@@ -528,3 +528,34 @@ def predict(predinfo, fitinfo, x, theta, return_grad=False, return_covx=True, xi
         if return_covx:
             dsq = 0.5 * dpvar / np.sqrt(pvar)[:, :, None]        # (B,k,d)
             predinfo['covxhalf_gradtheta'] = np.einsum('bkd,xk->xbkd', dsq, phi)
+
+
+def predictlpdf(predinfo, f, addvar=0):
+    """Log predictive density of simulator output f (m, B) given a predict() result   (PCGPwM.py:331-364)."""
+    totvar = addvar + predinfo['extravar']
+    isd = 1 / np.sqrt(totvar)
+    rf = (f - predinfo['mean']) * isd[:, None]
+    Gf = predinfo['phi'].T * isd
+    Gfrf = Gf @ rf
+    Gf2 = Gf @ Gf.T
+    likv = np.sum(rf ** 2, 0)
+    grad = predinfo['return_grad']
+    B = predinfo['predvars'].shape[0]
+    if grad:
+        rf2 = -predinfo['mean_gradtheta'] * isd[:, None, None]                 # (m, B, d)
+        Gfrf2 = np.einsum('km,mbd->kbd', Gf, rf2)
+        dlikv = 2 * np.einsum('mbd,mb->bd', rf2, rf)
+    for c in range(B):
+        v = predinfo['predvars'][c]
+        w, V = np.linalg.eig(np.diag(1 / v) + Gf2)
+        t1 = (V * (1 / w)) @ (V.T @ Gfrf[:, c])
+        likv[c] += -Gfrf[:, c] @ t1 + np.sum(np.log(v)) + np.sum(np.log(w))
+        if grad:
+            Si = (V * (1 / w)) @ V.T
+            dv = predinfo['predvars_gradtheta'][c]                              # (k, d)
+            grt = dv / v[:, None]
+            dlikv[c] += np.sum(grt, 0) + np.diag(Si) @ (-grt / v[:, None]) - 2 * Gfrf2[:, c, :].T @ t1 \
+                - ((t1 / v) ** 2) @ dv
+    if grad:
+        return (-likv / 2).reshape(-1, 1), -dlikv / 2
+    return (-likv / 2).reshape(-1, 1)

@@ -46,6 +46,7 @@ SIGNATURES = {
     'sb200_dgemm': (_i, [_i, _i, _i, _i, _i, _d, _p, _l, _l, _p, _l, _l, _d, _p, _l, _l, _i, _i, _i, _p]),
     'sb200_potrf_batched': (_i, [_i, _i, _i, _p, _l, _l, _p, _l, _l, _p, _p]),
     'sb200_trtri_tmp_elems': (_z, [_i]),
+    'sb200_debug_panel_stamps': (None, [_p]),
     'sb200_trtri_batched': (_i, [_i, _i, _p, _l, _l, _p, _l, _l, _p, _z, _p]),
     'sb200_lauum_batched': (_i, [_i, _i, _p, _l, _l, _p, _l, _l, _p]),
 }

@@ -179,6 +179,7 @@ int sb200_potrf_batched(int batch, int n, int mrows, double* A, long lda, long s
 }
 
 size_t sb200_trtri_tmp_elems(int n) { return trtri_tmp_elems(n); }
+void sb200_debug_panel_stamps(long long* device_ptr) { debug_panel_stamps(device_ptr); }
 
 int sb200_trtri_batched(int batch, int n, const double* L, long lda, long stride_a, double* Linv, long ldl,
                         long stride_linv, double* tmp, size_t tmp_elems_per_matrix, void* stream) {

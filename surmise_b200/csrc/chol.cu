@@ -32,7 +32,8 @@ __device__ __forceinline__ void cp_async8_plain(double* smem, const double* gmem
 __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ Abase, long lda, long strideA,
                                                           double* __restrict__ Dbase, long ldd, long strideD, int nb,
                                                           int j0, int below, int rows_per_cta,
-                                                          int* __restrict__ info, int* __restrict__ counters) {
+                                                          int* __restrict__ info, int* __restrict__ counters,
+                                                          long long* stamps) {
     extern __shared__ double sm[];
     double* S = sm;                       // [NB][SLD]  block, then L
     double* X = S + NB * SLD;             // [NB][SLD]  L^-1
@@ -40,6 +41,8 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
     double* colbuf = T + PT * SLD;        // [2][NB]
     double* invd = colbuf + 2 * NB;       // [NB]
     const int tid = threadIdx.x, z = blockIdx.y;
+#define SB_STAMP(slot) do { if (stamps && z == 0 && blockIdx.x == 0 && tid == 0) stamps[slot] = clock64(); } while (0)
+    SB_STAMP(0);
     double* A = Abase + (long)z * strideA;          // points at the diagonal block (j0, j0)
     const int cta_r0 = blockIdx.x * rows_per_cta;   // first panel row of this CTA (relative to the row below the block)
     const int cta_rows = min(rows_per_cta, below - cta_r0);     // <= 0 when there is nothing below
@@ -70,6 +73,7 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
             else if (i >= nb && c == i) v = 1.0;
             a[ii][cc] = v;
         }
+    SB_STAMP(1);
     // The block is factored in place by whichever CTA of this matrix loaded it LAST (all CTAs compute the
     // same L), so no CTA can still be reading A's block when it is overwritten.  No spinning: a counter.
     __shared__ int s_writer;
@@ -122,6 +126,7 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
             if (ti == jr && tc == jr) invd[j] = inv;
         }
     }
+    SB_STAMP(2);
 #pragma unroll
     for (int ii = 0; ii < 4; ii++)
 #pragma unroll
@@ -134,6 +139,7 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
     const bool writer = s_writer != 0;
     if (writer && tid == 0 && bad_at != 0 && info[z] == 0) info[z] = bad_at;
 
+    SB_STAMP(3);
     // ---- phase 2: X = L^-1; thread (c, q) owns rows q, q+4, ... of column c
     {
         const int c = tid >> 2, q = tid & 3, lane = tid & 31;
@@ -158,6 +164,7 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
         }
     }
     __syncthreads();
+    SB_STAMP(4);
     if (writer) {
         double* D = Dbase + (long)z * strideD;
         for (int idx = tid; idx < nb * nb; idx += 256) {
@@ -166,6 +173,7 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
             D[(long)i * ldd + c] = X[i * SLD + c];
         }
     }
+    SB_STAMP(5);
     if (cta_rows <= 0) return;
 
     // ---- phase 3: P <- P X'  (DMMA from shared memory), 128 rows at a time; warp w owns rows 16w .. 16w+15
@@ -211,7 +219,11 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
             }
         }
     }
+    SB_STAMP(6);
+#undef SB_STAMP
 }
+
+long long* g_panel_stamps = nullptr;      // instrumentation (sb200_debug_panel_stamps)
 
 int panel(const CholBatch& c, int j0, int nb, cudaStream_t stream) {
     constexpr size_t smem = (size_t)(2 * NB * SLD + PT * SLD + 3 * NB) * sizeof(double);
@@ -231,7 +243,7 @@ int panel(const CholBatch& c, int j0, int nb, cudaStream_t stream) {
     dim3 grid(below > 0 ? cdiv(below, rows_per_cta) : 1, c.batch);
     potrf_panel_kernel<<<grid, 256, smem, stream>>>(c.A + (long)j0 * c.lda + j0, c.lda, c.strideA,
                                                     c.Dinv + (long)(j0 / NB) * c.blockD, c.ldd, c.strideD, nb, j0,
-                                                    below, rows_per_cta, c.info, c.counters);
+                                                    below, rows_per_cta, c.info, c.counters, g_panel_stamps);
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -346,6 +358,8 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(int n, const double* __
 }
 
 }  // namespace
+
+void debug_panel_stamps(long long* p) { g_panel_stamps = p; }
 
 size_t trtri_tmp_elems(int n) {
     // level s uses full_pairs * s * s (+ rest * s for a ragged pair) <= n^2 / 4 (+ slack for block rounding)

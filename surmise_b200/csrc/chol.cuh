@@ -42,5 +42,6 @@ int trmv_lower_batched(int batch, int n, const double* Linv, long ldl, long stri
                        const double* x, long strideX, double* out, long strideOut, cudaStream_t stream);
 
 size_t trtri_tmp_elems(int n);
+void debug_panel_stamps(long long* device_ptr);   // instrumentation: 8 clock64 slots written by CTA (0,0) of each panel launch
 
 }  // namespace sb

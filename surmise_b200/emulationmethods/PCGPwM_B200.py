@@ -527,6 +527,33 @@ def predict(predinfo, fitinfo, x, theta, **kwargs):
     return
 
 
+def predictlpdf(predinfo, f, addvar=0, **kwargs):
+    """Log predictive density of simulator output f (m, B) at the predicted (x, theta); same contract as
+    PCGPwM.predictlpdf (PCGPwM.py:331-364): (B,1), plus the gradient (B,d) when predict ran with return_grad.
+
+    Host numpy on the small PC-space quantities of `predinfo` (k x k systems per theta, batched)."""
+    totvar = addvar + predinfo['extravar']
+    isd = 1 / np.sqrt(totvar)
+    rf = (np.asarray(f, dtype=np.float64) - predinfo['mean']) * isd[:, None]        # (m, B)
+    Gf = predinfo['phi'].T * isd                                                       # (k, m)
+    Gfrf = (Gf @ rf).T                                                                 # (B, k)
+    v = predinfo['predvars']                                                           # (B, k)
+    M = Gf @ Gf.T + np.einsum('bk,kl->bkl', 1 / v, np.eye(v.shape[1]))                # diag(1/v_b) + Gf Gf'
+    Minv = np.linalg.inv(M)
+    t1 = np.einsum('bkl,bl->bk', Minv, Gfrf)
+    _sign, logdet = np.linalg.slogdet(M)
+    likv = np.sum(rf ** 2, 0) - np.sum(Gfrf * t1, 1) + np.sum(np.log(v), 1) + logdet
+    if not predinfo['return_grad']:
+        return (-likv / 2).reshape(-1, 1)
+    rf2 = -predinfo['mean_gradtheta'] * isd[:, None, None]                            # (m, B, d)
+    dv = predinfo['predvars_gradtheta']                                                # (B, k, d)
+    grt = dv / v[:, :, None]
+    dlikv = 2 * np.einsum('mbd,mb->bd', rf2, rf) + grt.sum(1) \
+        - np.einsum('bk,bkd->bd', np.einsum('bkk->bk', Minv) / v, grt) \
+        - 2 * np.einsum('km,mbd,bk->bd', Gf, rf2, t1) - np.einsum('bk,bkd->bd', (t1 / v) ** 2, dv)
+    return (-likv / 2).reshape(-1, 1), -dlikv / 2
+
+
 def _param_desc(fitinfo):
     """Human-readable summary used by emulator.__repr__ (PCGPwM.py:938-964)."""
     el = fitinfo['emulist']

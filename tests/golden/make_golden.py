@@ -150,6 +150,12 @@ def golden_emulator(tag, n, d, m, k, seed, missing, nB, fit_args=None, yvar_scal
     # at-design predictions (cancellation regime), first 8 design points
     pdz = emu.predict(x, theta[:8])._info
     out.update({'design_predvecs': pdz['predvecs'], 'design_predvars': pdz['predvars']})
+    # predictive log-density of new simulator output (PCGPwM.predictlpdf, PCGPwM.py:331-364)
+    flp = truth(thetanew) + 0.01 * np.random.default_rng(seed + 7).normal(size=(x.shape[0], nB))
+    lp, dlp = ref_pcgpwm.predictlpdf(pi, flp, addvar=0.003)
+    out.update({'lpdf_f': flp, 'lpdf': lp, 'dlpdf': dlp})
+    olp, odlp = po.predictlpdf(opred, flp, addvar=0.003)
+    print(tag, 'oracle predictlpdf', rel(olp, lp), rel(odlp, dlp))
     # calibration log-likelihood
     theta_true, y, yvar = make_observation(truth, d, seed=seed + 1)
     yvar = yvar * yvar_scale

@@ -273,3 +273,30 @@ def test_fit_host_pca_option_agrees_with_device_pca():
     assert rel(means[0], means[1]) < 1e-2
     with pytest.raises(ValueError):
         _facade_fit(M, x, theta, f, pca='nowhere')
+
+
+def test_fitted_state_survives_pickle_and_predictlpdf_runs():
+    """emu.save_to / load_from pickle the whole _info dict (helper.py:9-23): the device state must round-trip."""
+    import pickle
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    x, theta, f, truth = make_simulator(120, 2, 20, 3, seed=31)
+    np.random.seed(31)
+    fi = _facade_fit(M, x, theta, f)
+    tn = np.random.default_rng(3).uniform(0.1, 0.9, size=(9, 2))
+    p0 = {}
+    M.predict(p0, fi, x, tn, return_grad=True)
+    fi2 = pickle.loads(pickle.dumps(fi))
+    p1 = {}
+    M.predict(p1, fi2, x, tn, return_grad=True)
+    assert np.array_equal(p0['mean'], p1['mean']) and np.array_equal(p0['covxhalf_gradtheta'], p1['covxhalf_gradtheta'])
+    lp, dlp = M.predictlpdf(p1, truth(tn), addvar=0.01)
+    assert lp.shape == (9, 1) and dlp.shape == (9, 2) and np.all(np.isfinite(lp))
+    h = 1e-6                                                    # finite-difference check of the lpdf gradient
+    tp = tn.copy()
+    tp[:, 1] += h
+    p2 = {}
+    M.predict(p2, fi, x, tp)
+    p2['return_grad'] = False
+    fd = (M.predictlpdf(p2, truth(tn), addvar=0.01) - lp)[:, 0] / h
+    # the reference's analytic lpdf gradient (reproduced here) is only approximately the derivative of its lpdf
+    assert rel(fd, dlp[:, 1]) < 5e-2

@@ -123,3 +123,23 @@ def test_register_into_surmise_if_installed():
         with pytest.raises(Exception) as e:
             emulator(x, theta, f, method='PCGPwM_B200')
         assert 'CUDA' in str(e.value) or 'cuda' in str(e.value)
+
+
+@pytest.mark.parametrize('tag', ['c1', 'misspd', 'trig', 'd1'])
+def test_predictlpdf_matches_reference(golden, tag):
+    """PCGPwM_B200.predictlpdf (host, batched) on the reference's own predict output vs the reference's value
+    (PCGPwM.py:331-364); the oracle's loop form is checked against the same fixture."""
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    from oracle import pcgpwm_oracle as po
+    g = golden('emu_' + tag)
+    phi = g['st_pcti'] * g['st_scale'][:, None]
+    pi = {'mean': g['mean'], 'extravar': g['st_extravar'], 'phi': phi, 'predvars': g['predvars'],
+          'mean_gradtheta': g['mean_grad'], 'predvars_gradtheta': g['predvars_grad'], 'return_grad': True}
+    for impl in (M.predictlpdf, po.predictlpdf):
+        lp, dlp = impl(pi, g['lpdf_f'], addvar=0.003)
+        assert lp.shape == g['lpdf'].shape and dlp.shape == g['dlpdf'].shape
+        # the value is a difference of O(m) terms (sum rf^2, log-determinants): scale the bar accordingly
+        assert np.max(np.abs(lp - g['lpdf']) / (np.abs(g['lpdf']) + g['mean'].shape[0])) < 1e-11
+        assert np.max(np.abs(dlp - g['dlpdf'])) / np.max(np.abs(g['dlpdf'])) < 1e-9
+    pi['return_grad'] = False
+    assert np.allclose(M.predictlpdf(pi, g['lpdf_f'], addvar=0.003), g['lpdf'], rtol=1e-9, atol=1e-9)
