@@ -273,6 +273,13 @@ def main():
     if rank == 0 and not args.skip_secondary:
         secondary = secondary_metrics(w, dev, torch, ops, world)
     barrier()
+    if world > 1 and not args.skip_secondary:
+        # calibration throughput over the box: every rank evaluates its own slice of a theta population
+        # (independent proposals); whole-job value = sum over ranks / max time over ranks
+        tot = calibration_scaling(w, dev, torch, dist, world)
+        if rank == 0:
+            secondary['theta_loglik_evals_per_s_all_ranks'] = tot
+    barrier()
 
     if rank == 0:
         evals = k * world
@@ -317,6 +324,42 @@ def main():
         dist.destroy_process_group()
 
 
+def calibration_scaling(w, dev, torch, dist, world):
+    """Log-likelihood (+gradient) evaluations/s summed over ranks: each rank fits the same C2 emulator (replicated
+    factors) and evaluates its own B/world slice of a population of B = 2048 * world proposals."""
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
+    from synth import make_observation
+    np.random.seed(0)
+    fi = {'method': 'PCGPwM_B200'}
+    M.fit(fi, w['x'], w['theta'], w['f'], fit_mode='parallel', distributed=False)
+    _, y, yvar = make_observation(w['truth'], w['theta'].shape[1], seed=3)
+
+    class Emu:
+        _info = fi
+    cal = {'yvar': yvar}
+    B = 2048
+    th = torch.from_numpy(np.random.default_rng(100 + dist.get_rank()).uniform(size=(B, w['theta'].shape[1]))).to(dev)
+    out = {}
+    for grad in (False, True):
+        for _ in range(3):
+            C.loglik_device(cal, Emu, th, y, w['x'], return_grad=grad)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            C.loglik_device(cal, Emu, th, y, w['x'], return_grad=grad)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        out['grad' if grad else 'nograd'] = {'value': world * B / (float(ms.item()) * 1e-3), 'unit': 'theta/s',
+                                             'B_per_rank': B, 'distinct_factors': int(fi['_b200']['Linv'].shape[0])}
+    return out
+
+
 def secondary_metrics(w, dev, torch, ops, world):
     """BASELINE.json's other two metrics on the same C2 problem, rank 0, one GPU."""
     from surmise_b200.emulationmethods import PCGPwM_B200 as M
@@ -337,7 +380,7 @@ def secondary_metrics(w, dev, torch, ops, world):
         np.random.seed(rep)
         fp = {'method': 'PCGPwM_B200'}
         t0 = time.perf_counter()
-        M.fit(fp, w['x'], w['theta'], w['f'], fit_mode='parallel')
+        M.fit(fp, w['x'], w['theta'], w['f'], fit_mode='parallel', distributed=False)
         torch.cuda.synchronize()
         pfits.append(time.perf_counter() - t0)
     tn = np.random.default_rng(5).uniform(0.05, 0.95, size=(256, w['theta'].shape[1]))

@@ -34,6 +34,7 @@ const char* sb200_last_error(void);
 long sb200_launch_count(void);
 void sb200_gemm_profile_enable(int on);
 int sb200_gemm_profile_collect(double* total_ms, double* total_flops);
+int sb200_gemm_profile_dump(double* ms, double* flops, int cap);   /* per launch, host arrays */
 
 /* Replaces surmise.emulationsupport.matern_covmat.covmat (emulationsupport/matern_covmat.pyx:27-64,
  * map4 at :13-24).  R[i][j] (n1 x n2, leading dimension ldr) is the separable Matern-3/2 correlation

@@ -14,8 +14,10 @@ import numpy as np
 class Comm:
     """Thin view of the default torch.distributed group (or a single-process stand-in)."""
 
-    def __init__(self):
+    def __init__(self, enabled=True):
         self.rank, self.world, self.dist = 0, 1, None
+        if not enabled:
+            return
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():

@@ -43,6 +43,26 @@ long sb200_launch_count(void) { return sb::g_launches.load(); }
 
 void sb200_gemm_profile_enable(int on) { sb::g_prof_on.store(on != 0); }
 
+// Per-launch variant of sb200_gemm_profile_collect: fills ms[i], flops[i] for up to cap launches (in launch order),
+// returns the number of launches recorded; clears the record.
+int sb200_gemm_profile_dump(double* ms, double* flops, int cap) {
+    std::lock_guard<std::mutex> lk(sb::g_prof_mu);
+    int n = 0;
+    for (auto& smp : sb::g_prof) {
+        float t = 0.f;
+        bool ok = cudaEventSynchronize(smp.b) == cudaSuccess && cudaEventElapsedTime(&t, smp.a, smp.b) == cudaSuccess;
+        if (ok && n < cap) {
+            ms[n] = t;
+            flops[n] = smp.flops;
+            n++;
+        }
+        cudaEventDestroy(smp.a);
+        cudaEventDestroy(smp.b);
+    }
+    sb::g_prof.clear();
+    return n;
+}
+
 // Synchronises the recorded events, returns the number of DMMA GEMM launches booked since the last call and
 // their summed device time (ms) and algorithmic flop; clears the record.
 int sb200_gemm_profile_collect(double* total_ms, double* total_flops) {

@@ -97,7 +97,11 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 1
 
     const int tid = threadIdx.x;
     const int z = blockIdx.z;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    // longest-k tiles first: with a lower-triangular A the k-range grows with m, so walk the row tiles backwards
+    // (lower-triangular B / upper-triangular A and B already start with their longest tiles)
+    const int tile_m = (p.flags & GEMM_A_LOWER) ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y;
+    const int tile_n = (p.flags & GEMM_B_LOWER) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
+    const int m0 = tile_m * BM, n0 = tile_n * BN;
     const int m_end = min(p.M, m0 + BM), n_end = min(p.N, n0 + BN);
     if ((p.flags & GEMM_C_LOWER) && n0 > m_end - 1) return;
 

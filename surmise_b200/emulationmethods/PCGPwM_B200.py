@@ -42,13 +42,15 @@ def _ops():
 # ------------------------------------------------------------------------------------------------
 def fit(fitinfo, x, theta, f, epsilonPC=0.001, epsilonImpute=10e-6, lognugmean=-10, lognugLB=-20,
         varconstant=None, dampalpha=0.3, eta=10, standardpcinfo=None, verbose=0, nhyptrain=None,
-        fit_mode='reference', pca='device', **kwargs):
+        fit_mode='reference', pca='device', distributed=True, **kwargs):
     """Same arguments as PCGPwM.fit (PCGPwM.py:12-137) plus
     nhyptrain : None (reference rule min(20 d, n), PCGPwM.py:744), an int, or 'all'.
     fit_mode  : 'reference' -- the reference's sequential Gauss-Seidel sweeps (PCGPwM.py:691-721), one GPU;
                 'parallel'  -- Jacobi sweeps: every PC sees the previous sweep's leaders, PCs are sharded over
                                the ranks of the initialised torch.distributed group (results do not depend on
                                the number of ranks); see surmise_b200/_dist.py.
+    distributed : with fit_mode='parallel', shard the PCs over the torch.distributed group if one is initialised
+                (every rank must then call fit with the same data); False keeps the fit on this process only.
     pca       : 'device' (default) -- standardisation / imputation / PCA on the GPU (_pca_device.py: Gram-matrix
                 eigendecomposition and batched ridge solves); 'host' -- the numpy implementation (_pca.py), which
                 takes the SVD exactly as the reference does.
@@ -91,6 +93,7 @@ def fit(fitinfo, x, theta, f, epsilonPC=0.001, epsilonImpute=10e-6, lognugmean=-
 
     logvarc = np.log(varconstant) if varconstant is not None else None
     fitter = _GPFitter(fitinfo, theta, lognugmean, lognugLB, logvarc, nhyptrain)
+    fitter.distributed = bool(distributed)
     if fit_mode not in ('reference', 'parallel'):
         raise ValueError("fit_mode must be 'reference' or 'parallel'")
     emulist = (fitter.run if fit_mode == 'reference' else fitter.run_parallel)(previous=fitinfo.get('emulist'))
@@ -244,7 +247,7 @@ class _GPFitter:
     def run_parallel(self, previous=None):
         """Jacobi sweeps with the PCs sharded over torch.distributed ranks (see _dist.jacobi_sweeps)."""
         from .. import _dist
-        comm = _dist.Comm()
+        comm = _dist.Comm(enabled=getattr(self, 'distributed', True))
         k = self.pc.shape[1]
         start_hyps = start_inds = None
         if previous is not None and previous[0]['hyp'].shape[0] == self.p and len(previous) >= k:
