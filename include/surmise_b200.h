@@ -49,15 +49,15 @@ int sb200_matern_covmat(const double* x1, int n1, const double* x2, int n2, int 
  * theta (n,d), g (n), gvar (n, may be NULL) with per-problem strides in elements (0 = shared);
  * hyp (batch, d+3) = [gamma_0..gamma_d, log var-const, logit nugget]; regmean/regstd (d+3) shared.
  * Outputs nll (batch), grad (batch, d+3; only if want_grad), info (batch).
- * Problems with n <= sb200_gp_nll_small_max_n() (207) run as ONE launch, one CTA per problem (register-resident
- * sweep operator); larger ones use the blocked DMMA path.  sb200_gp_force_blocked_path(1) sends everything through
+ * Problems with n <= sb200_gp_nll_small_max_n() (207) take three launches (assemble, register-resident sweep
+ * operator with one CTA per problem, gradient contraction); larger ones use the blocked DMMA path.  sb200_gp_force_blocked_path(1) sends everything through
  * the blocked path (testing). */
 int sb200_gp_nll_small_max_n(void);
 void sb200_gp_force_blocked_path(int on);
 /* instrumentation: as sb200_gp_nll_grad on shared theta/g without gvar, plus clock64() stamps (8 slots) of CTA 0 */
 int sb200_gp_nll_small_profile(int batch, int n, int d, const double* theta, const double* g, const double* hyp,
                                const double* regmean, const double* regstd, double* nll, double* grad, int* info,
-                               long long* stamps, void* stream);
+                               long long* stamps, void* workspace, size_t workspace_bytes, void* stream);
 size_t sb200_gp_nll_grad_workspace(int batch, int n, int d, int want_grad);
 int sb200_gp_nll_grad(int batch, int n, int d, const double* theta, long stride_theta, const double* g,
                       long stride_g, const double* gvar, long stride_gvar, const double* hyp,

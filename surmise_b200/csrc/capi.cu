@@ -106,14 +106,14 @@ int sb200_gp_nll_grad(int batch, int n, int d, const double* theta, long stride_
 }
 
 void sb200_gp_force_blocked_path(int on) { gp_force_blocked_path(on); }
+int sb200_gp_nll_small_max_n(void) { return gp_nll_small_max_n(); }
 
 int sb200_gp_nll_small_profile(int batch, int n, int d, const double* theta, const double* g, const double* hyp,
                                const double* regmean, const double* regstd, double* nll, double* grad, int* info,
-                               long long* stamps, void* stream) {
+                               long long* stamps, void* workspace, size_t workspace_bytes, void* stream) {
     return gp_nll_grad_small(batch, n, d, theta, 0, g, 0, nullptr, 0, hyp, regmean, regstd, 0.01, 1, nll, grad, info,
-                             ST(stream), stamps);
+                             workspace, workspace_bytes, ST(stream), stamps);
 }
-int sb200_gp_nll_small_max_n(void) { return gp_nll_small_max_n(); }
 
 size_t sb200_gp_factorize_workspace(int batch, int n) { return gp_factorize_workspace(batch, n); }
 int sb200_gp_factorize(int batch, int n, int d, const double* theta, long stride_theta, const double* g,

@@ -242,6 +242,7 @@ void gp_force_blocked_path(int on) { g_force_blocked = on != 0; }
 
 // ------------------------------------------------------------------------------------------------
 size_t gp_nll_grad_workspace(int batch, int n, int d, int want_grad) {
+    if (n <= gp_nll_small_max_n() && !g_force_blocked) return gp_nll_small_workspace(batch, n, want_grad);
     Workspace w(nullptr, 0);
     long lda = lda_for(n);
     w.take<double>((size_t)batch * (n + 1) * lda);
@@ -268,7 +269,7 @@ int gp_nll_grad(int batch, int n, int d, const double* theta, long strideTheta, 
     SB_CHECK_ARG(!want_grad || grad != nullptr, "gp_nll_grad: grad is NULL");
     if (n <= gp_nll_small_max_n() && !g_force_blocked)
         return gp_nll_grad_small(batch, n, d, theta, strideTheta, g, strideG, gvar, strideGvar, hyp, regmean, regstd,
-                                 s0, want_grad, nll, grad, info, stream);
+                                 s0, want_grad, nll, grad, info, workspace, workspace_bytes, stream);
     Workspace w(workspace, workspace_bytes);
     const long lda = lda_for(n);
     const long strideA = (long)(n + 1) * lda;

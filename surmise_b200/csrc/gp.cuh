@@ -16,7 +16,8 @@ int gp_nll_small_max_n();
 int gp_nll_grad_small(int batch, int n, int d, const double* theta, long strideTheta, const double* g, long strideG,
                       const double* gvar, long strideGvar, const double* hyp, const double* regmean,
                       const double* regstd, double s0, int want_grad, double* nll, double* grad, int* info,
-                      cudaStream_t stream, long long* stamps = nullptr);
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream, long long* stamps = nullptr);
+size_t gp_nll_small_workspace(int batch, int n, int want_grad);
 
 size_t gp_factorize_workspace(int batch, int n);
 int gp_factorize(int batch, int n, int d, const double* theta, long strideTheta, const double* g, long strideG,
