@@ -112,39 +112,78 @@ class GPData:
             self.nb_fixed = self.g.shape[0]
 
 
+_io_cache = {}
+
+
+def _io_buffers(torch, dev, nb, p):
+    """Per-(device, nb, p) staging: pinned host hyp buffer, one flat device result buffer and its pinned mirror.
+
+    Layout of the result buffer (doubles): nll[nb] | grad[nb*p] | info[nb] (int32 in the low half of each slot)."""
+    key = (dev.index, nb, p)
+    buf = _io_cache.get(key)
+    if buf is None:
+        if len(_io_cache) > 64:
+            _io_cache.clear()
+        total = nb * (p + 2)
+        buf = {'hyp_h': torch.empty((nb, p), dtype=torch.float64).pin_memory(),
+               'hyp_d': torch.empty((nb, p), dtype=torch.float64, device=dev),
+               'res_d': torch.empty(total, dtype=torch.float64, device=dev),
+               'res_h': torch.empty(total, dtype=torch.float64).pin_memory()}
+        _io_cache[key] = buf
+    return buf
+
+
 def gp_nll_grad(data, hyp, regmean, regstd, sig2ofconst=0.01, want_grad=True, return_device=False):
     """Batched PCGPwM.__negloglik (+ __negloglikgrad) (PCGPwM.py:850-907).
 
     hyp: (nb, d+3) numpy or tensor.  Returns numpy (nll (nb,), grad (nb,p) or None, info (nb,)), or with
     return_device=True one device tensor (nb, p+2) = [nll | grad | info] without synchronising.
+    The numpy path stages hyp through pinned memory and reads everything back with ONE device-to-host copy.
     """
     torch = _torch()
-    hyp_t = _f64(torch, np.atleast_2d(hyp) if not isinstance(hyp, torch.Tensor) else hyp)
-    nb, p = hyp_t.shape
     n, d = data.n, data.d
-    if p != d + 3:
-        raise ValueError('hyp must have d+3 = %d columns' % (d + 3))
+    p = d + 3
+    dev = data.theta.device
+    if isinstance(hyp, torch.Tensor):
+        hyp_t = _f64(torch, hyp)
+        nb = hyp_t.shape[0]
+        io = None
+    else:
+        hyp_np = np.atleast_2d(np.asarray(hyp, dtype=np.float64))
+        nb = hyp_np.shape[0]
+        io = _io_buffers(torch, dev, nb, p)
+        io['hyp_h'].numpy()[...] = hyp_np
+        io['hyp_d'].copy_(io['hyp_h'], non_blocking=True)
+        hyp_t = io['hyp_d']
+    if hyp_t.shape[1] != p:
+        raise ValueError('hyp must have d+3 = %d columns' % p)
     if data.nb_fixed is not None and data.nb_fixed != nb:
         raise ValueError('batch mismatch between data (%d) and hyp (%d)' % (data.nb_fixed, nb))
-    rm, rs = _f64(torch, regmean), _f64(torch, regstd)
-    dev = hyp_t.device
-    nll = torch.empty(nb, dtype=torch.float64, device=dev)
-    grad = torch.empty((nb, p), dtype=torch.float64, device=dev) if want_grad else None
-    info = torch.empty(nb, dtype=torch.int32, device=dev)
+    rm = regmean if (isinstance(regmean, torch.Tensor) and regmean.is_cuda) else _f64(torch, regmean)
+    rs = regstd if (isinstance(regstd, torch.Tensor) and regstd.is_cuda) else _f64(torch, regstd)
+    if io is None:
+        io = _io_buffers(torch, dev, nb, p)
+    res = io['res_d']
+    base = res.data_ptr()
+    nll_ptr, grad_ptr, info_ptr = base, base + 8 * nb, base + 8 * nb * (p + 1)
     nbytes = lib.sb200_gp_nll_grad_workspace(nb, n, d, int(want_grad))
     ws = workspace(nbytes)
     check(lib.sb200_gp_nll_grad(nb, n, d, _ptr(data.theta), data.stride_theta, _ptr(data.g), data.stride_g,
                                 _ptr(data.gvar), data.stride_gvar, _ptr(hyp_t),
-                                _ptr(rm), _ptr(rs), float(sig2ofconst), int(want_grad), _ptr(nll), _ptr(grad),
-                                _ptr(info), _ptr(ws), ws.numel(), _stream(torch)), 'sb200_gp_nll_grad')
+                                _ptr(rm), _ptr(rs), float(sig2ofconst), int(want_grad), nll_ptr,
+                                grad_ptr if want_grad else 0, info_ptr, _ptr(ws), ws.numel(), _stream(torch)),
+          'sb200_gp_nll_grad')
     if return_device:
-        cols = [nll[:, None]] + ([grad] if want_grad else []) + [info.to(torch.float64)[:, None]]
+        info = res[nb * (p + 1):].view(torch.int32)[:nb].to(torch.float64)
+        cols = [res[:nb, None]] + ([res[nb:nb * (p + 1)].view(nb, p)] if want_grad else []) + [info[:, None]]
         return torch.cat(cols, dim=1)
-    if want_grad:
-        packed = torch.cat([nll[:, None], grad, info.to(torch.float64)[:, None]], dim=1).cpu().numpy()
-        return packed[:, 0], packed[:, 1:1 + p], packed[:, -1].astype(np.int64)
-    packed = torch.stack([nll, info.to(torch.float64)], dim=1).cpu().numpy()
-    return packed[:, 0], None, packed[:, 1].astype(np.int64)
+    io['res_h'].copy_(res, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    host = io['res_h'].numpy()
+    nll = host[:nb].copy()
+    info = host[nb * (p + 1):].view(np.int32)[:nb].astype(np.int64)
+    grad = host[nb:nb * (p + 1)].reshape(nb, p).copy() if want_grad else None
+    return nll, grad, info
 
 
 def force_blocked_path(on):
