@@ -114,6 +114,12 @@ int sb200_woodbury_loglik(int B, int k, int m, int d, const double* predvecs, co
 int sb200_woodbury_trigger(int B, int k, int m, const double* predvars, const double* phiT, const double* extravar,
                            int* fired, void* stream);
 
+/* Host-side helper (no device work) for the PTLMC_B200 sampler plugin: the temperature-exchange sweep of
+ * utilitiesmethods/PTLMC.py:259-273 (tempexchange), with the random draws supplied by the caller.  lpost, temps (B);
+ * rtv, logu (iters*B); order (B) out. */
+void sb200_host_tempexchange(const double* lpost, const double* temps, int B, const int* rtv, const double* logu,
+                             int iters, int* order);
+
 /* Building blocks, exported for testing and reuse (no reference counterpart: the reference calls LAPACK).
  * sb200_dgemm: C[m][n] = alpha sum_k Aop[m][k] Bop[n][k] + beta C[m][n] on the FP64 tensor cores (DMMA);
  *   a_kc != 0: Aop[m][k] = A[m*lda+k] else A[k*lda+m]; same for B.  flags: 1 A lower, 2 A upper,

@@ -4,7 +4,7 @@ for bandframework/surmise, registered as additional surmise method modules.
     import surmise_b200; surmise_b200.register()
     emu = emulator(x, theta, f, method='PCGPwM_B200')
     cal = calibrator(emu, y, x, thetaprior, method='directbayeswoodbury_B200', yvar=yvar,
-                     args={'sampler': 'PTLMC'})
+                     args={'sampler': 'PTLMC_B200'})      # or surmise's own 'PTLMC', 'LMC', 'metropolis_hastings'
 
 The compute path is a C-ABI CUDA library (include/surmise_b200.h, surmise_b200/csrc); there is no CPU
 fallback -- calling any method without a CUDA device raises.
@@ -14,6 +14,7 @@ import sys
 
 EMULATION_METHODS = ('PCGPwM_B200',)
 CALIBRATION_METHODS = ('directbayeswoodbury_B200',)
+UTILITIES_METHODS = ('PTLMC_B200',)
 
 __version__ = '0.1.0'
 
@@ -29,6 +30,7 @@ def register():
     """
     import surmise.emulationmethods as _em
     import surmise.calibrationmethods as _cm
+    import surmise.utilitiesmethods as _um
     for name in EMULATION_METHODS:
         mod = importlib.import_module('surmise_b200.emulationmethods.' + name)
         sys.modules['surmise.emulationmethods.' + name] = mod
@@ -37,7 +39,11 @@ def register():
         mod = importlib.import_module('surmise_b200.calibrationmethods.' + name)
         sys.modules['surmise.calibrationmethods.' + name] = mod
         setattr(_cm, name, mod)
-    return EMULATION_METHODS + CALIBRATION_METHODS
+    for name in UTILITIES_METHODS:            # sampler plugins: 'surmise.utilitiesmethods.' + name (utilities.py:62-63)
+        mod = importlib.import_module('surmise_b200.utilitiesmethods.' + name)
+        sys.modules['surmise.utilitiesmethods.' + name] = mod
+        setattr(_um, name, mod)
+    return EMULATION_METHODS + CALIBRATION_METHODS + UTILITIES_METHODS
 
 
 def covmat(x1, x2, gammav, return_gradhyp=False, return_gradx1=False):

@@ -44,6 +44,7 @@ SIGNATURES = {
     'sb200_pc_backproject': (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'sb200_woodbury_loglik': (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
     'sb200_woodbury_trigger': (_i, [_i, _i, _i, _p, _p, _p, _p, _p]),
+    'sb200_host_tempexchange': (None, [_p, _p, _i, _p, _p, _i, _p]),
     'sb200_dgemm': (_i, [_i, _i, _i, _i, _i, _d, _p, _l, _l, _p, _l, _l, _d, _p, _l, _l, _i, _i, _i, _p]),
     'sb200_potrf_batched': (_i, [_i, _i, _i, _p, _l, _l, _p, _l, _l, _p, _p]),
     'sb200_trtri_tmp_elems': (_z, [_i]),

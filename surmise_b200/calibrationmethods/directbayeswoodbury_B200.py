@@ -183,7 +183,10 @@ def make_logpost(fitinfo, emu, x, y):
 
 def fit(fitinfo, emu, x, y, **bayeswoodbury_args):
     """Posterior sampling with surmise's own sampler plugins (dbw.py:7-163)."""
-    from surmise.utilities import sampler            # the reference's dispatcher, used unmodified
+    try:
+        from surmise.utilities import sampler        # the reference's dispatcher, used unmodified
+    except ImportError:
+        from ..utilities import sampler              # same contract, for installations without surmise
     if 'shard_theta' in bayeswoodbury_args:          # our option, not a sampler option
         fitinfo['shard_theta'] = bool(bayeswoodbury_args.pop('shard_theta'))
     woodbury_constants(fitinfo, emu, x, y)

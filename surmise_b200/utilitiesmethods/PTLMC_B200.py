@@ -1,0 +1,231 @@
+"""PTLMC_B200 -- parallel-tempering Langevin Monte Carlo sampler plugin, batched for the B200 path.
+
+Same algorithm and options as surmise/utilitiesmethods/PTLMC.py (`sampler(logpostfunc, draw_func, theta0, numsamp,
+numtemps, numchain, sampperchain, maxtemp)` -> {'theta', 'logpost'}, utilities.py:62-71), restructured so that the
+log-posterior closure -- one fused device evaluation per call in directbayeswoodbury_B200 -- only ever sees large
+batches:
+  * the pre-optimiser (PTLMC.py:140-173: one L-BFGS-B run per chain, B = 1 calls, value and gradient separately:
+    thousands of latency-bound calls) runs all chains in lock step, one batched call per optimiser step;
+  * the temperature-exchange sweep (PTLMC.py:259-273, 8.8 ms per step as a Python loop) is a compiled host helper
+    (sb200_host_tempexchange) fed with pre-drawn random numbers;
+  * the gradient-free probe uses a 2-D theta, so `return_grad=False` is honoured instead of silently falling back to
+    gradient evaluations (PTLMC.py:96-105).
+Registered by surmise_b200.register() as surmise.utilitiesmethods.PTLMC_B200, so
+`calibrator(..., args={'sampler': 'PTLMC_B200', ...})` is drop-in; usable without surmise as well.
+"""
+import ctypes
+import threading
+
+import numpy as np
+import scipy.optimize as spo
+
+
+def temperature_ladder(numtemps, numchain, maxtemp):
+    """maxtemp ... maxtemp^(1/(numtemps+1)) geometrically, then numchain chains at T = 1 (PTLMC.py:75-82)."""
+    hot = np.exp(np.linspace(np.log(maxtemp), np.log(maxtemp) / (numtemps + 1), numtemps))
+    return np.concatenate((hot, np.ones(numchain)))[:, None]
+
+
+def tempexchange(lpost, temps, rtv, logu):
+    """Revised chain order after len(rtv)/B exchange passes (PTLMC.py:259-273); random draws supplied."""
+    from .. import _lib
+    lp = np.ascontiguousarray(np.squeeze(lpost), dtype=np.float64)
+    tt = np.ascontiguousarray(np.squeeze(temps), dtype=np.float64)
+    B = lp.shape[0]
+    rtv = np.ascontiguousarray(rtv, dtype=np.int32)
+    logu = np.ascontiguousarray(logu, dtype=np.float64)
+    iters = rtv.size // B
+    order = np.empty(B, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    _lib.lib.sb200_host_tempexchange(p(lp), p(tt), B, p(rtv), p(logu), iters, p(order))
+    return order.astype(np.int64)
+
+
+class _Lockstep:
+    """Batch the evaluations requested by several optimiser threads into one closure call."""
+
+    def __init__(self, fn, nthreads):
+        self.fn, self.live, self.pending = fn, nthreads, []
+        self.cv = threading.Condition()
+
+    def __call__(self, theta_row):
+        req = {'x': theta_row, 'out': None}
+        with self.cv:
+            self.pending.append(req)
+            if len(self.pending) >= self.live:
+                self._flush()
+            else:
+                while req['out'] is None:
+                    self.cv.wait()
+        if isinstance(req['out'], BaseException):
+            raise req['out']
+        return req['out']
+
+    def retire(self):
+        with self.cv:
+            self.live -= 1
+            if self.live > 0 and len(self.pending) >= self.live:
+                self._flush()
+
+    def _flush(self):
+        reqs, self.pending = self.pending, []
+        try:
+            vals, grads = self.fn(np.array([r['x'] for r in reqs]))
+            for i, r in enumerate(reqs):
+                r['out'] = (float(vals[i]), None if grads is None else grads[i])
+        except BaseException as exc:
+            for r in reqs:
+                r['out'] = exc
+        self.cv.notify_all()
+
+
+def _preoptimise(theta0, value_and_grad, has_grad):
+    """One bounded L-BFGS-B run per chain from its starting point, then a random move off the optimum
+    (PTLMC.py:122-173), all chains advancing in lock step."""
+    numopt, d = theta0.shape
+    cen = np.mean(theta0, 0)
+    sca = np.maximum(np.std(theta0, 0), 1e-8 * np.std(theta0))
+    lo = np.maximum(-10 * np.ones(d), np.min((theta0 - cen) / sca, 0))
+    hi = np.minimum(10 * np.ones(d), np.max((theta0 - cen) / sca, 0))
+    bounds = spo.Bounds(lo, hi)
+    kicks = np.random.standard_normal(size=(numopt, 8, d))        # drawn up-front: results independent of scheduling
+    out = np.array(theta0, dtype=np.float64)
+
+    def batch(thetas):
+        v, g = value_and_grad(thetas)
+        return np.squeeze(v, axis=1) if v.ndim > 1 else v, g
+    ev = _Lockstep(batch, numopt)
+
+    def neg(xp):                                                   # scaled coordinates, as the reference
+        v, g = ev(cen + sca * xp)
+        return (-v, -sca * g) if has_grad else -v
+
+    def work(c):
+        try:
+            x0 = (theta0[c] - cen) / sca
+            res = spo.minimize(neg, x0, method='L-BFGS-B', jac=bool(has_grad), bounds=bounds)
+            best = cen + sca * res.x
+            if c > 0:                                              # the first chain stays on its optimum (PTLMC.py:160)
+                W, V = np.linalg.eigh(res.hess_inv @ np.eye(d))
+                l0 = neg(res.x)[0] if has_grad else neg(res.x)
+                step = 4.0
+                for t in range(8):
+                    r = (V.T * np.sqrt(np.abs(W))) @ (V @ kicks[c, t])
+                    trial = neg(step * r + res.x)
+                    trial = trial[0] if has_grad else trial
+                    if trial - l0 < 3 * d:
+                        best = cen + sca * (step * r + res.x)
+                        break
+                    step /= 2
+                    if step < 1 / 16:
+                        break
+            out[c] = best
+        finally:
+            ev.retire()
+    threads = [threading.Thread(target=work, args=(c,)) for c in range(numopt)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    return out
+
+
+def sampler(logpostfunc, draw_func, theta0=None, numsamp=2000, numtemps=32, numchain=16, sampperchain=400,
+            maxtemp=30, **ptlmc_options):
+    """Parallel-tempering ensemble MCMC with Langevin proposals; returns {'theta': (numsamp, d), 'logpost': ...}."""
+    if theta0 is None or theta0.shape[0] < 10 * theta0.shape[1]:
+        theta0 = draw_func(1000)
+    theta0 = np.array(theta0, dtype=np.float64)
+    d = theta0.shape[1]
+    tune = int(np.ceil(sampperchain * 0.5))
+    B = numtemps + numchain
+    temps = temperature_ladder(numtemps, numchain, maxtemp)
+
+    probe = logpostfunc(theta0[0:2, :])
+    has_grad = isinstance(probe, tuple)
+    if has_grad:
+        if len(probe) != 2:
+            raise ValueError('log density does not return 1 or 2 elements')
+        if probe[1].shape[1] != d:
+            raise ValueError('derivative appears to be the wrong shape')
+        try:
+            t = logpostfunc(theta0[0:2, :], return_grad=False)
+            if isinstance(t, tuple):
+                raise ValueError('Cannot stop returning a grad')
+
+            def value_only(th):
+                return logpostfunc(th, return_grad=False)
+        except (TypeError, ValueError):
+            def value_only(th):
+                return logpostfunc(th)[0]
+
+        def value_and_grad(th):
+            return logpostfunc(th)
+    else:
+        def value_only(th):
+            return logpostfunc(th)
+
+        def value_and_grad(th):
+            return logpostfunc(th), None
+    taracc = 0.60 if has_grad else 0.25
+
+    # starting points: best-ranked draws (with a random tie-breaker), each improved by a bounded optimiser
+    rank = np.argsort(-np.squeeze(value_only(theta0)) + d * np.random.standard_normal(size=theta0.shape[0]) ** 2)
+    thetac = _preoptimise(theta0[rank[:B]], value_and_grad, has_grad)
+
+    if has_grad:
+        fval, dfval = value_and_grad(thetac)
+        fval, dfval = fval / temps, dfval / temps
+    else:
+        fval, dfval = value_only(thetac) / temps, None
+    save = np.zeros((numchain, sampperchain, d))
+    cov0 = np.atleast_2d(np.cov(thetac.T))
+    if d > 1:
+        cov0 = 0.9 * cov0 + 0.1 * np.diag(np.diag(cov0))
+        W, V = np.linalg.eigh(cov0)
+        hc = V @ np.diag(np.sqrt(W)) @ V.T
+    else:
+        hc = np.sqrt(cov0)
+    tau = -1.0
+    rho = 2 * (1 + np.tanh(tau))
+    adjrho = rho * temps ** (1 / 3)
+    accepted = 0.0
+    for k in range(tune + sampperchain):
+        z = np.random.normal(0, 1, thetac.shape)
+        thetap = thetac + np.sqrt(2) * adjrho * (z @ hc)
+        if has_grad:
+            thetap = thetap + (adjrho ** 2) * (dfval @ cov0)
+            fvalp, dfvalp = value_and_grad(thetap)
+            fvalp, dfvalp = fvalp / temps, dfvalp / temps
+            t1 = z / np.sqrt(2)
+            t2 = (adjrho / 2) * ((dfval + dfvalp) @ hc)
+            qadj = -(2 * np.sum(t1 * t2, 1) + np.sum(t2 ** 2, 1))
+        else:
+            fvalp = value_only(thetap) / temps
+            qadj = np.zeros(B)
+        take = np.where(np.log(np.random.uniform(size=B)) < np.squeeze(fvalp - fval) + np.squeeze(qadj))[0]
+        if take.size:
+            accepted += take.size / B
+            thetac[take] = thetap[take]
+            fval[take] = fvalp[take]
+            if has_grad:
+                dfval[take] = dfvalp[take]
+        # exchange along the temperature ladder (5 passes)
+        fn = fval * temps
+        rtv = np.random.choice(np.arange(1, B), size=5 * B)
+        logu = np.log(np.random.uniform(size=5 * B))
+        order = tempexchange(fn, temps, rtv, logu)
+        fval = fn[order] / temps
+        thetac = thetac[order]
+        if has_grad:
+            dfval = (temps * dfval)[order] / temps
+        if k < tune and k % 10 == 0:
+            tau = tau + (accepted / 10 - taracc) / np.sqrt(1 + k / 10)
+            rho = 2 * (1 + np.tanh(tau))
+            adjrho = rho * temps ** (1 / 3)
+            accepted = 0.0
+        elif k >= tune:
+            save[:, k - tune, :] = thetac[numtemps:]
+    flat = save.reshape(-1, d)
+    theta = flat[np.random.choice(flat.shape[0], size=numsamp)]
+    return {'theta': theta, 'logpost': value_only(theta)}

@@ -300,3 +300,40 @@ def test_fitted_state_survives_pickle_and_predictlpdf_runs():
     fd = (M.predictlpdf(p2, truth(tn), addvar=0.01) - lp)[:, 0] / h
     # the reference's analytic lpdf gradient (reproduced here) is only approximately the derivative of its lpdf
     assert rel(fd, dlp[:, 1]) < 5e-2
+
+
+def test_calibration_with_ptlmc_b200_sampler():
+    """End to end: PCGPwM_B200 emulator -> directbayeswoodbury_B200 -> PTLMC_B200 (config C5 in miniature)."""
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
+    from synth import make_observation
+    x, theta, f, truth = make_simulator(150, 2, 25, 4, seed=21)
+    np.random.seed(21)
+    fi = _facade_fit(M, x, theta, f)
+    emu = _ShimEmulator(M, fi, theta)
+    theta_true, y, yvar = make_observation(truth, 2, seed=22)
+    ncalls = {'n': 0, 'rows': 0}
+
+    class prior:
+        @staticmethod
+        def lpdf(th):
+            th = np.atleast_2d(th)
+            ncalls['n'] += 1
+            ncalls['rows'] += th.shape[0]
+            return np.where(np.all((th >= 0) & (th <= 1), axis=1), 0.0, -np.inf).reshape(-1, 1)
+
+        @staticmethod
+        def lpdf_grad(th):
+            return np.zeros_like(np.atleast_2d(th))
+
+        @staticmethod
+        def rnd(n):
+            return np.random.uniform(size=(n, 2))
+    cal = {'thetaprior': prior, 'yvar': yvar}
+    np.random.seed(5)
+    C.fit(cal, emu, x, y, sampler='PTLMC_B200', numsamp=1000, numtemps=6, numchain=18, sampperchain=120)
+    assert cal['thetarnd'].shape == (1000, 2)
+    err = np.abs(cal['thetarnd'].mean(0) - theta_true[0])
+    report('calibration_ptlmc_b200', err0=float(err[0]), err1=float(err[1]), mean_batch=ncalls['rows'] / ncalls['n'])
+    assert np.all(err < 0.1)
+    assert ncalls['rows'] / ncalls['n'] > 10                # batched log-posterior calls, also in the pre-optimiser

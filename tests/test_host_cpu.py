@@ -111,6 +111,8 @@ def test_register_into_surmise_if_installed():
     assert 'PCGPwM_B200' in names
     m = importlib.import_module('surmise.emulationmethods.PCGPwM_B200')
     assert hasattr(m, 'fit') and hasattr(m, 'predict')
+    smp = importlib.import_module('surmise.utilitiesmethods.PTLMC_B200')
+    assert hasattr(smp, 'sampler') and 'PTLMC_B200' in names
     c = importlib.import_module('surmise.calibrationmethods.directbayeswoodbury_B200')
     for fn in ('fit', 'predict', 'thetarnd', 'thetalpdf', 'loglik', 'loglik_grad'):
         assert hasattr(c, fn)
