@@ -280,3 +280,48 @@ def test_logpost_closure_contract(ops, golden):
     assert np.allclose(np.delete(lp2[:, 0], 1), np.delete(lp[:, 0], 1), rtol=1e-12)
     assert np.allclose(np.delete(lp[:, 0], 1), np.delete(g['loglik'][:, 0], 1), rtol=1e-7)
     assert draw(10).shape == (10, 3)
+
+
+def test_edge_shapes_single_pc_max_dim_tiny_n(ops):
+    """k = 1 (dbw.py:293-301, 371-374 special-case it), d = 16 (the compiled maximum), very small n, B = 1."""
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
+    rng = np.random.default_rng(2)
+    n, d, m = 40, 16, 7
+    theta = rng.uniform(size=(n, d))
+    load = rng.normal(size=m)
+    f = (np.sin(theta @ rng.normal(size=d))[:, None] * load[None, :] + 1e-6 * rng.normal(size=(n, m))).T   # rank 1
+    x = np.arange(m, dtype=float)[:, None]
+    np.random.seed(2)
+    fi = {}
+    M.fit(fi, x, theta, f)
+    assert len(fi['emulist']) == 1
+    # oracle at the same hyper-parameters
+    e = fi['emulist'][0]
+    o = po.final_factorisation(theta, fi['pc'][:, 0], np.zeros(n), e['hyp'])
+    o['hypind'] = 0
+    fo = {'theta': theta, 'emulist': [o], 'pcti': fi['pcti'], 'standardpcinfo': fi['standardpcinfo']}
+    for B in (1, 5):
+        tn = rng.uniform(size=(B, d))
+        pg, pr = {}, {}
+        M.predict(pg, fi, x, tn, return_grad=True)
+        po.predict(pr, fo, x, tn, return_grad=True)
+        assert pg['covxhalf'].shape == (m, B, 1) and pg['covxhalf_gradtheta'].shape == (m, B, 1, d)
+        assert rel(pg['mean'], pr['mean']) < 1e-7 and rel(pg['var'], pr['var']) < 1e-6
+        assert rel(pg['mean_gradtheta'], pr['mean_gradtheta']) < 1e-6
+        y = pr['mean'][:, 0] + 0.01
+        yvar = np.full(m, 1e-3)
+
+        class Emu:
+            _info = fi
+        ll, dll = C.loglik_grad({'yvar': yvar}, Emu, tn, y, x)
+        oll, odll = wo.loglik_mspace(fo, yvar, tn, y, return_grad=True)
+        assert np.max(np.abs(ll - oll) / np.abs(oll)) < 1e-6 and rel(dll, odll) < 1e-5
+    # n = 2 design points, B larger than n
+    th2 = rng.uniform(size=(2, 3))
+    mean, lo, hi, std = M.hyper_prior(rng.uniform(size=(30, 3)), -10, -20, None)
+    g2 = np.array([0.3, -0.2])
+    info = {'theta': th2, 'g': g2, 'gvar': np.zeros(2), 'sig2ofconst': 0.01, 'hypregmean': mean, 'hypregstd': std}
+    v, gr, code = ops.gp_nll_grad(ops.GPData(th2, g2, np.zeros(2)), mean[None, :], mean, std, 0.01, True)
+    assert code[0] == 0 and abs(v[0] - po.negloglik_eigh(mean, info)) < 1e-12
+    assert rel(gr[0], po.negloglikgrad_eigh(mean, info)) < 1e-10
