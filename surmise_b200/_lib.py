@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libsurmise_b200.so')
+LIB_PATH = os.environ.get('SURMISE_B200_LIB') or os.path.join(_HERE, 'lib', 'libsurmise_b200.so')   # env: experiments only
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

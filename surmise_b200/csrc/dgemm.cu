@@ -15,8 +15,14 @@ using std::max;
 namespace sb {
 namespace {
 
-constexpr int BK = 16;
-constexpr int STAGES = 3;
+#ifndef SB_BK
+#define SB_BK 16
+#endif
+#ifndef SB_STAGES
+#define SB_STAGES 3
+#endif
+constexpr int BK = SB_BK;
+constexpr int STAGES = SB_STAGES;
 
 __device__ __forceinline__ void cp_async16(double* smem, const double* gmem, int src_bytes) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -101,9 +107,12 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 1
     // (lower-triangular B / upper-triangular A and B already start with their longest tiles)
     const int tile_m = (p.flags & GEMM_A_LOWER) ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y;
     const int tile_n = (p.flags & GEMM_B_LOWER) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
-    const int m0 = tile_m * BM, n0 = tile_n * BN;
+    const int n0 = tile_n * BN;
+    // lower-only output: row tiles of column block J start ON the diagonal (row n0), so only the first tile of each
+    // column block straddles it (25 % of one tile wasted per block instead of 50 % of two)
+    const int m0 = (p.flags & GEMM_C_LOWER) ? n0 + tile_m * BM : tile_m * BM;
+    if (m0 >= p.M) return;
     const int m_end = min(p.M, m0 + BM), n_end = min(p.N, n0 + BN);
-    if ((p.flags & GEMM_C_LOWER) && n0 > m_end - 1) return;
 
     const int z1 = p.inner_batch > 0 ? z % p.inner_batch : z;
     const long z2 = p.inner_batch > 0 ? z / p.inner_batch : 0;
@@ -122,11 +131,39 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 1
     const bool a16 = ((p.lda & 1) == 0) && (((uintptr_t)A & 15) == 0);
     const bool b16 = ((p.ldb & 1) == 0) && (((uintptr_t)B & 15) == 0);
 
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
+    const bool c16 = ((p.ldc & 1) == 0) && (((uintptr_t)C & 15) == 0);
+    const double alpha = p.alpha, beta = p.beta;
+
+    // beta * C is folded into the accumulators up front: alpha (A B' + (beta/alpha) C).  The C loads then overlap
+    // the cp.async prologue instead of serialising (load -> fma -> store per fragment) in the epilogue.
     double acc[MI][NI][2];
+    const bool fold = (beta != 0.0) && (alpha != 0.0);
+    const double cscale = fold ? beta / alpha : 0.0;
 #pragma unroll
-    for (int i = 0; i < MI; i++)
+    for (int i = 0; i < MI; i++) {
+        const int row = m0 + wm0 + i * 8 + g;
 #pragma unroll
-        for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NI; j++) {
+            const int col = n0 + wn0 + j * 8 + 2 * t;
+            double c0 = 0.0, c1 = 0.0;
+            if (fold && row < p.M) {
+                const double* ptr = C + (long)row * p.ldc + col;
+                if (c16 && col + 1 < p.N) {
+                    double2 o = *reinterpret_cast<const double2*>(ptr);
+                    c0 = o.x;
+                    c1 = o.y;
+                } else {
+                    if (col < p.N) c0 = ptr[0];
+                    if (col + 1 < p.N) c1 = ptr[1];
+                }
+            }
+            acc[i][j][0] = cscale * c0;
+            acc[i][j][1] = cscale * c1;
+        }
+    }
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
@@ -136,10 +173,6 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 1
         }
         cp_async_commit();
     }
-
-    const int warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
 
     for (int kt = 0; kt < ktiles; kt++) {
         cp_async_wait<STAGES - 2>();
@@ -172,9 +205,8 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 1
     }
     cp_async_wait<0>();
 
-    const bool c16 = ((p.ldc & 1) == 0) && (((uintptr_t)C & 15) == 0);
-    const double alpha = p.alpha, beta = p.beta;
     const bool lower_only = (p.flags & GEMM_C_LOWER) != 0;
+    const double beta_ep = fold ? 0.0 : beta;          // only the degenerate alpha == 0 case still reads C here
 #pragma unroll
     for (int i = 0; i < MI; i++) {
         int row = m0 + wm0 + i * 8 + g;
@@ -188,19 +220,19 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 1
             const bool w0 = (col < p.N) && !(lower_only && col > row);
             const bool w1 = (col + 1 < p.N) && !(lower_only && col + 1 > row);
             if (w0 && w1 && c16) {
-                if (beta != 0.0) {
+                if (beta_ep != 0.0) {
                     double2 o = *reinterpret_cast<const double2*>(ptr);
-                    v0 += beta * o.x;
-                    v1 += beta * o.y;
+                    v0 += beta_ep * o.x;
+                    v1 += beta_ep * o.y;
                 }
                 *reinterpret_cast<double2*>(ptr) = make_double2(v0, v1);
             } else {
                 if (w0) {
-                    if (beta != 0.0) v0 += beta * ptr[0];
+                    if (beta_ep != 0.0) v0 += beta_ep * ptr[0];
                     ptr[0] = v0;
                 }
                 if (w1) {
-                    if (beta != 0.0) v1 += beta * ptr[1];
+                    if (beta_ep != 0.0) v1 += beta_ep * ptr[1];
                     ptr[1] = v1;
                 }
             }
