@@ -283,6 +283,14 @@ def main():
 
     if rank == 0:
         evals = k * world
+        traffic, traffic_note = None, None
+        try:                                            # DRAM bytes of the DMMA GEMM launches of one step, from the committed ncu run
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'dram_traffic_r1.json')))['kernels']['dgemm_dmma_kernel']
+            traffic = (tj['dram_read_bytes'] + tj['dram_write_bytes']) / tj['launches']
+            traffic_note = ('ncu dram__bytes_read+write summed over the %d DMMA GEMM launches of one step / launches '
+                            '(profiles/dram_traffic_r1.json): %.2f GB per step' % (tj['launches'], (tj['dram_read_bytes'] + tj['dram_write_bytes']) / 1e9))
+        except Exception:
+            pass
         ach = (g_fl.value / (g_ms.value * 1e-3) / 1e12) if g_ms.value > 0 else None
         cpu = None
         if world == 1:
@@ -310,7 +318,7 @@ def main():
             'clocks': clk.summary(),
             'roofline': {'bound': 'tensor', 'kernel': 'dgemm_dmma_kernel (FP64 DMMA.8x8x4)', 'achieved': ach,
                          'peak': peak, 'unit': 'TFLOP/s', 'frac': (ach / peak) if (ach and peak) else None,
-                         'traffic': None, 'launches_timed': g_n, 'gemm_ms_per_step': g_ms.value / K,
+                         'traffic': traffic, 'traffic_note': traffic_note, 'launches_timed': g_n, 'gemm_ms_per_step': g_ms.value / K,
                          'gemm_share_of_step': (g_ms.value / K) / ms_dev,
                          'algorithmic_flop_per_step': g_fl.value / K,
                          'whole_step_tflops': k * float(n) ** 3 / (ms_dev * 1e-3) / 1e12,
