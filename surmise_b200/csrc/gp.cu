@@ -60,7 +60,7 @@ constexpr int XLD = MAXD + 1;
 
 // Per (PC, 32 new thetas, 256 design points): partial sums over j of
 //   T1^2, r pw, and (with gradients) T2 dr_i, dr_i pw, where dr_i = dR0/dtheta*_i rebuilt from r.
-__global__ void __launch_bounds__(256) predict_partial_kernel(
+__global__ void __launch_bounds__(256, 2) predict_partial_kernel(
     int n, int d, int B, const double* __restrict__ theta, const double* __restrict__ thetanew,
     const double* __restrict__ hypcovb, const int* __restrict__ fidx, const int* __restrict__ fu,
     const double* __restrict__ pwb, const double* __restrict__ rTb, long ldb, long strideU,
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) predict_partial_kernel(
                 for (int i = 0; i < MAXD; i++)
                     if (i < d) {
                         double s = xb[tx * XLD + i] - xj[jl * XLD + i];
-                        double dr = rp * (-cc.ginv[i] * s / (1.0 + fabs(s)));   // matern_covmat.pyx:13-24
+                        double dr = rp * (-cc.ginv[i] * s * __drcp_rn(1.0 + fabs(s)));   // matern_covmat.pyx:13-24
                         dv[i] += t2 * dr;
                         dp[i] += dr * pwv;
                     }
