@@ -63,7 +63,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -228,8 +228,9 @@ def main():
     for _ in range(W):
         step_device()
     l0 = _lib.lib.sb200_launch_count()
-    with ClockSampler(local) as clk:
-        ms_dev = timed(step_device, K)
+    clk = ClockSampler(local)
+    clk.__enter__()                                   # sampled across the device-timed, e2e and roofline legs
+    ms_dev = timed(step_device, K)
     launches = (_lib.lib.sb200_launch_count() - l0)
     res = step_device()
     torch.cuda.synchronize()
@@ -249,6 +250,7 @@ def main():
     _lib.lib.sb200_gemm_profile_enable(0)
     g_ms, g_fl = ctypes.c_double(0), ctypes.c_double(0)
     g_n = _lib.lib.sb200_gemm_profile_collect(ctypes.byref(g_ms), ctypes.byref(g_fl))
+    clk.__exit__(None, None, None)
 
     # FP64 peak measured in this run (MEASURED_PEAKS.json carries no FP64 entry): cuBLAS DGEMM 8192^3
     peak = None

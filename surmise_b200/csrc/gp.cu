@@ -60,12 +60,14 @@ constexpr int XLD = MAXD + 1;
 
 // Per (PC, 32 new thetas, 256 design points): partial sums over j of
 //   T1^2, r pw, and (with gradients) T2 dr_i, dr_i pw, where dr_i = dR0/dtheta*_i rebuilt from r.
+template <bool WANT_GRAD>
 __global__ void __launch_bounds__(256, 2) predict_partial_kernel(
     int n, int d, int B, const double* __restrict__ theta, const double* __restrict__ thetanew,
     const double* __restrict__ hypcovb, const int* __restrict__ fidx, const int* __restrict__ fu,
     const double* __restrict__ pwb, const double* __restrict__ rTb, long ldb, long strideU,
-    const double* __restrict__ T1b, const double* __restrict__ T2b, long strideT, int want_grad,
+    const double* __restrict__ T1b, const double* __restrict__ T2b, long strideT, int /*want_grad*/,
     double* __restrict__ partial, int nchunks, int Q) {
+    constexpr bool want_grad = WANT_GRAD;
     __shared__ double xj[JC * XLD];
     __shared__ double xb[32 * XLD];
     __shared__ double pwj[JC];
@@ -104,16 +106,19 @@ __global__ void __launch_bounds__(256, 2) predict_partial_kernel(
         const double* rT = rTb + (long)u * strideU;
         const double* T1 = T1b + (long)f * strideT;
         const double* T2 = T2b ? T2b + (long)f * strideT : nullptr;
-        for (int jl = ty; jl < JC; jl += 8) {
-            int j = j0 + jl;
-            if (j >= n) break;
+        const int jmax = min(JC, n - j0);
+        // unrolled so that the three global loads of several design points are in flight together: the loop is
+        // bound by L2 latency, not by arithmetic
+#pragma unroll(WANT_GRAD ? 2 : 4)
+        for (int jl = ty; jl < jmax; jl += 8) {
+            const int j = j0 + jl;
             double r = rT[(long)j * ldb + b];
             double t1 = T1[(long)j * ldb + b];
+            double t2 = want_grad ? T2[(long)j * ldb + b] : 0.0;
             double pwv = pwj[jl];
             s1 += t1 * t1;
             s2 += r * pwv;
             if (want_grad) {
-                double t2 = T2[(long)j * ldb + b];
                 double rp = r - cc.onemc;                          // R_pre
 #pragma unroll
                 for (int i = 0; i < MAXD; i++)
@@ -429,8 +434,12 @@ int gp_predict(int K, int nf, int nu, int n, int d, int B, const double* theta, 
     }
     {
         dim3 grid(cdiv(B, 32), nchunks, K);
-        predict_partial_kernel<<<grid, 256, 0, stream>>>(n, d, B, theta, thetanew, hypcov, fidx, fu, pw, rT, ldb, strideT,
-                                                         T1, T2, strideT, want_grad, partial, nchunks, Q);
+        if (want_grad)
+            predict_partial_kernel<true><<<grid, 256, 0, stream>>>(n, d, B, theta, thetanew, hypcov, fidx, fu, pw, rT, ldb,
+                                                                   strideT, T1, T2, strideT, 1, partial, nchunks, Q);
+        else
+            predict_partial_kernel<false><<<grid, 256, 0, stream>>>(n, d, B, theta, thetanew, hypcov, fidx, fu, pw, rT, ldb,
+                                                                    strideT, T1, T2, strideT, 0, partial, nchunks, Q);
         SB_LAUNCH_CHECK();
         dim3 grid2(cdiv(B, 128), K);
         predict_reduce_kernel<<<grid2, 128, 0, stream>>>(K, d, B, ldb, nchunks, Q, partial, nug, sig2, want_grad,
