@@ -54,7 +54,6 @@ int sb200_matern_covmat(const double* x1, int n1, const double* x2, int n2, int 
  * the blocked path (testing). */
 int sb200_gp_nll_small_max_n(void);
 void sb200_gp_force_blocked_path(int on);
-void sb200_gp_small_variant(int v);   /* testing: 1 = rank-4 DMMA sweep kernel (default), 0 = rank-1 register sweep */
 /* instrumentation: as sb200_gp_nll_grad on shared theta/g without gvar, plus clock64() stamps (8 slots) of CTA 0 */
 int sb200_gp_nll_small_profile(int batch, int n, int d, const double* theta, const double* g, const double* hyp,
                                const double* regmean, const double* regstd, double* nll, double* grad, int* info,

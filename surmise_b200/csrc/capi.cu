@@ -128,7 +128,6 @@ int sb200_gp_nll_grad(int batch, int n, int d, const double* theta, long stride_
 
 void sb200_gp_force_blocked_path(int on) { gp_force_blocked_path(on); }
 int sb200_gp_nll_small_max_n(void) { return gp_nll_small_max_n(); }
-void sb200_gp_small_variant(int v) { gp_small_variant(v); }
 
 int sb200_gp_nll_small_profile(int batch, int n, int d, const double* theta, const double* g, const double* hyp,
                                const double* regmean, const double* regstd, double* nll, double* grad, int* info,

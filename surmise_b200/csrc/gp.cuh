@@ -13,7 +13,6 @@ int gp_nll_grad(int batch, int n, int d, const double* theta, long strideTheta, 
 void gp_force_blocked_path(int on);
 // single-CTA fused path for n <= gp_nll_small_max_n() (nll_small.cu); gp_nll_grad dispatches to it
 int gp_nll_small_max_n();
-void gp_small_variant(int v);       // testing: 1 = rank-4 DMMA sweep (default), 0 = rank-1 register sweep
 int gp_nll_grad_small(int batch, int n, int d, const double* theta, long strideTheta, const double* g, long strideG,
                       const double* gvar, long strideGvar, const double* hyp, const double* regmean,
                       const double* regstd, double s0, int want_grad, double* nll, double* grad, int* info,

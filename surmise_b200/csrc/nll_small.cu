@@ -196,271 +196,6 @@ __global__ void __launch_bounds__(256, 1) gp_sweep_small_kernel(SweepArgs p) {
 #undef SB_STAMP
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// Blocked variant: four pivots per step, the rank-4 update of the whole matrix on the FP64 tensor cores.
-//   [[P, B'], [B, C]]  --sweep the 4x4 block P-->  [[-P^-1, (B P^-1)'], [B P^-1, C - B P^-1 B']]
-// The lower triangle lives in registers as 8x8 DMMA accumulator tiles (warp w owns tiles w, w+8, ...; lane (g,t)
-// holds (8I+g, 8J+2t..2t+1); diagonal tiles are held full).  Per step: the four pivot columns sit in shared memory
-// (gathered while the previous step's tiles were updated); every thread factors the 4x4 block P = L D L'; each row
-// b of B becomes y = b L^-T (forward substitution -- the same operations the four scalar sweeps would do, so the
-// conditioning of P never enters an explicit inverse), and with z = y D^-1
-//     C - B P^-1 B' = C - Z Y'      -> ONE DMMA.8x8x4 per tile,          B P^-1 = Z L^-1  -> the pivot rows / columns.
-// One pass over a warp's tiles per step does the DMMA, the pivot fix-ups and the gather for the next step.
-// register-array access with a run-time (warp-uniform) slot index: binary decision tree over compile-time indices
-template <int NS, int LO, int HI>
-__device__ __forceinline__ void slot_get(const double (&acc)[NS][2], int slot, double& v0, double& v1) {
-    if constexpr (LO == HI) {
-        v0 = acc[LO][0];
-        v1 = acc[LO][1];
-    } else {
-        constexpr int MID = (LO + HI) / 2;
-        if (slot <= MID) slot_get<NS, LO, MID>(acc, slot, v0, v1);
-        else slot_get<NS, MID + 1, HI>(acc, slot, v0, v1);
-    }
-}
-template <int NS, int LO, int HI>
-__device__ __forceinline__ void slot_set(double (&acc)[NS][2], int slot, double v0, double v1) {
-    if constexpr (LO == HI) {
-        acc[LO][0] = v0;
-        acc[LO][1] = v1;
-    } else {
-        constexpr int MID = (LO + HI) / 2;
-        if (slot <= MID) slot_set<NS, LO, MID>(acc, slot, v0, v1);
-        else slot_set<NS, MID + 1, HI>(acc, slot, v0, v1);
-    }
-}
-
-template <int NT8>
-__global__ void __launch_bounds__(256, 1) gp_sweep_dmma_kernel(SweepArgs p) {
-    constexpr int NP = 8 * NT8;
-    constexpr int NTILES = NT8 * (NT8 + 1) / 2;
-    constexpr int NS = (NTILES + 7) / 8;
-    __shared__ double Bs[2][4][NP];                 // pivot columns of the current / next step
-    __shared__ double Ws[4][NP], Vs[4][NP], Us[4][NP];   // -Z, Y, B P^-1 (rows of P^-1 at the pivot rows)
-    __shared__ double piv[NP];
-    __shared__ double red[32];
-    __shared__ int s_bad;
-    __shared__ double s_qf;
-    const int z = blockIdx.x, tid = threadIdx.x, n = p.n, d = p.d;
-    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    double* A = p.A + (long)z * p.strideA;
-#define SB_STAMP(slot) do { if (p.stamps && z == 0 && tid == 0) p.stamps[slot] = clock64(); } while (0)
-    SB_STAMP(0);
-    if (tid == 0) s_bad = 0x7fffffff;
-
-    // ---- registers <- tiles.  Tile tl = I (I+1)/2 + J belongs to warp tl % 8, slot tl / 8.  Per slot the shared-
-    // memory word offsets of its W and V fragments are kept packed in one register (tiles past the end point at
-    // row / column 0 and carry zeros, so the hot loop needs no test).
-    double acc[NS][2];
-    unsigned woff[NS];
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        const int tl = warp + 8 * s;
-        int I = 0;
-        while ((I + 1) * (I + 2) / 2 <= tl) I++;
-        const int J = tl - I * (I + 1) / 2;
-        const bool live = tl < NTILES;
-        woff[s] = live ? (unsigned)((t * NP + 8 * I + g) | ((t * NP + 8 * J + g) << 16)) : 0u;
-        acc[s][0] = acc[s][1] = 0.0;
-        if (live) {
-            const int i = 8 * I + g;
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int c = 8 * J + 2 * t + e;
-                const int hi = max(i, c), lo = min(i, c);          // symmetric fetch for the diagonal tiles
-                double v = 0.0;
-                if (hi <= n && lo < n) v = A[(long)hi * p.lda + lo];
-                else if (hi > n && hi == lo) v = 1.0;
-                acc[s][e] = v;
-            }
-        }
-    }
-    // pivot columns k .. k+3 of tile (I, J) -> B[4][NP]   (Jn = k / 8, offn = k % 8)
-    auto gather = [&](double (*Bn)[NP], int I, int J, int Jn, int offn, double v0, double v1) {
-        if (J == Jn) {                                             // tile column of the pivots, rows 8I .. 8I+7
-            const int si = 2 * t - offn;
-            if (si == 0 || si == 2) {
-                Bn[si][8 * I + g] = v0;
-                Bn[si + 1][8 * I + g] = v1;
-            }
-        } else {                                                   // tile row of the pivots, columns left of them
-            const int sr = g - offn;
-            if (sr >= 0 && sr < 4) {
-                Bn[sr][8 * J + 2 * t] = v0;
-                Bn[sr][8 * J + 2 * t + 1] = v1;
-            }
-        }
-    };
-    // visit the tiles of tile column Jq (rows Jq..NT8-1) and of tile row Jq (columns 0..Jq-1) that this warp owns
-    auto for_pivot_tiles = [&](int Jq, auto&& fn) {
-        for (int I = Jq; I < NT8; I++) {
-            const int tl = I * (I + 1) / 2 + Jq;
-            if ((tl & 7) == warp) fn(I, Jq, tl >> 3);
-        }
-        const int base = Jq * (Jq + 1) / 2;
-        for (int J = 0; J < Jq; J++) {
-            const int tl = base + J;
-            if ((tl & 7) == warp) fn(Jq, J, tl >> 3);
-        }
-    };
-    for_pivot_tiles(0, [&](int I, int J, int slot) {
-        double v0, v1;
-        slot_get<NS, 0, NS - 1>(acc, slot, v0, v1);
-        gather(Bs[0], I, J, 0, 0, v0, v1);
-    });
-    __syncthreads();
-    SB_STAMP(1);
-
-    int bad_at = 0;
-    const int nblocks = (n + 3) / 4;
-    for (int kb = 0; kb < nblocks; kb++) {
-        const int k0 = 4 * kb, Jst = k0 >> 3, na = min(4, n - k0);
-        double (*Bc)[NP] = Bs[kb & 1];
-        double (*Bn)[NP] = Bs[(kb + 1) & 1];
-        // ---- panel: P = L D L' in every thread (pivots >= n are masked out: identity rows, zero columns)
-        double P[4][4];
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int b = 0; b <= a; b++) {
-                double v = Bc[b][k0 + a];
-                if (a >= na) v = (a == b) ? 1.0 : 0.0;
-                P[a][b] = v;
-            }
-        double dv[4], di[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            double dq = P[q][q];
-#pragma unroll
-            for (int r = 0; r < q; r++) dq -= P[q][r] * P[q][r] * dv[r];
-            if (!(dq > 0.0)) {
-                if (bad_at == 0 && q < na) bad_at = k0 + q + 1;
-                dq = 1.0;
-            }
-            dv[q] = dq;
-            di[q] = __drcp_rn(dq);
-#pragma unroll
-            for (int a = q + 1; a < 4; a++) {
-                double v = P[a][q];
-#pragma unroll
-                for (int r = 0; r < q; r++) v -= P[a][r] * P[q][r] * dv[r];
-                P[a][q] = v * di[q];                               // L[a][q]
-            }
-        }
-        if (tid == 0) {
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-                if (a < na) piv[k0 + a] = dv[a];
-        }
-        for (int i = tid; i < NP; i += 256) {
-            const int sr = i - k0;
-            const bool pivrow = (sr >= 0 && sr < na);
-            double y[4], zz[4], u[4];
-#pragma unroll
-            for (int a = 0; a < 4; a++) y[a] = pivrow ? (a == sr ? 1.0 : 0.0) : ((a < na) ? Bc[a][i] : 0.0);
-            y[1] -= P[1][0] * y[0];                                // y = b L^-T
-            y[2] -= P[2][0] * y[0] + P[2][1] * y[1];
-            y[3] -= P[3][0] * y[0] + P[3][1] * y[1] + P[3][2] * y[2];
-#pragma unroll
-            for (int a = 0; a < 4; a++) zz[a] = y[a] * di[a];
-            u[3] = zz[3];                                          // u = z L^-1  (= row of B P^-1, or of P^-1)
-            u[2] = zz[2] - u[3] * P[3][2];
-            u[1] = zz[1] - u[2] * P[2][1] - u[3] * P[3][1];
-            u[0] = zz[0] - u[1] * P[1][0] - u[2] * P[2][0] - u[3] * P[3][0];
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-                const bool live = (a < na) && !pivrow;
-                Ws[a][i] = live ? -zz[a] : 0.0;
-                Vs[a][i] = live ? y[a] : 0.0;
-                Us[a][i] = (a < na) ? u[a] : 0.0;
-            }
-        }
-        __syncthreads();
-        // ---- hot loop: one DMMA per tile, straight-line (pivot rows / columns carry zeros in W, V: untouched)
-        const double* wbase = &Ws[0][0];
-        const double* vbase = &Vs[0][0];
-#pragma unroll
-        for (int s = 0; s < NS; s++) {
-            const double av = wbase[woff[s] & 0xffffu], bv = vbase[woff[s] >> 16];
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                         : "+d"(acc[s][0]), "+d"(acc[s][1])
-                         : "d"(av), "d"(bv));
-        }
-        // ---- the few tiles that contain pivot rows / columns take their swept values ...
-        for_pivot_tiles(Jst, [&](int I, int J, int slot) {
-            double v[2];
-            slot_get<NS, 0, NS - 1>(acc, slot, v[0], v[1]);
-            const int i = 8 * I + g, sr = i - k0;
-            const bool pr = (sr >= 0 && sr < na);
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int c = 8 * J + 2 * t + e, sc = c - k0;
-                const bool pc = (sc >= 0 && sc < na);
-                if (pc && pr) v[e] = -Us[sc][i];                   // -P^-1
-                else if (pc) v[e] = Us[sc][i];                     // B P^-1
-                else if (pr) v[e] = Us[sr][c];                     // (B P^-1)'
-            }
-            slot_set<NS, 0, NS - 1>(acc, slot, v[0], v[1]);
-        });
-        // ---- ... and the next step's pivot columns are published
-        if (kb + 1 < nblocks) {
-            const int k1 = k0 + 4, Jn = k1 >> 3, offn = k1 & 7;
-            for_pivot_tiles(Jn, [&](int I, int J, int slot) {
-                double v0, v1;
-                slot_get<NS, 0, NS - 1>(acc, slot, v0, v1);
-                gather(Bn, I, J, Jn, offn, v0, v1);
-            });
-        }
-        __syncthreads();
-    }
-    SB_STAMP(2);
-    if (bad_at != 0) atomicMin(&s_bad, bad_at);
-
-    // ---- write back  R^-1 (lower) | alpha' ;  g' R^-1 g
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        const int tl = warp + 8 * s;
-        if (tl >= NTILES) continue;
-        int I = 0;
-        while ((I + 1) * (I + 2) / 2 <= tl) I++;
-        const int J = tl - I * (I + 1) / 2;
-        const int i = 8 * I + g;
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int c = 8 * J + 2 * t + e;
-            if (c > i) continue;
-            if (i < n) A[(long)i * p.lda + c] = -acc[s][e];
-            else if (i == n && c < n) A[(long)n * p.lda + c] = acc[s][e];
-            else if (i == n && c == n) s_qf = -acc[s][e];
-        }
-    }
-    __syncthreads();
-    double ld = 0.0;
-    for (int k = tid; k < n; k += 256) ld += log(piv[k]);
-    const double logdet = block_sum(ld, red);
-    if (tid == 0) {
-        const double sig2hat = (s_qf + p.s0) / (n + p.s0);
-        const int np = d + 3;
-        const double* hyp = p.hyp + (long)z * np;
-        double pr = 0.0;
-        for (int k = 0; k < np; k++) {
-            double tt = (1e-8 + hyp[k] - p.regmean[k]) / p.regstd[k];
-            pr += tt * tt;
-        }
-        p.nll[z] = 0.5 * logdet + 0.5 * n * log(sig2hat) + 0.5 * pr;
-        p.sig2hat[z] = sig2hat;
-        p.info[z] = (s_bad == 0x7fffffff) ? 0 : s_bad;
-    }
-    SB_STAMP(3);
-#undef SB_STAMP
-}
-
-template <int NT8>
-int launch_sweep_dmma(const SweepArgs& a, int batch, cudaStream_t stream) {
-    gp_sweep_dmma_kernel<NT8><<<batch, 256, 0, stream>>>(a);
-    SB_LAUNCH_CHECK();
-    return 0;
-}
 
 template <int R>
 int launch_sweep(const SweepArgs& a, int batch, cudaStream_t stream) {
@@ -472,9 +207,6 @@ int launch_sweep(const SweepArgs& a, int batch, cudaStream_t stream) {
 long lda_small(int n) { return round_up(n, 8); }
 
 }  // namespace
-
-static int g_small_variant = 1;     // 1: rank-4 DMMA sweep (default), 0: rank-1 register sweep
-void gp_small_variant(int v) { g_small_variant = v; }
 
 int gp_nll_small_max_n() { return T16 * 13 - 1; }
 
@@ -499,14 +231,6 @@ int gp_nll_grad_small(int batch, int n, int d, const double* theta, long strideT
     double* sig2hat = w.take<double>((size_t)batch);
     SB_TRY(gp_assemble(batch, n, d, theta, strideTheta, g, strideG, gvar, strideGvar, hyp, A, lda, strideA, stream));
     SweepArgs a{n, d, A, lda, strideA, hyp, regmean, regstd, s0, nll, sig2hat, info, stamps};
-    const int nt8 = (n + 1 + 7) / 8;
-    if (g_small_variant == 1) {
-        if (nt8 <= 8) SB_TRY(launch_sweep_dmma<8>(a, batch, stream));
-        else if (nt8 <= 12) SB_TRY(launch_sweep_dmma<12>(a, batch, stream));
-        else if (nt8 <= 16) SB_TRY(launch_sweep_dmma<16>(a, batch, stream));
-        else if (nt8 <= 21) SB_TRY(launch_sweep_dmma<21>(a, batch, stream));
-        else SB_TRY(launch_sweep_dmma<26>(a, batch, stream));
-    } else {
     const int R = (n + 1 + T16 - 1) / T16;
     if (R <= 4) SB_TRY(launch_sweep<4>(a, batch, stream));
     else if (R <= 6) SB_TRY(launch_sweep<6>(a, batch, stream));
@@ -514,7 +238,6 @@ int gp_nll_grad_small(int batch, int n, int d, const double* theta, long strideT
     else if (R <= 10) SB_TRY(launch_sweep<10>(a, batch, stream));
     else if (R <= 11) SB_TRY(launch_sweep<11>(a, batch, stream));
     else SB_TRY(launch_sweep<13>(a, batch, stream));
-    }
     if (!want_grad) return 0;
     double* partial = w.take<double>((size_t)batch * grad_contract_tiles(n) * MAXP);
     return gp_grad_contract(batch, n, d, theta, strideTheta, gvar, strideGvar, hyp, regmean, regstd, A, lda, strideA,
