@@ -174,6 +174,23 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 1
         cp_async_commit();
     }
 
+    // warp-level k-range: inside the CTA's k-range a warp whose rows (columns) lie deeper in the triangle only
+    // meets stored zeros for part of it, and a warp block entirely above the diagonal of a lower-only C is never
+    // written -- those k-slabs are staged (other warps need them) but their DMMAs are skipped
+    int wkt_lo = 0, wkt_hi = ktiles;
+    {
+        const int wr0 = m0 + wm0, wc0 = n0 + wn0;
+        int wk_lo = k_lo, wk_hi = k_hi;
+        if (p.flags & GEMM_A_LOWER) wk_hi = min(wk_hi, wr0 + WM);
+        if (p.flags & GEMM_A_UPPER) wk_lo = max(wk_lo, wr0);
+        if (p.flags & GEMM_B_LOWER) wk_hi = min(wk_hi, wc0 + WN);
+        if (p.flags & GEMM_B_UPPER) wk_lo = max(wk_lo, wc0);
+        if ((p.flags & GEMM_C_LOWER) && wc0 > wr0 + WM - 1) wk_hi = wk_lo;
+        if (wr0 >= p.M || wc0 >= p.N) wk_hi = wk_lo;
+        wkt_lo = (wk_lo - k_lo) / BK;
+        wkt_hi = wk_hi > wk_lo ? (wk_hi - k_lo + BK - 1) / BK : 0;
+    }
+
     for (int kt = 0; kt < ktiles; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -186,6 +203,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 1
             }
             cp_async_commit();
         }
+        if (kt < wkt_lo || kt >= wkt_hi) continue;
         const double* as = As + (kt % STAGES) * A_TILE;
         const double* bs = Bs + (kt % STAGES) * B_TILE;
 #pragma unroll
