@@ -17,7 +17,7 @@ class sampler(object):
             self.method = importlib.import_module('surmise_b200.utilitiesmethods.' + sampler)
         except ImportError:
             raise ValueError("sampler '%s' is not available without surmise installed "
-                             "(surmise_b200 ships: PTLMC_B200)." % sampler)
+                             "(surmise_b200 ships: PTLMC_B200, LMC_B200, metropolis_hastings_B200)." % sampler)
         self.sampler_info = self.method.sampler(self.logpost_func, self.draw_func, **self.options)
         if 'theta' not in self.sampler_info.keys():
             raise ValueError('A sample from a posterior distribution is required.')

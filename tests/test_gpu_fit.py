@@ -337,3 +337,44 @@ def test_calibration_with_ptlmc_b200_sampler():
     report('calibration_ptlmc_b200', err0=float(err[0]), err1=float(err[1]), mean_batch=ncalls['rows'] / ncalls['n'])
     assert np.all(err < 0.1)
     assert ncalls['rows'] / ncalls['n'] > 10                # batched log-posterior calls, also in the pre-optimiser
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,opts', [('LMC_B200', {'numsamp': 800}),
+                                       ('metropolis_hastings_B200', {'numsamp': 4000, 'numchain': 128,
+                                                                     'burnSamples': 300,
+                                                                     'stepParam': np.array([0.03, 0.03])})])
+def test_calibration_with_batched_sampler_plugins(name, opts):
+    """directbayeswoodbury_B200 driven by the other two batched sampler plugins."""
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
+    from synth import make_observation
+    x, theta, f, truth = make_simulator(150, 2, 25, 4, seed=21)
+    np.random.seed(21)
+    fi = _facade_fit(M, x, theta, f)
+    emu = _ShimEmulator(M, fi, theta)
+    theta_true, y, yvar = make_observation(truth, 2, seed=22)
+    rows = []
+
+    class prior:
+        @staticmethod
+        def lpdf(th):
+            th = np.atleast_2d(th)
+            rows.append(th.shape[0])
+            return np.where(np.all((th >= 0) & (th <= 1), axis=1), 0.0, -np.inf).reshape(-1, 1)
+
+        @staticmethod
+        def lpdf_grad(th):
+            return np.zeros_like(np.atleast_2d(th))
+
+        @staticmethod
+        def rnd(n):
+            return np.random.uniform(size=(n, 2))
+    cal = {'thetaprior': prior, 'yvar': yvar}
+    np.random.seed(6)
+    C.fit(cal, emu, x, y, sampler=name, **opts)
+    assert cal['thetarnd'].shape == (opts['numsamp'], 2)
+    err = np.abs(cal['thetarnd'].mean(0) - theta_true[0])
+    report('calibration_' + name, err0=float(err[0]), err1=float(err[1]), mean_batch=float(np.mean(rows)))
+    assert np.all(err < 0.1)
+    assert np.mean(rows) > 10

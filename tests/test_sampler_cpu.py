@@ -67,3 +67,60 @@ def test_dispatcher_contract():
     from surmise_b200.utilities import sampler
     with pytest.raises(ValueError):
         sampler(lambda t: t, lambda n: None, sampler='does_not_exist')
+
+
+# ---- metropolis_hastings_B200 / LMC_B200 against chains drawn by the reference samplers (tests/golden/samplers.npz)
+def _golden_samplers():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'samplers.npz'))
+
+
+@pytest.mark.parametrize('step', ['normal', 'uniform'])
+def test_mh_single_chain_reproduces_reference_chain(step):
+    from surmise_b200.utilitiesmethods import metropolis_hastings_B200 as S
+    from synth import boxed_logpost, box_draws
+    gold = _golden_samplers()
+    np.random.seed(11)
+    out = S.sampler(boxed_logpost, box_draws, numsamp=400, stepType=step, burnSamples=150)
+    assert np.array_equal(out['theta'], gold['mh_%s_theta' % step])
+    assert out['acc_rate'] == float(gold['mh_%s_acc' % step])
+    assert np.array_equal(out['lpostlist'], gold['mh_%s_lpostlist' % step])
+
+
+def test_mh_population_batches_every_step_and_recovers_target():
+    from surmise_b200.utilitiesmethods import metropolis_hastings_B200 as S
+    from synth import boxed_logpost, box_draws, _MU
+    rows = []
+
+    def logpost(theta, return_grad=False):
+        rows.append(theta.shape[0])
+        return boxed_logpost(theta)
+    np.random.seed(5)
+    out = S.sampler(logpost, box_draws, numsamp=6000, numchain=64, burnSamples=400,
+                    stepParam=np.array([0.15, 0.1, 0.08]))
+    assert out['theta'].shape == (6000, 3) and set(rows) == {64}
+    assert len(rows) == 400 + (-(-6000 // 64))
+    assert 0.1 < out['acc_rate'] < 0.9
+    assert np.all(np.abs(out['theta'].mean(0) - _MU) < 0.05)
+    assert np.all(np.abs(out['theta'].std(0) - np.array([0.2, 0.1414, 0.1])) < 0.04)
+
+
+@pytest.mark.parametrize('with_grad', [True, False])
+def test_lmc_reproduces_reference_draws(with_grad):
+    from surmise_b200.utilitiesmethods import LMC_B200 as S
+    from synth import gaussian_logpost, box_draws
+    gold = _golden_samplers()
+    rows = []
+
+    def logpost(theta, return_grad=True):
+        rows.append(np.atleast_2d(theta).shape[0])
+        if with_grad:
+            return gaussian_logpost(theta, return_grad=return_grad)
+        return gaussian_logpost(theta, return_grad=False)
+    np.random.seed(12 if with_grad else 13)
+    out = S.sampler(logpost, box_draws, numsamp=500)
+    want = gold['lmc_grad_theta' if with_grad else 'lmc_nograd_theta']
+    assert out['theta'].shape == want.shape
+    assert np.allclose(out['theta'], want, rtol=0, atol=1e-12)
+    # the polishing stage is batched: ten optimisers per call until the first of them converges
+    assert 10 in rows and rows.count(1) < rows.count(10)
