@@ -557,6 +557,43 @@ def predictlpdf(predinfo, f, addvar=0, **kwargs):
     return (-likv / 2).reshape(-1, 1), -dlikv / 2
 
 
+def supplementtheta(fitinfo, size, theta, thetachoices, choicecosts, cal, **kwargs):
+    """Suggest `size` new parameters out of `thetachoices` (PCGPwM.py:367-530), as the reference behaves today.
+
+    The reference's selection and obviation criteria are commented out (PCGPwM.py:468-478, 517-526): every
+    criterion it compares is an array of zeros, so a pick is `argmax(0 / choicecosts)` over the remaining choices
+    (the first one for positive costs), `info['crit']` is 0 / cost and no pending run is ever suggested for
+    obviation.  The covariance matrices it still builds never reach the result and are not computed here; the
+    zero criteria go through the same floating-point expressions so signed-zero / NaN costs select as they do there.
+    kwargs: 'pending', 'costpending', 'includepending' as in the reference.  Returns (theta (size, d), info)."""
+    if theta is None:
+        raise ValueError('this method is designed to take in the theta values.')
+    nfit, d = fitinfo['theta'].shape
+    include = kwargs.get('includepending') is True
+    costs = np.asarray(choicecosts)
+    if include:
+        base = kwargs['costpending'] if 'costpending' in kwargs else np.mean(costs)
+        costpending = base * np.ones(nfit)
+    poss = np.asarray(thetachoices)
+    critsave = np.zeros(poss.shape[0])
+    picks = np.zeros((size, d))
+    with np.errstate(divide='ignore', invalid='ignore'):
+        for j in range(size):
+            if poss.shape[0] < 1.5:
+                break
+            crit = np.zeros(poss.shape[0])
+            jstar = np.argmax(crit / costs)
+            critsave[j] = crit[jstar] / costs[jstar]
+            picks[j] = poss[jstar]
+            poss = np.delete(poss, jstar, 0)
+            costs = np.delete(costs, jstar)
+        info = {'crit': critsave}
+        if include:
+            critpend = np.zeros(nfit)
+            info['obviatesugg'] = np.where((np.mean(critsave[:size]) > critpend / costpending) > 0.5)[0]
+    return picks, info
+
+
 def _param_desc(fitinfo):
     """Human-readable summary used by emulator.__repr__ (PCGPwM.py:938-964)."""
     el = fitinfo['emulist']

@@ -145,3 +145,21 @@ def test_predictlpdf_matches_reference(golden, tag):
         assert np.max(np.abs(dlp - g['dlpdf'])) / np.max(np.abs(g['dlpdf'])) < 1e-9
     pi['return_grad'] = False
     assert np.allclose(M.predictlpdf(pi, g['lpdf_f'], addvar=0.003), g['lpdf'], rtol=1e-9, atol=1e-9)
+
+
+def test_supplementtheta_matches_reference_outputs():
+    """PCGPwM_B200.supplementtheta against the reference's function (tests/golden/supplement.npz)."""
+    import os
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'supplement.npz'))
+    fitinfo = {'theta': g['theta']}
+    for name, kw in (('plain', {}), ('costs', {}),
+                     ('pending', {'pending': g['pending'], 'includepending': True, 'costpending': 0.3})):
+        th, info = M.supplementtheta(fitinfo, 4, g['new'], g['choices'].copy(), g[name + '_costs'].copy(), None, **kw)
+        assert np.array_equal(th, g[name + '_theta'])
+        assert np.array_equal(info['crit'], g[name + '_crit'])
+        assert np.array_equal(np.signbit(info['crit']), np.signbit(g[name + '_crit']))
+        if name == 'pending':
+            assert np.array_equal(info['obviatesugg'], g[name + '_obviate'])
+    with pytest.raises(ValueError):
+        M.supplementtheta(fitinfo, 4, None, g['choices'], np.ones(9), None)
