@@ -443,6 +443,27 @@ def import_state(theta, pc, gvar_damped, hyps, hypinds, pcti, spc):
     return emulist, fitter.device_state(emulist, spc, pcti)
 
 
+def adopt(fitinfo):
+    """Attach the device state to a `fitinfo` produced by the reference's own PCGPwM.fit (no optimisation).
+
+    Factors R at the stored hyper-parameters of every component (emulist[k]['hyp'], 'hypind'; PCGPwM.py:810-846)
+    and keeps the reference's PCA (pc, pcti, standardpcinfo).  After this, PCGPwM_B200.predict and
+    directbayeswoodbury_B200 work on an emulator that was fitted on the CPU with method='PCGPwM':
+        PCGPwM_B200.adopt(emu._info)
+    directbayeswoodbury_B200 does it on first use."""
+    need = ('emulist', 'pc', 'pcti', 'standardpcinfo', 'unscaled_pcstdvar', 'theta', 'eta', 'dampalpha')
+    if not isinstance(fitinfo, dict) or any(k not in fitinfo for k in need):
+        raise ValueError('adopt() needs the fitinfo dictionary of an emulator fitted with PCGPwM.')
+    theta = np.asarray(fitinfo['theta'], dtype=np.float64)
+    fitter = _GPFitter(fitinfo, theta, -10, -20, None, None)
+    hyps = np.array([e['hyp'] for e in fitinfo['emulist']], dtype=np.float64)
+    hypinds = np.array([e['hypind'] for e in fitinfo['emulist']]).astype(int)
+    rows = [np.arange(fitter.n)] * hyps.shape[0]
+    emulist = fitter._finalise(hyps, hypinds, rows)
+    fitinfo['_b200'] = fitter.device_state(emulist, fitinfo['standardpcinfo'], fitinfo['pcti'])
+    return fitinfo
+
+
 # ------------------------------------------------------------------------------------------------
 # predict
 # ------------------------------------------------------------------------------------------------

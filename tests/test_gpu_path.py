@@ -233,6 +233,32 @@ def test_woodbury_loglik_golden(ops, golden, tag):
     assert e_l < 10 * tol and e_d < 100 * tol
 
 
+@pytest.mark.parametrize('tag', ['c1', 'misspd'])
+def test_calibration_adopts_reference_fitted_emulator(ops, golden, tag):
+    """A fitinfo laid out as the reference's PCGPwM.fit leaves it (no device state): directbayeswoodbury_B200
+    factors it on first use and reproduces the reference's log-likelihoods."""
+    from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    g = golden('emu_' + tag)
+    k = g['st_hyp'].shape[0]
+    fitinfo = {'method': 'PCGPwM', 'theta': g['st_theta'], 'x': g['in_x'], 'pc': g['st_pc'], 'pcti': g['st_pcti'],
+               'unscaled_pcstdvar': g['st_unscaled_pcstdvar'], 'eta': 10, 'dampalpha': 0.3,
+               'standardpcinfo': {'offset': g['st_offset'], 'scale': g['st_scale'], 'extravar': g['st_extravar']},
+               'emulist': [{'hyp': g['st_hyp'][j], 'hypind': int(g['st_hypind'][j])} for j in range(k)]}
+    emu = _Emu(M, fitinfo)
+    ll, dll = C.loglik_grad({'yvar': g['yvar']}, emu, g['thetanew'], g['y'], g['in_x'])
+    assert '_b200' in fitinfo
+    tol = max(1e-9, 100 * EPS * float(g['st_condR'].max()))
+    e_l = float(np.max(np.abs(ll - g['loglik']) / np.abs(g['loglik'])))
+    report('loglik_adopted_' + tag, ll=e_l, dll=rel(dll, g['dloglik']))
+    assert e_l < 10 * tol and rel(dll, g['dloglik']) < 100 * tol
+    pred = {}
+    M.predict(pred, fitinfo, g['in_x'], g['thetanew'])
+    assert rel(pred['mean'], g['mean']) < 1e-6 and rel(pred['var'], g['var']) < 1e-6
+    with pytest.raises(ValueError):
+        M.adopt({'theta': g['st_theta']})
+
+
 def test_woodbury_kernel_isolated(ops, golden):
     """Feed the reference's own PC-space predictions to the kernel: 1e-9 per theta, no GP error."""
     for tag in ['c1', 'trig', 'd1']:
