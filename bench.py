@@ -97,16 +97,36 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(self.rows)}
 
 
+def cpu_functions():
+    """(negloglik, negloglikgrad, kind) of the CPU arm.
+
+    kind 'reference': the unmodified reference's own PCGPwM.__negloglik / __negloglikgrad, when it is installed in the
+    git-ignored baseline/_ref (pip install --target baseline/_ref; it travels to the GPU box with the snapshot).
+    kind 'port': otherwise the oracle's restatement of the same eigh-based algorithm (oracle/pcgpwm_oracle.py)."""
+    ref_dir = os.path.join(ROOT, 'baseline', '_ref')
+    if os.path.isdir(os.path.join(ref_dir, 'surmise')):
+        try:
+            if ref_dir not in sys.path:
+                sys.path.insert(0, ref_dir)
+            import importlib
+            mod = importlib.import_module('surmise.emulationmethods.PCGPwM')
+            return getattr(mod, '__negloglik'), getattr(mod, '__negloglikgrad'), 'reference'
+        except Exception:
+            pass
+    from oracle import pcgpwm_oracle as po
+    return po.negloglik_eigh, po.negloglikgrad_eigh, 'port'
+
+
 def cpu_nll_grad_sample(w, npcs=1):
     """Reference-algorithm NLL + gradient (eigh form, PCGPwM.py:850-907) for `npcs` components on the host."""
-    from oracle import pcgpwm_oracle as po
+    nll_fn, grad_fn, _kind = cpu_functions()
     n = w['theta'].shape[0]
     t0 = time.perf_counter()
     out = []
     for j in range(npcs):
         info = {'theta': w['theta'], 'g': w['pc'][:, j], 'gvar': np.zeros(n), 'sig2ofconst': 0.01,
                 'hypregmean': w['mean'], 'hypregstd': w['std']}
-        out.append((po.negloglik_eigh(w['hyps'][j], info), po.negloglikgrad_eigh(w['hyps'][j], info)))
+        out.append((nll_fn(w['hyps'][j], info), grad_fn(w['hyps'][j], info)))
     return npcs / (time.perf_counter() - t0), out
 
 
@@ -120,11 +140,13 @@ def host_threads():
 
 
 def run_reference(args):
-    """CPU arm: the oracle's restatement of the reference algorithm (numpy + LAPACK eigh, all host threads)."""
+    """CPU arm: the reference's NLL + gradient (baseline/_ref when installed, else the oracle's restatement of the
+    same algorithm), numpy + LAPACK eigh on all host threads."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     w = workload()
+    kind = cpu_functions()[2]
     for _ in range(args.warmup if args.warmup < 2 else 1):      # one untimed pass is enough to page LAPACK in
         cpu_nll_grad_sample(w, 1)
     t0 = time.perf_counter()
@@ -136,9 +158,12 @@ def run_reference(args):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': 'C2: PCGPwM n=2000 d=8 m=500 k=20; NLL+grad at full n (PCGPwM.py:850-907)',
-                       'note': 'each step = 1 of the 20 components (bounded sample); eigh-based numpy port of the '
-                               'reference algorithm (oracle/pcgpwm_oracle.py), checked bit-exact against surmise'},
-            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port',
+                       'note': 'each step = 1 of the 20 components (bounded sample); ' +
+                               ("surmise's own PCGPwM.__negloglik + __negloglikgrad from baseline/_ref"
+                                if kind == 'reference' else
+                                'eigh-based numpy port of the reference algorithm (oracle/pcgpwm_oracle.py), '
+                                'checked bit-exact against surmise')},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': host_threads(), 'kind': kind,
                              'sample': '1 component x 1 NLL+grad evaluation per step'},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
@@ -300,7 +325,7 @@ def main():
             got = res[0].cpu().numpy()
             nerr = abs(got[0] - ref_out[0][0]) / (abs(ref_out[0][0]) + n)
             gerr = float(np.max(np.abs(got[1:1 + p] - ref_out[0][1])) / np.max(np.abs(ref_out[0][1])))
-            cpu = {'value': v, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port',
+            cpu = {'value': v, 'unit': UNIT, 'cores': host_threads(), 'kind': cpu_functions()[2],
                    'sample': '1 of %d components, one NLL+grad evaluation (eigh form, numpy/LAPACK)' % k,
                    'parity_vs_gpu': {'nll_rel': nerr, 'grad_rel': gerr}}
         line = {
