@@ -151,7 +151,9 @@ __device__ __forceinline__ void stage_scaled_n(double* dst, const double* __rest
     }
 }
 
-__global__ void __launch_bounds__(256, 2) gp_grad_contract_kernel(int n, int d, const double* __restrict__ thetab,
+// DT: compile-time bound on d (the per-dimension loops are unrolled into registers up to DT, not MAXD)
+template <int DT>
+__global__ void __launch_bounds__(256, DT <= 8 ? 3 : 2) gp_grad_contract_kernel(int n, int d, const double* __restrict__ thetab,
                                                                long strideTheta, const double* __restrict__ gvarb,
                                                                long strideGvar, const double* __restrict__ hypb,
                                                                const double* __restrict__ Rinvb, long ldr, long strideR,
@@ -180,9 +182,9 @@ __global__ void __launch_bounds__(256, 2) gp_grad_contract_kernel(int n, int d, 
     __syncthreads();
     const double cq = 0.5 * n / ((n + s0) * sig2hat[z]);           // PCGPwM.py:898-902
     const double omn = 1.0 - gc.nu;
-    double acc[MAXD], acc_g = 0.0, acc_v = 0.0, acc_n = 0.0;      // length-scales | gamma_d | h_v | h_nu
+    double acc[DT], acc_g = 0.0, acc_v = 0.0, acc_n = 0.0;      // length-scales | gamma_d | h_v | h_nu
 #pragma unroll
-    for (int k = 0; k < MAXD; k++) acc[k] = 0.0;
+    for (int k = 0; k < DT; k++) acc[k] = 0.0;
 
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int j = j0 + tx;
@@ -200,20 +202,22 @@ __global__ void __launch_bounds__(256, 2) gp_grad_contract_kernel(int n, int d, 
             }
             w *= 2.0;                                              // (a,b) and (b,a)
             const double* a = xa + r * XLD;
-            double prod = gc.c, ssum = 0.0, wsum[MAXD];
+            double prod = gc.c, ssum = 0.0, wsum[DT];
 #pragma unroll
-            for (int k = 0; k < MAXD; k++)
+            for (int k = 0; k < DT; k++)
                 if (k < d) {
                     double S = fabs(a[k] - b[k]);
                     double op = 1.0 + S;
                     prod *= op;
                     ssum -= S;
-                    wsum[k] = (S * S) * __drcp_rn(op);             // dR0/dgamma_k / R_pre
+                    // dR0/dgamma_k / R_pre.  (One reciprocal of the product plus leave-one-out products was
+                    // measured slower: the kernel is FP64-pipe bound and __drcp_rn is only a few DFMAs.)
+                    wsum[k] = (S * S) * __drcp_rn(op);
                 }
             double rp = prod * exp(ssum);
             double wr = w * omn * rp;
 #pragma unroll
-            for (int k = 0; k < MAXD; k++)
+            for (int k = 0; k < DT; k++)
                 if (k < d) acc[k] += wr * wsum[k];                 // (1-nu) dR0/dgamma_k
             acc_g += w * omn * gc.onemc * (gc.c - rp);             // (1-nu) dR0/dgamma_d
             acc_n -= w * gc.nu * omn * (rp + gc.onemc);            // nu (1-nu) (I - R0), PCGPwM.py:878
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(256, 2) gp_grad_contract_kernel(int n, int d, 
     // warp shuffles, then one pass through shared memory (fixed order)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < MAXD; k++)
+    for (int k = 0; k < DT; k++)
         if (k < d) {
             double sv = warp_sum(acc[k]);
             if (lane == 0) red[k][warp] = sv;
@@ -325,7 +329,13 @@ int gp_grad_contract(int batch, int n, int d, const double* theta, long strideTh
     SB_CHECK_ARG(d >= 1 && d <= MAXD, "gp_grad_contract: d=%d outside [1,%d]", d, MAXD);
     int ntiles = grad_contract_tiles(n);
     dim3 grid(ntiles, batch);
-    gp_grad_contract_kernel<<<grid, 256, 0, stream>>>(n, d, theta, strideTheta, gvar, strideGvar, hyp, Rinv, ldr,
+    if (d <= 4) gp_grad_contract_kernel<4><<<grid, 256, 0, stream>>>(n, d, theta, strideTheta, gvar, strideGvar, hyp, Rinv, ldr,
+                                                      strideR, alpha, strideAlpha, sig2hat, s0, partial, ntiles);
+    else if (d <= 8) gp_grad_contract_kernel<8><<<grid, 256, 0, stream>>>(n, d, theta, strideTheta, gvar, strideGvar, hyp, Rinv, ldr,
+                                                      strideR, alpha, strideAlpha, sig2hat, s0, partial, ntiles);
+    else if (d <= 12) gp_grad_contract_kernel<12><<<grid, 256, 0, stream>>>(n, d, theta, strideTheta, gvar, strideGvar, hyp, Rinv, ldr,
+                                                      strideR, alpha, strideAlpha, sig2hat, s0, partial, ntiles);
+    else gp_grad_contract_kernel<16><<<grid, 256, 0, stream>>>(n, d, theta, strideTheta, gvar, strideGvar, hyp, Rinv, ldr,
                                                       strideR, alpha, strideAlpha, sig2hat, s0, partial, ntiles);
     SB_LAUNCH_CHECK();
     gp_grad_finalize_kernel<<<batch, 32 * (d + 3), 0, stream>>>(d, ntiles, partial, hyp, regmean, regstd, grad);

@@ -51,10 +51,14 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
                                           int kbase, int k_hi, bool vec16, int tid) {
     const double* dummy = (const double*)((uintptr_t)G & ~(uintptr_t)15);
     if (KC) {
+        // chunk order: (16-byte half of a k-quad, row, k-quad).  A warp then writes 16 rows x 32 contiguous bytes of
+        // one k-quad = 512 contiguous bytes of shared memory (conflict-free; walking along k first put the four
+        // k-quads of a row 4 KB apart, a 4-way bank conflict on every staging write) and still reads whole 32-byte
+        // sectors from global memory
         constexpr int CHUNKS = BMN * (BK / 2);
 #pragma unroll
         for (int c = tid; c < CHUNKS; c += NTHREADS) {
-            int mn = c / (BK / 2), kl = 2 * (c % (BK / 2));
+            int mn = (c >> 1) % BMN, kl = 4 * (c / (2 * BMN)) + 2 * (c & 1);
             int gk = kbase + kl, gmn = mn0 + mn;
             bool rok = gmn < MN;
             bool v0 = rok && gk < k_hi, v1 = rok && (gk + 1) < k_hi;

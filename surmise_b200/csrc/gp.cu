@@ -60,7 +60,8 @@ constexpr int XLD = MAXD + 1;
 
 // Per (PC, 32 new thetas, 256 design points): partial sums over j of
 //   T1^2, r pw, and (with gradients) T2 dr_i, dr_i pw, where dr_i = dR0/dtheta*_i rebuilt from r.
-template <bool WANT_GRAD>
+// DT: compile-time bound on d for the register-resident per-dimension sums
+template <bool WANT_GRAD, int DT>
 __global__ void __launch_bounds__(256, 2) predict_partial_kernel(
     int n, int d, int B, const double* __restrict__ theta, const double* __restrict__ thetanew,
     const double* __restrict__ hypcovb, const int* __restrict__ fidx, const int* __restrict__ fu,
@@ -99,9 +100,9 @@ __global__ void __launch_bounds__(256, 2) predict_partial_kernel(
 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int b = b0 + tx;
-    double s1 = 0.0, s2 = 0.0, dv[MAXD], dp[MAXD];
+    double s1 = 0.0, s2 = 0.0, dv[DT], dp[DT];
 #pragma unroll
-    for (int i = 0; i < MAXD; i++) dv[i] = dp[i] = 0.0;
+    for (int i = 0; i < DT; i++) dv[i] = dp[i] = 0.0;
     if (b < B) {
         const double* rT = rTb + (long)u * strideU;
         const double* T1 = T1b + (long)f * strideT;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(256, 2) predict_partial_kernel(
             if (want_grad) {
                 double rp = r - cc.onemc;                          // R_pre
 #pragma unroll
-                for (int i = 0; i < MAXD; i++)
+                for (int i = 0; i < DT; i++)
                     if (i < d) {
                         double s = xb[tx * XLD + i] - xj[jl * XLD + i];
                         double dr = rp * (-cc.ginv[i] * s * __drcp_rn(1.0 + fabs(s)));   // matern_covmat.pyx:13-24
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256, 2) predict_partial_kernel(
             int i = (q - 2) >> 1;
             double sel = 0.0;
 #pragma unroll
-            for (int ii = 0; ii < MAXD; ii++)
+            for (int ii = 0; ii < DT; ii++)
                 if (ii == i) sel = ((q - 2) & 1) ? dp[ii] : dv[ii];
             v = sel;
         }
@@ -434,12 +435,17 @@ int gp_predict(int K, int nf, int nu, int n, int d, int B, const double* theta, 
     }
     {
         dim3 grid(cdiv(B, 32), nchunks, K);
-        if (want_grad)
-            predict_partial_kernel<true><<<grid, 256, 0, stream>>>(n, d, B, theta, thetanew, hypcov, fidx, fu, pw, rT, ldb,
-                                                                   strideT, T1, T2, strideT, 1, partial, nchunks, Q);
-        else
-            predict_partial_kernel<false><<<grid, 256, 0, stream>>>(n, d, B, theta, thetanew, hypcov, fidx, fu, pw, rT, ldb,
-                                                                    strideT, T1, T2, strideT, 0, partial, nchunks, Q);
+#define SB_PREDICT_PARTIAL(G, DTV)                                                                                  \
+    predict_partial_kernel<G, DTV><<<grid, 256, 0, stream>>>(n, d, B, theta, thetanew, hypcov, fidx, fu, pw, rT, ldb,   \
+                                                              strideT, T1, T2, strideT, G ? 1 : 0, partial, nchunks, Q)
+        if (want_grad) {
+            if (d <= 4) SB_PREDICT_PARTIAL(true, 4);
+            else if (d <= 8) SB_PREDICT_PARTIAL(true, 8);
+            else SB_PREDICT_PARTIAL(true, 16);
+        } else {
+            SB_PREDICT_PARTIAL(false, 1);
+        }
+#undef SB_PREDICT_PARTIAL
         SB_LAUNCH_CHECK();
         dim3 grid2(cdiv(B, 128), K);
         predict_reduce_kernel<<<grid2, 128, 0, stream>>>(K, d, B, ldb, nchunks, Q, partial, nug, sig2, want_grad,
