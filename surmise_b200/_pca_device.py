@@ -59,6 +59,45 @@ def _ridge_rows(basis, obs, cur, diag_add, torch, want_qih=False):
     return vec, term3
 
 
+def _missing_index(miss, torch):
+    """Padded column indices of the missing entries of each row: idx (nr, qmax) and valid mask (nr, qmax)."""
+    q = miss.sum(1)
+    qmax = int(q.max().item())
+    order = torch.argsort((~miss).to(torch.int8), dim=1, stable=True)      # missing columns first, in column order
+    idx = order[:, :qmax]
+    valid = torch.arange(qmax, device=miss.device)[None, :] < q[:, None]
+    return idx, valid
+
+
+def _impute_schur(Up, sp2, eps_impute, cur, obs, idx, valid, torch):
+    """The ridge update of the missing entries (PCGPwM.py:576-586) through the |missing| x |missing| system.
+
+    The reference solves, per row, the k x k system (H + D) sol = J with H = Up' diag(obs) Up, D = diag(eps / sp2),
+    J = Up' (obs * cur) and fills the missing entries with Up sol.  Up has orthonormal columns, so
+    H + D = Lam - M' M with Lam = I + D and M = Up[missing rows of this output row], and by the Woodbury identity the
+    filled values are  w = (I - P_mm)^-1 P_mo cur_o  with P = Up Lam^-1 Up' (m x m, once per sweep): one GEMM for
+    all rows plus a batched Cholesky of size |missing| instead of size k.  Early sweeps keep k ~ m components
+    (k^3 per row); |missing| is the missing fraction of m.  Returns the filled values, (nr, qmax), 0 where padded."""
+    lam_inv = sp2 / (sp2 + eps_impute)
+    P = (Up * lam_inv) @ Up.T
+    Z = (obs * cur) @ P                                            # (nr, m): P_{.,o} cur_o for every column
+    z = torch.gather(Z, 1, idx) * valid
+    nr, qmax = idx.shape
+    w = torch.zeros_like(z)
+    eye = torch.eye(qmax, dtype=Up.dtype, device=Up.device)
+    per_row = 8 * qmax * qmax * 3
+    step = max(1, min(nr, _CHUNK_BYTES // max(per_row, 1)))
+    for lo in range(0, nr, step):
+        hi = min(lo + step, nr)
+        ii = idx[lo:hi]
+        vv = valid[lo:hi].to(Up.dtype)
+        S = P[ii[:, :, None], ii[:, None, :]] * (vv[:, :, None] * vv[:, None, :])
+        S = eye - S                                                # padded rows / columns: identity
+        L = torch.linalg.cholesky(S)
+        w[lo:hi] = torch.cholesky_solve(z[lo:hi, :, None], L).squeeze(2)
+    return w * valid
+
+
 def standardize(f, eps_pc, eps_impute, n_iter=40):
     """f: (n, m) numpy with NaN/inf for missing.  Returns (standardpcinfo of numpy arrays, mof, mofrows)."""
     torch = _torch()
@@ -86,15 +125,21 @@ def standardize(f, eps_pc, eps_impute, n_iter=40):
         rows = torch.from_numpy(mofrows_np).to(dev)
         miss = torch.from_numpy(mof_np[mofrows_np]).to(dev)
         obs = (~miss).to(torch.float64)
+        idx, valid = _missing_index(miss, torch)
         for _ in range(n_iter):                                   # PCGPwM.py:573-587
             U, _S, lam = _left_singular(fs, torch)
             keep = (lam - eps_pc) > 0
             Up = U[:, keep]
             sp2 = lam[keep] - eps_pc
             cur = fs[rows]
-            vec, _ = _ridge_rows(Up, obs, cur, eps_impute / sp2, torch)
-            filled = vec @ (Up * (sp2 / eps_impute)).T
-            fs[rows] = torch.where(miss, filled, cur)
+            if Up.shape[1] > idx.shape[1]:                        # more components than missing entries per row
+                w = _impute_schur(Up, sp2, eps_impute, cur, obs, idx, valid, torch)
+                filled = cur.scatter(1, idx, torch.where(valid, w, torch.gather(cur, 1, idx)))
+                fs[rows] = filled
+            else:
+                vec, _ = _ridge_rows(Up, obs, cur, eps_impute / sp2, torch)
+                filled = vec @ (Up * (sp2 / eps_impute)).T
+                fs[rows] = torch.where(miss, filled, cur)
     U, S, lam = _left_singular(fs, torch)
     Up = U[:, (lam - eps_pc) > 0]
     resid = fs - (fs @ Up) @ Up.T
