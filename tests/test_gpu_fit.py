@@ -378,3 +378,27 @@ def test_calibration_with_batched_sampler_plugins(name, opts):
     report('calibration_' + name, err0=float(err[0]), err1=float(err[1]), mean_batch=float(np.mean(rows)))
     assert np.all(err < 0.1)
     assert np.mean(rows) > 10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag,method', [('knn', 'KNN'), ('br', 'BayesianRidge')])
+def test_pcgpwimpute_b200_matches_reference_fit(golden, tag, method):
+    """PCGPwImpute_B200 (sklearn completion + the device PCGPwM path) against a seeded fit and
+    prediction of the reference's PCGPwImpute (tests/golden/impute.npz)."""
+    from surmise_b200.emulationmethods import PCGPwImpute_B200 as M
+    g = golden('impute')
+    np.random.seed(41)
+    fi = {'method': 'PCGPwImpute_B200'}
+    M.fit(fi, g['x'], g['theta'], g[tag + '_f'], completionmethod=method)
+    assert np.allclose(fi['f'], g[tag + '_fcompleted'], rtol=1e-10, atol=1e-12)
+    hyp = np.array([e['hyp'] for e in fi['emulist']])
+    assert hyp.shape == g[tag + '_hyp'].shape
+    assert np.array_equal([e['hypind'] for e in fi['emulist']], g[tag + '_hypind'])
+    assert fi['param_desc'].startswith('\tcompletion method: IterativeImputer:' + method)
+    p = {}
+    M.predict(p, fi, g['x'], g['thetanew'])
+    e_h, e_m, e_v = rel(hyp, g[tag + '_hyp']), rel(p['mean'], g[tag + '_mean']), rel(p['var'], g[tag + '_var'])
+    report('pcgpwimpute_' + tag, hyp=e_h, mean=e_m, var=e_v)
+    assert e_h < 1e-5 and e_m < 1e-6 and e_v < 1e-5
+    with pytest.raises(ValueError):
+        M.fit({}, g['x'], g['theta'], g[tag + '_f'], completionmethod='nope')
