@@ -13,7 +13,7 @@ import importlib
 import sys
 
 EMULATION_METHODS = ('PCGPwM_B200', 'PCGPwImpute_B200')
-CALIBRATION_METHODS = ('directbayeswoodbury_B200',)
+CALIBRATION_METHODS = ('directbayeswoodbury_B200', 'mlbayeswoodbury_B200')
 UTILITIES_METHODS = ('PTLMC_B200', 'LMC_B200', 'metropolis_hastings_B200')
 
 __version__ = '0.1.0'

@@ -138,33 +138,42 @@ def loglik_grad(fitinfo, emu, theta, y, x):
     return packed[:, :1].copy(), packed[:, 1:].copy()
 
 
-def make_logpost(fitinfo, emu, x, y):
-    """The closure handed to the sampler (dbw.py:100-129) and the initial-draw function (132-146)."""
+def make_logpost(fitinfo, emu, x, y, fd_step=10 ** (-6), extra_logp=None, with_grad=True):
+    """The closure handed to the sampler (dbw.py:100-129) and the initial-draw function (132-146).
+
+    fd_step: step of the finite-difference prior gradient used when the prior has no lpdf_grad (dbw.py:82-98).
+    extra_logp: optional (value(theta) -> (B,1), grad(theta) -> (B,d)) pair added on the rows with finite prior
+    (mlbayeswoodbury's classifier term).  with_grad=False: the closure never returns gradients."""
     thetaprior = fitinfo['thetaprior']
-    if 'lpdf_grad' not in dir(thetaprior):                                    # dbw.py:82-98
+    if with_grad and 'lpdf_grad' not in dir(thetaprior):
         def lpdf_grad(theta):
             base = thetaprior.lpdf(theta)
             inds = np.where(np.isfinite(base))[0]
             grad = np.zeros((theta.shape[0], theta.shape[1]))
             for k in range(theta.shape[1]):
                 prop = copy.copy(theta)
-                prop[:, k] += 10 ** (-6)
-                grad[inds, k] = 10 ** 6 * (thetaprior.lpdf(prop[inds, :]) - base[inds]).reshape(len(inds),)
+                prop[:, k] += fd_step
+                grad[inds, k] = (1 / fd_step) * (thetaprior.lpdf(prop[inds, :]) - base[inds]).reshape(len(inds),)
             return grad
         thetaprior.lpdf_grad = lpdf_grad
 
     def logpostfull_wgrad(theta, return_grad=True):
         logpost = thetaprior.lpdf(theta)
         inds = np.where(np.isfinite(logpost))[0]
-        if return_grad:
+        if with_grad and return_grad:
             dlogpost = thetaprior.lpdf_grad(theta)
             if len(inds):
                 ll, dll = loglik_grad(fitinfo, emu, theta[inds, :], y, x)
                 logpost[inds] += ll
                 dlogpost[inds] += dll
+                if extra_logp is not None:
+                    logpost[inds] += extra_logp[0](theta[inds, :])
+                    dlogpost[inds] += extra_logp[1](theta[inds, :])
             return logpost, dlogpost
         if len(inds) > 0:
             logpost[inds] += loglik(fitinfo, emu, theta[inds, :], y, x)
+            if extra_logp is not None:
+                logpost[inds] += extra_logp[0](theta[inds, :])
         return logpost
 
     def draw_func(n):

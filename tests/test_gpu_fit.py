@@ -402,3 +402,74 @@ def test_pcgpwimpute_b200_matches_reference_fit(golden, tag, method):
     assert e_h < 1e-5 and e_m < 1e-6 and e_v < 1e-5
     with pytest.raises(ValueError):
         M.fit({}, g['x'], g['theta'], g[tag + '_f'], completionmethod='nope')
+
+
+@pytest.mark.gpu
+def test_mlbayeswoodbury_b200_adds_classifier_term():
+    """mlbayeswoodbury_B200 = directbayeswoodbury_B200's device log-likelihood + log acceptance probability of a
+    classifier over quadratic features (mlbayeswoodbury.py:111-164); SURVEY 8f row 4."""
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
+    from surmise_b200.calibrationmethods import mlbayeswoodbury_B200 as ML
+    from synth import make_observation
+    x, theta, f, truth = make_simulator(120, 2, 20, 3, seed=51)
+    np.random.seed(51)
+    fi = _facade_fit(M, x, theta, f)
+    emu = _ShimEmulator(M, fi, theta)
+    theta_true, y, yvar = make_observation(truth, 2, seed=52)
+
+    class prior:
+        @staticmethod
+        def lpdf(th):
+            th = np.atleast_2d(th)
+            return (-0.5 * np.sum((th - 0.5) ** 2, 1) / 0.3 ** 2
+                    + np.where(np.all((th >= 0) & (th <= 1), axis=1), 0.0, -np.inf)).reshape(-1, 1)
+
+        @staticmethod
+        def rnd(n):
+            return np.random.uniform(size=(n, 2))
+
+    class clf:                                          # logistic acceptance model over [t1, t2, t1^2, t1 t2, t2^2]
+        w = np.array([0.5, -1.0, 0.3, 0.8, -0.4])
+
+        @classmethod
+        def predict_proba(cls, feats):
+            assert feats.shape[1] == 5
+            p = 1 / (1 + np.exp(-(feats @ cls.w)))
+            return np.stack([1 - p, p], axis=1)
+    assert np.allclose(ML.quadratic_features(np.array([[2.0, 3.0]])), [[2, 3, 4, 6, 9]])
+    th = np.vstack([np.random.default_rng(1).uniform(0.05, 0.95, size=(9, 2)), [[1.5, 0.5]]])
+    cal = {'thetaprior': prior, 'yvar': yvar}
+    base, _ = C.make_logpost(cal, emu, x, y, fd_step=1e-3)
+    np.random.seed(3)
+    ML.fit(cal, emu, x, y, clf_method=clf, sampler='metropolis_hastings_B200', numsamp=300, numchain=32,
+           burnSamples=100, stepParam=np.array([0.03, 0.03]))
+    assert cal['thetarnd'].shape == (300, 2) and cal['lpdfapproxnorm_un'].shape == (300, 1)
+    # the stored un-normalised log-posterior is prior + device log-likelihood + classifier term
+    t = cal['thetarnd'][:20]
+    want = base(t, return_grad=False) + np.log(clf.predict_proba(ML.quadratic_features(t))[:, 1]).reshape(-1, 1)
+    assert rel(cal['lpdfapproxnorm_un'][:20], want) < 1e-9
+    # myusedir=False: the closure handed to the sampler must not return gradients
+    seen = {}
+
+    def fake_sampler(logpost_func, draw_func, **kw):
+        out = logpost_func(th)
+        seen['tuple'] = isinstance(out, tuple)
+        seen['val'] = out[0] if isinstance(out, tuple) else out
+
+        class R:
+            sampler_info = {'theta': th[:9]}
+        return R()
+    import surmise_b200.utilities as U
+    saved = U.sampler
+    try:
+        import sys
+        U.sampler = fake_sampler
+        if 'surmise.utilities' in sys.modules:
+            pytest.skip('surmise installed: dispatcher not patchable here')
+        ML.fit(dict(cal), emu, x, y, clf_method=clf, myusedir=False)
+        assert seen['tuple'] is False and np.isneginf(seen['val'][-1, 0])
+        ML.fit(dict(cal), emu, x, y, clf_method=clf, myusedir=True)
+        assert seen['tuple'] is True
+    finally:
+        U.sampler = saved
