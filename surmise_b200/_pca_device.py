@@ -169,7 +169,10 @@ def principal_components(spc, mof, mofrows, eps_pc, eps_impute):
     pct = basis * pcw / torch.sqrt(effn)
     out = {'pcw': pcw, 'pcto': basis.clone(), 'pct': pct, 'pcti': basis * (torch.sqrt(effn) / pcw),
            'pc': fs @ pct, 'unscaled_pcstdvar': pcstdvar}
-    out = {k: v.cpu().numpy() for k, v in out.items()}
-    for k in ('fs', 'U', 'S'):
-        spc[k] = spc[k].cpu().numpy()
+    from . import ops
+    keys = list(out)
+    host = ops.to_host([out[k] for k in keys] + [spc[k] for k in ('fs', 'U', 'S')])   # pinned copies, one sync
+    out = dict(zip(keys, host[:len(keys)]))
+    for k, v in zip(('fs', 'U', 'S'), host[len(keys):]):
+        spc[k] = v
     return out

@@ -525,29 +525,39 @@ def predict(predinfo, fitinfo, x, theta, **kwargs):
                                                 pv, pvar, dpv, dpvar, want_covx=return_covx)
     K = pv.shape[1]
 
-    def scatter(t, tail):
+    in_order = xnewind.shape[0] == nx and np.array_equal(xnewind, np.arange(nx))
+
+    def scatter(a, tail):
+        if in_order:                                   # every requested x row matched, in order: nothing to fill
+            return a
         out = np.full((nx,) + tail, np.nan)
-        out[xnewind] = t.cpu().numpy()
+        out[xnewind] = a
         return out
 
-    predinfo['mean'] = scatter(mean, (B,))
-    predinfo['var'] = scatter(var, (B,))
-    predinfo['extravar'] = st['extravar'][sel].cpu().numpy()
-    predinfo['predvars'] = pvar.cpu().numpy()
-    predinfo['predvecs'] = pv.cpu().numpy()
-    predinfo['phi'] = phi.cpu().numpy()
+    want_cg = return_grad and return_covx
+    if want_cg and not np.array_equal(xnewind, xind):
+        raise ValueError('Check shuffling of x indices within predictions.')   # PCGPwM.py:318-320
+    # one synchronisation for all results, copied through pinned host memory
+    (mean_h, var_h, ev_h, pvar_h, pv_h, phi_h, cxh_h, mg_h, dpvar_h, dpv_h, cg_h) = ops.to_host(
+        [mean, var, st['extravar'][sel], pvar, pv, phi, cxh if return_covx else None,
+         mg if return_grad else None, dpvar if return_grad else None, dpv if return_grad else None,
+         cg if want_cg else None])
+    predinfo['mean'] = scatter(mean_h, (B,))
+    predinfo['var'] = scatter(var_h, (B,))
+    predinfo['extravar'] = ev_h
+    predinfo['predvars'] = pvar_h
+    predinfo['predvecs'] = pv_h
+    predinfo['phi'] = phi_h
     predinfo['return_covx'] = return_covx
     predinfo['return_grad'] = return_grad
     if return_covx:
-        predinfo['covxhalf'] = scatter(cxh, (B, K))
+        predinfo['covxhalf'] = scatter(cxh_h, (B, K))
     if return_grad:
-        predinfo['mean_gradtheta'] = scatter(mg, (B, d))
-        predinfo['predvars_gradtheta'] = dpvar.cpu().numpy()
-        predinfo['predvecs_gradtheta'] = dpv.cpu().numpy()
+        predinfo['mean_gradtheta'] = scatter(mg_h, (B, d))
+        predinfo['predvars_gradtheta'] = dpvar_h
+        predinfo['predvecs_gradtheta'] = dpv_h
         if return_covx:
-            if not np.array_equal(xnewind, xind):
-                raise ValueError('Check shuffling of x indices within predictions.')   # PCGPwM.py:318-320
-            predinfo['covxhalf_gradtheta'] = cg.cpu().numpy()
+            predinfo['covxhalf_gradtheta'] = cg_h
     return
 
 
