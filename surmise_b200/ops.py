@@ -23,7 +23,7 @@ def _stream(torch):
     return torch.cuda.current_stream().cuda_stream
 
 
-_PIN_LIMIT = 1 << 30        # results above this size are copied through pageable memory
+_PIN_LIMIT = 4 << 30        # results above this size are copied through pageable memory
 
 
 def to_host(tensors):
