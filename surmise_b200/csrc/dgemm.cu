@@ -141,6 +141,16 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 1
     const bool c16 = ((p.ldc & 1) == 0) && (((uintptr_t)C & 15) == 0);
     const double alpha = p.alpha, beta = p.beta;
 
+    // the cp.async prologue goes out first so that its latency overlaps the (blocking) loads of the C tile below
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < ktiles) {
+            load_tile<BM, AKC, NTHREADS>(As + s * A_TILE, A, p.lda, m0, p.M, k_lo + s * BK, k_hi, a16, tid);
+            load_tile<BN, BKC, NTHREADS>(Bs + s * B_TILE, B, p.ldb, n0, p.N, k_lo + s * BK, k_hi, b16, tid);
+        }
+        cp_async_commit();
+    }
+
     // beta * C is folded into the accumulators up front: alpha (A B' + (beta/alpha) C).  The C loads then overlap
     // the cp.async prologue instead of serialising (load -> fma -> store per fragment) in the epilogue.
     double acc[MI][NI][2];
@@ -167,15 +177,6 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 1
             acc[i][j][0] = cscale * c0;
             acc[i][j][1] = cscale * c1;
         }
-    }
-
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < ktiles) {
-            load_tile<BM, AKC, NTHREADS>(As + s * A_TILE, A, p.lda, m0, p.M, k_lo + s * BK, k_hi, a16, tid);
-            load_tile<BN, BKC, NTHREADS>(Bs + s * B_TILE, B, p.ldb, n0, p.N, k_lo + s * BK, k_hi, b16, tid);
-        }
-        cp_async_commit();
     }
 
     // warp-level k-range: inside the CTA's k-range a warp whose rows (columns) lie deeper in the triangle only
