@@ -473,3 +473,42 @@ def test_mlbayeswoodbury_b200_adds_classifier_term():
         assert seen['tuple'] is True
     finally:
         U.sampler = saved
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag', ['full', 'miss'])
+def test_indgp_b200_matches_reference_fit(golden, tag):
+    """indGP_B200 (one GP per output row on the PCGPwM kernels) against a fit and prediction of
+    the reference's indGP (tests/golden/indgp.npz); 'miss' has rows observed at different parameter subsets."""
+    from surmise_b200.emulationmethods import indGP_B200 as M
+    g = golden('indgp')
+    fi = {'method': 'indGP_B200'}
+    M.fit(fi, g['x'], g['theta'], g[tag + '_f'])
+    hyp = np.array([e['hyp'] for e in fi['emulist']])
+    sig2 = np.array([e['sig2'] for e in fi['emulist']])
+    p = {}
+    M.predict(p, fi, g['x'], g['thetanew'], return_grad=True)
+    errs = {'hyp': rel(hyp, g[tag + '_hyp']), 'sig2': rel(sig2, g[tag + '_sig2'])}
+    for k in ('mean', 'var', 'predvecs', 'predvars', 'covxhalf'):
+        assert p[k].shape == g[tag + '_' + k].shape
+        errs[k] = rel(p[k], g[tag + '_' + k])
+    report('indgp_' + tag, **errs)
+    assert errs['hyp'] < 1e-5 and errs['mean'] < 1e-6 and errs['var'] < 1e-5 and errs['covxhalf'] < 1e-5
+    # the gradient arrays (extra keys here) against central differences of the prediction
+    h = 1e-6
+    tp, tm = g['thetanew'].copy(), g['thetanew'].copy()
+    tp[:, 0] += h
+    tm[:, 0] -= h
+    pp, pm = {}, {}
+    M.predict(pp, fi, g['x'], tp, return_covx=False)
+    M.predict(pm, fi, g['x'], tm, return_covx=False)
+    nug = np.array([e['nug'] for e in fi['emulist']])
+    fd = ((pp['predvecs'] - pm['predvecs']) / (2 * h)).T                      # (B, nx)
+    assert rel(p['predvecs_gradtheta'][:, :, 0], fd * (1 - nug)) < 1e-5       # (1 - nug) twice, as the reference
+    fdv = ((pp['predvars'] - pm['predvars']) / (2 * h)).T
+    assert rel(p['predvars_gradtheta'][:, :, 0], fdv) < 1e-4
+    if tag == 'miss':
+        p1 = {}
+        M.predict(p1, fi, g['x'], g['thetanew'][:1])
+        assert rel(p1['mean'], g['miss_one_mean']) < 1e-6 and p1['covxhalf'].shape == g['miss_one_covxhalf'].shape
+        assert len(fi['_b200']['groups']) == 3
