@@ -29,7 +29,7 @@ def _device_state(emu):
     info = getattr(emu, '_info', None)
     if isinstance(info, dict) and '_b200' not in info and 'emulist' in info and 'unscaled_pcstdvar' in info:
         _emu_method.adopt(info)                      # an emulator fitted by the reference's PCGPwM: factor on the device
-    if not isinstance(info, dict) or '_b200' not in info:
+    if not isinstance(info, dict) or 'phi' not in info.get('_b200', {}):        # e.g. an indGP_B200 emulator
         raise ValueError("directbayeswoodbury_B200 needs an emulator fitted with method='PCGPwM_B200' "
                          "(or the reference's 'PCGPwM').")
     return info
