@@ -4,7 +4,7 @@ One-off validation, not part of tests/ or bench.py: it needs the unmodified refe
 baseline/_ref (python -m pip install --no-index --no-build-isolation --no-deps --target baseline/_ref <copy of
 /root/reference>), which travels to the GPU box with the snapshot.  The selected test files are copied to a
 scratch directory with the method names swapped ('PCGPwM' -> 'PCGPwM_B200', 'PCGPwImpute' -> 'PCGPwImpute_B200',
-'directbayeswoodbury' -> 'directbayeswoodbury_B200', 'mlbayeswoodbury' -> 'mlbayeswoodbury_B200', 'indGP' -> 'indGP_B200') and a conftest that calls surmise_b200.register(); pytest then runs them through
+'directbayeswoodbury' -> 'directbayeswoodbury_B200', 'mlbayeswoodbury' -> 'mlbayeswoodbury_B200', 'indGP' -> 'indGP_B200', 'PCSK' -> 'PCSK_B200') and a conftest that calls surmise_b200.register(); pytest then runs them through
 surmise's unmodified emulator / calibrator facades.
 
     python scripts/run_reference_suite.py [--orig]      # --orig: run the same files unmodified (CPU reference)
@@ -39,6 +39,7 @@ def main():
             text = re.sub(r"(['\"])PCGPwImpute\1", r"\1PCGPwImpute_B200\1", text)
             text = re.sub(r"(['\"])mlbayeswoodbury\1", r"\1mlbayeswoodbury_B200\1", text)
             text = re.sub(r"(['\"])indGP\1", r"\1indGP_B200\1", text)
+            text = re.sub(r"(['\"])PCSK\1", r"\1PCSK_B200\1", text)
         open(os.path.join(out, name), 'w').write(text)
     with open(os.path.join(out, 'conftest.py'), 'w') as fh:
         fh.write('import sys\nsys.path.insert(0, %r)\nsys.path.insert(0, %r)\n' % (REF, ROOT))

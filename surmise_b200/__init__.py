@@ -12,7 +12,7 @@ fallback -- calling any method without a CUDA device raises.
 import importlib
 import sys
 
-EMULATION_METHODS = ('PCGPwM_B200', 'PCGPwImpute_B200', 'indGP_B200')
+EMULATION_METHODS = ('PCGPwM_B200', 'PCGPwImpute_B200', 'indGP_B200', 'PCSK_B200')
 CALIBRATION_METHODS = ('directbayeswoodbury_B200', 'mlbayeswoodbury_B200')
 UTILITIES_METHODS = ('PTLMC_B200', 'LMC_B200', 'metropolis_hastings_B200')
 

@@ -123,7 +123,11 @@ def hyper_prior(theta, lognugmean, lognugLB, logvarc):
 class _GPFitter:
     """Hyper-parameter search for all PCs with device-side likelihoods (PCGPwM.py:678-847)."""
 
-    def __init__(self, fitinfo, theta, lognugmean, lognugLB, logvarc, nhyptrain):
+    def __init__(self, fitinfo, theta, lognugmean, lognugLB, logvarc, nhyptrain, variant=None):
+        """variant: None for PCGPwM, or a dict for a sibling method that shares the search (PCSK_B200):
+        prior (mean, lo, hi, std), nh_rule (d, n) -> int, share_bar (p) -> float, sweeps, gtol, skip_test,
+        use_gvar, s0_noleader (sig2ofconst of a search that has no leaders yet)."""
+        variant = variant or {}
         self.ops = _ops()
         torch = self.ops._torch()
         self.torch = torch
@@ -132,12 +136,24 @@ class _GPFitter:
         self.pc = fitinfo['pc']
         # damped per-row variance of the imputed PCs: min(eta, v / (1-v)^alpha)   (PCGPwM.py:755)
         v = fitinfo['unscaled_pcstdvar']
-        self.gvar = np.minimum(fitinfo['eta'], v / ((1 - v) ** fitinfo['dampalpha']))
-        self.mean, self.lo, self.hi, self.std = hyper_prior(theta, lognugmean, lognugLB, logvarc)
+        if variant.get('use_gvar', True):
+            self.gvar = np.minimum(fitinfo['eta'], v / ((1 - v) ** fitinfo['dampalpha']))
+        else:
+            self.gvar = np.zeros_like(self.pc)         # sized by the scores: PCSK's simsd may be stale after update/remove
+        if self.gvar.shape != self.pc.shape or self.pc.shape[0] != self.n:
+            raise ValueError('PC scores (%s), their variances (%s) and theta (%d rows) do not match.'
+                             % (self.pc.shape, self.gvar.shape, self.n))
+        self.mean, self.lo, self.hi, self.std = variant.get('prior') or hyper_prior(theta, lognugmean, lognugLB, logvarc)
         self.p = self.mean.shape[0]
         self.share_bar = 1.25 * (self.p + 5 * np.sqrt(self.p))       # PCGPwM.py:776-777, 808-809
+        if 'share_bar' in variant:
+            self.share_bar = variant['share_bar'](self.p)
+        self.sweeps = variant.get('sweeps', 3)
+        self.gtol = variant.get('gtol', 0.1)
+        self.skip_test = variant.get('skip_test', True)
+        self.s0_noleader = variant.get('s0_noleader')
         if nhyptrain is None:
-            self.nh = min(20 * self.d, self.n)
+            self.nh = variant['nh_rule'](self.d, self.n) if 'nh_rule' in variant else min(20 * self.d, self.n)
         elif nhyptrain == 'all':
             self.nh = self.n
         else:
@@ -168,13 +184,13 @@ class _GPFitter:
             data = self.ops.GPData(self.theta_dev, self.pc_dev[j], self.gvar_dev[j])
         return rows, data
 
-    def _nll(self, data, hyps, want_grad):
+    def _nll(self, data, hyps, want_grad, s0=SIG2_OF_CONST):
         self.nevals += len(hyps)
         if self._lockstep is not None:
             val, grad, info = self._lockstep.evaluate(data, np.asarray(hyps), want_grad)
         else:
             val, grad, info = self.ops.gp_nll_grad(data, np.asarray(hyps), self.mean_dev, self.std_dev,
-                                                   SIG2_OF_CONST, want_grad)
+                                                   s0, want_grad)
         bad = (info != 0) | ~np.isfinite(val)
         val = np.where(bad, _INFEASIBLE, val)
         if grad is not None:
@@ -186,25 +202,26 @@ class _GPFitter:
         rows, data = self._subsample(j, rows)
         hyp = 1 * self.mean
         lead = -1
+        s0 = self.s0_noleader if (cand is None and self.s0_noleader is not None) else SIG2_OF_CONST
         # candidate scan (PCGPwM.py:761-769): prior mean first, then every leader's hyper-parameters
         trial = [self.mean] if cand is None else [self.mean] + [c for c in cand]
-        vals, _ = self._nll(data, trial, want_grad=False)
+        vals, _ = self._nll(data, trial, want_grad=False, s0=s0)
         L0 = vals[0]
         for c in range(1, len(trial)):
             if vals[c] < L0:
                 hyp, L0, lead = trial[c], 1 * vals[c], cand_ids[c - 1]
         skip = False
-        if lead > -0.5 and cand.ndim > 1:                           # PCGPwM.py:771-781
-            _, dL = self._nll(data, [hyp], want_grad=True)
+        if self.skip_test and lead > -0.5 and cand.ndim > 1:        # PCGPwM.py:771-781
+            _, dL = self._nll(data, [hyp], want_grad=True, s0=s0)
             nc = cand.shape[0]
             scal = np.std(cand, 0) * nc / (1 + nc) + self.std / (1 + nc)
             skip = np.sum((dL[0] * scal) ** 2) < self.share_bar
         if not skip:                                                # PCGPwM.py:783-805
             def scaled(v):
-                val, grad = self._nll(data, [self.mean + v * self.std], want_grad=True)
+                val, grad = self._nll(data, [self.mean + v * self.std], want_grad=True, s0=s0)
                 return float(val[0]), grad[0] * self.std
             res = spo.minimize(scaled, (hyp - self.mean) / self.std, method='L-BFGS-B', jac=True,
-                               options={'gtol': 0.1},
+                               options={'gtol': self.gtol},
                                bounds=spo.Bounds((self.lo - self.mean) / self.std, (self.hi - self.mean) / self.std))
             hypn = self.mean + res.x * self.std
             likdiff = L0 - res.fun                                  # res.fun == nll(hypn): same kernel, same input
@@ -230,7 +247,7 @@ class _GPFitter:
         own = np.arange(k)
         hyps = [None] * k
         rows_used = [None] * k
-        for _sweep in range(3):
+        for _sweep in range(self.sweeps):
             for j in range(k):
                 if np.sum(hypinds == own) > 0.5:
                     leaders = np.where(hypinds == own)[0]

@@ -512,3 +512,33 @@ def test_indgp_b200_matches_reference_fit(golden, tag):
         M.predict(p1, fi, g['x'], g['thetanew'][:1])
         assert rel(p1['mean'], g['miss_one_mean']) < 1e-6 and p1['covxhalf'].shape == g['miss_one_covxhalf'].shape
         assert len(fi['_b200']['groups']) == 3
+
+
+@pytest.mark.gpu
+def test_pcsk_b200_matches_reference_fit(golden):
+    """PCSK_B200 (PCGPwM's device search with PCSK's constants) against a seeded fit and prediction
+    of the reference's PCSK (tests/golden/pcsk.npz)."""
+    from surmise_b200.emulationmethods import PCSK_B200 as M
+    g = golden('pcsk')
+    np.random.seed(71)
+    fi = {'method': 'PCSK_B200'}
+    M.fit(fi, g['x'], g['theta'], g['f'], simsd=g['simsd'])
+    hyp = np.array([e['hyp'] for e in fi['emulist']])
+    assert hyp.shape == g['hyp'].shape
+    assert np.array_equal([e['hypind'] for e in fi['emulist']], g['hypind'])
+    sign = np.sign(np.sum(fi['pc'] * g['pc'], 0))
+    assert rel(fi['pc'] * sign, g['pc']) < 1e-9 and rel(fi['pcstdvar'], g['pcstdvar']) < 1e-9
+    p = {}
+    M.predict(p, fi, g['x'], g['thetanew'], return_grad=True)
+    errs = {'hyp': rel(hyp, g['hyp']), 'sig2': rel([e['sig2'] for e in fi['emulist']], g['sig2'])}
+    for k in ('mean', 'var', 'mean_gradtheta'):
+        assert p[k].shape == g['p_' + k].shape
+        errs[k] = rel(p[k], g['p_' + k])
+    errs['predvars'] = rel(p['predvars'], g['p_predvars'])
+    errs['covx'] = rel(np.einsum('xbk,ybk->bxy', p['covxhalf'], p['covxhalf']),
+                       np.einsum('xbk,ybk->bxy', g['p_covxhalf'], g['p_covxhalf']))      # sign-free
+    report('pcsk', **errs)
+    assert errs['hyp'] < 1e-5 and errs['mean'] < 1e-6 and errs['var'] < 1e-5 and errs['mean_gradtheta'] < 1e-5
+    assert errs['covx'] < 1e-5 and str(g['desc'])[:60] == fi['param_desc'][:60]
+    with pytest.raises(AssertionError):
+        M.fit({}, g['x'], g['theta'], g['f'])
