@@ -39,19 +39,26 @@ def woodbury_constants(fitinfo, emu, x, y):
     """theta-independent device constants for (x, y, yvar); cached in fitinfo['_b200cal']."""
     if 'yvar' not in fitinfo:
         raise ValueError('Must provide yvar in this software.')            # dbw.py:266-269
-    ops = _ops()
-    torch = ops._torch()
+    cache = fitinfo.get('_b200cal')
     info = _device_state(emu)
     st = info['_b200']
+    # fast path for the sampler loop: the same x / y / yvar objects (with unchanged sums, in case they were edited in
+    # place) as last time -> skip row matching and the byte-wise comparison
+    ident = (id(x), id(y), id(fitinfo['yvar']), id(st['Linv']), float(np.sum(y)), float(np.sum(fitinfo['yvar'])))
+    if cache is not None and cache.get('ident') == ident and cache['refs'][0] is x and cache['refs'][1] is y:
+        return cache
+    ops = _ops()
+    torch = ops._torch()
+    y_in = y
     y = np.squeeze(np.asarray(y, dtype=np.float64))
     yvar = 1 * np.squeeze(np.asarray(fitinfo['yvar'], dtype=np.float64))
     xind, xnewind = _emu_method.match_rows(x, info['x'])
     nx = info['x'].shape[0] if x is None else x.shape[0]
     if xind.shape[0] != nx or not np.array_equal(xnewind, np.arange(nx)):
         raise ValueError('Every calibration x must match exactly one row of the emulator x.')
-    cache = fitinfo.get('_b200cal')
     key = (xind.tobytes(), y.tobytes(), yvar.tobytes(), id(st['Linv']))
     if cache is not None and cache['key'] == key:
+        cache['ident'], cache['refs'] = ident, (x, y_in, fitinfo['yvar'])
         return cache
     dev = st['phi'].device
     sel = torch.from_numpy(xind.astype(np.int64)).to(dev)
@@ -62,8 +69,8 @@ def woodbury_constants(fitinfo, emu, x, y):
     sinv = np.stack([1 / yv, 1 / (yv + np.abs(extravar))])                   # dbw.py:280-284 when triggered
     G = np.stack([phi.T @ (phi * s[:, None]) for s in sinv])
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    cache = {'key': key, 'phiT': t(phi.T), 'resid0': t(y - offset), 'extravar': t(extravar), 'sinv': t(sinv),
-             'G': t(G), 'xind': xind}
+    cache = {'key': key, 'ident': ident, 'refs': (x, y_in, fitinfo['yvar']), 'phiT': t(phi.T), 'resid0': t(y - offset),
+             'extravar': t(extravar), 'sinv': t(sinv), 'G': t(G), 'xind': xind}
     fitinfo['_b200cal'] = cache
     return cache
 
@@ -79,14 +86,59 @@ def loglik_device(fitinfo, emu, theta, y, x, return_grad=False, chunk=4096):
     return ops.woodbury_loglik(consts, pv, pvar, dpv, dpvar)
 
 
-def _packed(fitinfo, emu, theta, y, x, return_grad):
-    """numpy (B, 1) or (B, 1+d) from one fused device evaluation and one D2H copy."""
+_closure_buffers = {}
+
+
+def _buffers(torch, dev, B, d, K, return_grad):
+    """Per-shape staging of the sampler closure: pinned theta, device theta / predictions / results, pinned results.
+
+    A sampler evaluates the same population size thousands of times; allocating eight small tensors per call cost
+    more host time than launching the kernels."""
+    key = (dev.index, B, d, K, bool(return_grad))
+    buf = _closure_buffers.get(key)
+    if buf is None:
+        if len(_closure_buffers) > 32:
+            _closure_buffers.clear()
+        f64 = dict(dtype=torch.float64, device=dev)
+        width = 1 + (d if return_grad else 0)
+        res = torch.empty(B * width, **f64)
+        buf = {'theta_h': torch.empty((B, d), dtype=torch.float64).pin_memory(), 'theta_d': torch.empty((B, d), **f64),
+               'pred': (torch.empty((B, K), **f64), torch.empty((B, K), **f64),
+                        torch.empty((B, K, d), **f64) if return_grad else None,
+                        torch.empty((B, K, d), **f64) if return_grad else None),
+               'res_d': res, 'res_h': torch.empty(B * width, dtype=torch.float64).pin_memory(),
+               'out': (res[:B], res[B:].view(B, d) if return_grad else None,
+                       torch.empty(1, dtype=torch.int32, device=dev))}
+        _closure_buffers[key] = buf
+    return buf
+
+
+def _packed(fitinfo, emu, theta, y, x, return_grad, chunk=4096):
+    """numpy (B, 1) or (B, 1+d) from one fused device evaluation: theta goes up through pinned memory, the packed
+    [ll | dll] table comes back with one copy, and every intermediate lives in per-shape cached buffers."""
     ops = _ops()
     torch = ops._torch()
-    ll, dll, _ = loglik_device(fitinfo, emu, theta, y, x, return_grad=return_grad)
+    theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+    B, d = theta.shape
+    if B > chunk:                                     # large one-off populations: the general path
+        ll, dll, _ = loglik_device(fitinfo, emu, theta, y, x, return_grad=return_grad, chunk=chunk)
+        if return_grad:
+            return torch.cat([ll[:, None], dll], dim=1).cpu().numpy()
+        return ll.cpu().numpy().reshape(-1, 1)
+    consts = woodbury_constants(fitinfo, emu, x, y)
+    st = _device_state(emu)['_b200']
+    K = st['pw'].shape[0]
+    buf = _buffers(torch, consts['phiT'].device, B, d, K, return_grad)
+    buf['theta_h'].numpy()[...] = theta
+    buf['theta_d'].copy_(buf['theta_h'], non_blocking=True)
+    pv, pvar, dpv, dpvar = ops.gp_predict(st, buf['theta_d'], return_grad, out=buf['pred'])
+    ops.woodbury_loglik(consts, pv, pvar, dpv, dpvar, out=buf['out'])
+    buf['res_h'].copy_(buf['res_d'], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    host = buf['res_h'].numpy()
     if return_grad:
-        return torch.cat([ll[:, None], dll], dim=1).cpu().numpy()
-    return ll.cpu().numpy().reshape(-1, 1)
+        return np.concatenate([host[:B, None], host[B:].reshape(B, d)], axis=1)
+    return host[:B].reshape(-1, 1).copy()
 
 
 def _evaluate(fitinfo, emu, theta, y, x, return_grad):

@@ -260,10 +260,11 @@ def gp_weights(Linv, fidx, g, sig2ofconst=0.01):
     return pw, sig2
 
 
-def gp_predict(state, thetanew, want_grad=False):
+def gp_predict(state, thetanew, want_grad=False, out=None):
     """PC-space prediction (PCGPwM.py:219-270) from a device state dict (see emulation module).
 
     Returns device tensors predvecs, predvars (B,k) and, if want_grad, gradients (B,k,d).
+    out: optional (pv, pvar, dpv, dpvar) to write into (callers that evaluate the same shape repeatedly).
     """
     torch = _torch()
     tn = _f64(torch, thetanew)
@@ -272,10 +273,13 @@ def gp_predict(state, thetanew, want_grad=False):
     nf, n, ldl = state['Linv'].shape
     nu = state['hypcov'].shape[0]
     dev = tn.device
-    pv = torch.empty((B, K), dtype=torch.float64, device=dev)
-    pvar = torch.empty((B, K), dtype=torch.float64, device=dev)
-    dpv = torch.empty((B, K, d), dtype=torch.float64, device=dev) if want_grad else None
-    dpvar = torch.empty((B, K, d), dtype=torch.float64, device=dev) if want_grad else None
+    if out is not None:
+        pv, pvar, dpv, dpvar = out
+    else:
+        pv = torch.empty((B, K), dtype=torch.float64, device=dev)
+        pvar = torch.empty((B, K), dtype=torch.float64, device=dev)
+        dpv = torch.empty((B, K, d), dtype=torch.float64, device=dev) if want_grad else None
+        dpvar = torch.empty((B, K, d), dtype=torch.float64, device=dev) if want_grad else None
     nbytes = lib.sb200_gp_predict_workspace(K, nf, nu, n, d, B, int(want_grad))
     ws = workspace(nbytes)
     check(lib.sb200_gp_predict(K, nf, nu, n, d, B, _ptr(state['theta']), _ptr(tn), _ptr(state['hypcov']),
@@ -316,7 +320,7 @@ def woodbury_trigger(consts, pvar):
     return fired
 
 
-def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1):
+def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1, out=None):
     """Batched directbayeswoodbury log-likelihood (+ gradient) (dbw.py:261-383).
 
     consts: dict of device tensors phiT (k,m), resid0 (m), extravar (m), sinv (2,m), G (2,k,k).
@@ -329,9 +333,12 @@ def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1):
     want_grad = dpv is not None
     d = dpv.shape[2] if want_grad else 1
     dev = pv.device
-    ll = torch.empty(B, dtype=torch.float64, device=dev)
-    dll = torch.empty((B, d), dtype=torch.float64, device=dev) if want_grad else None
-    fired = torch.empty(1, dtype=torch.int32, device=dev)
+    if out is not None:                              # (ll, dll, fired) preallocated by the caller
+        ll, dll, fired = out
+    else:
+        ll = torch.empty(B, dtype=torch.float64, device=dev)
+        dll = torch.empty((B, d), dtype=torch.float64, device=dev) if want_grad else None
+        fired = torch.empty(1, dtype=torch.int32, device=dev)
     check(lib.sb200_woodbury_loglik(B, K, m, d, _ptr(pv), _ptr(pvar), _ptr(dpv), _ptr(dpvar), _ptr(consts['phiT']),
                                     _ptr(consts['resid0']), _ptr(consts['extravar']), _ptr(consts['sinv']),
                                     _ptr(consts['G']), int(want_grad), int(variant), _ptr(ll), _ptr(dll), _ptr(fired),
