@@ -58,6 +58,13 @@ void sb200_gp_force_blocked_path(int on);
 int sb200_gp_nll_small_profile(int batch, int n, int d, const double* theta, const double* g, const double* hyp,
                                const double* regmean, const double* regstd, double* nll, double* grad, int* info,
                                long long* stamps, void* workspace, size_t workspace_bytes, void* stream);
+/* Batched symmetric-positive-definite solve on the same register-resident sweep kernel, n <= sb200_gp_nll_small_max_n().
+ * A (batch, n+1, lda): lower triangle of S in rows 0..n-1 and the right-hand side z' as row n.  On return rows 0..n-1
+ * hold the lower triangle of S^-1 and row n holds (S^-1 z)'; logdet (batch, may be NULL) = log|S|; info per problem
+ * (LAPACK convention).  Replaces the per-row ridge solves of the imputation sweeps, PCGPwM.__standardizef
+ * (emulationmethods/PCGPwM.py:573-587), in their |missing| x |missing| Schur form. */
+int sb200_spd_solve_small(int batch, int n, double* A, long lda, long stride_a, double* logdet, int* info,
+                          void* stream);
 size_t sb200_gp_nll_grad_workspace(int batch, int n, int d, int want_grad);
 int sb200_gp_nll_grad(int batch, int n, int d, const double* theta, long stride_theta, const double* g,
                       long stride_g, const double* gvar, long stride_gvar, const double* hyp,

@@ -31,6 +31,7 @@ SIGNATURES = {
     'sb200_gemm_profile_dump': (_i, [_p, _p, _i]),
     'sb200_matern_covmat': (_i, [_p, _i, _p, _i, _i, _p, _p, _l, _p, _i, _p]),
     'sb200_gp_nll_small_max_n': (_i, []),
+    'sb200_spd_solve_small': (_i, [_i, _i, _p, _l, _l, _p, _p, _p]),
     'sb200_gp_force_blocked_path': (None, [_i]),
     'sb200_gp_nll_small_profile': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
     'sb200_gp_nll_grad_workspace': (_z, [_i, _i, _i, _i]),

@@ -87,14 +87,26 @@ def _impute_schur(Up, sp2, eps_impute, cur, obs, idx, valid, torch):
     eye = torch.eye(qmax, dtype=Up.dtype, device=Up.device)
     per_row = 8 * qmax * qmax * 3
     step = max(1, min(nr, _CHUNK_BYTES // max(per_row, 1)))
+    from . import ops
+    small = qmax <= ops.small_max_n()                 # the register-resident sweep kernel solves these directly
     for lo in range(0, nr, step):
         hi = min(lo + step, nr)
         ii = idx[lo:hi]
         vv = valid[lo:hi].to(Up.dtype)
         S = P[ii[:, :, None], ii[:, None, :]] * (vv[:, :, None] * vv[:, None, :])
         S = eye - S                                                # padded rows / columns: identity
-        L = torch.linalg.cholesky(S)
-        w[lo:hi] = torch.cholesky_solve(z[lo:hi, :, None], L).squeeze(2)
+        if small:
+            lda = (qmax + 7) // 8 * 8
+            A = torch.zeros((hi - lo, qmax + 1, lda), dtype=Up.dtype, device=Up.device)
+            A[:, :qmax, :qmax] = S
+            A[:, qmax, :qmax] = z[lo:hi]
+            info = ops.spd_solve_small(A, qmax)
+            if bool((info != 0).any()):
+                raise ValueError('imputation: a Schur system of the missing entries is not positive definite')
+            w[lo:hi] = A[:, qmax, :qmax]
+        else:
+            L = torch.linalg.cholesky(S)
+            w[lo:hi] = torch.cholesky_solve(z[lo:hi, :, None], L).squeeze(2)
     return w * valid
 
 

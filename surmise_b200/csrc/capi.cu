@@ -129,6 +129,12 @@ int sb200_gp_nll_grad(int batch, int n, int d, const double* theta, long stride_
 void sb200_gp_force_blocked_path(int on) { gp_force_blocked_path(on); }
 int sb200_gp_nll_small_max_n(void) { return gp_nll_small_max_n(); }
 
+int sb200_spd_solve_small(int batch, int n, double* A, long lda, long strideA, double* logdet, int* info,
+                          void* stream) {
+    SB_CHECK_ARG(A && info, "spd_solve_small: NULL pointer");
+    return spd_solve_small(batch, n, A, lda, strideA, logdet, info, ST(stream));
+}
+
 int sb200_gp_nll_small_profile(int batch, int n, int d, const double* theta, const double* g, const double* hyp,
                                const double* regmean, const double* regstd, double* nll, double* grad, int* info,
                                long long* stamps, void* workspace, size_t workspace_bytes, void* stream) {

@@ -13,6 +13,8 @@ int gp_nll_grad(int batch, int n, int d, const double* theta, long strideTheta, 
 void gp_force_blocked_path(int on);
 // single-CTA fused path for n <= gp_nll_small_max_n() (nll_small.cu); gp_nll_grad dispatches to it
 int gp_nll_small_max_n();
+int spd_solve_small(int batch, int n, double* A, long lda, long strideA, double* logdet, int* info,
+                    cudaStream_t stream);
 int gp_nll_grad_small(int batch, int n, int d, const double* theta, long strideTheta, const double* g, long strideG,
                       const double* gvar, long strideGvar, const double* hyp, const double* regmean,
                       const double* regstd, double s0, int want_grad, double* nll, double* grad, int* info,

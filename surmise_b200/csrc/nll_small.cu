@@ -179,7 +179,10 @@ __global__ void __launch_bounds__(256, 1) gp_sweep_small_kernel(SweepArgs p) {
     double ld = 0.0;                                               // sum log d_k = log|R|
     for (int k = tid; k < n; k += 256) ld += log(piv[k]);
     const double logdet = block_sum(ld, red);
-    if (tid == 0) {
+    if (tid == 0 && p.hyp == nullptr) {                            // plain SPD solve (spd_solve_small): no GP terms
+        if (p.nll) p.nll[z] = logdet;
+        p.info[z] = (s_bad == 0x7fffffff) ? 0 : s_bad;
+    } else if (tid == 0) {
         const double sig2hat = (s_qf + p.s0) / (n + p.s0);         // PCGPwM.py:863
         const int np = d + 3;
         const double* hyp = p.hyp + (long)z * np;
@@ -210,6 +213,28 @@ long lda_small(int n) { return round_up(n, 8); }
 
 int gp_nll_small_max_n() { return T16 * 13 - 1; }
 
+static int launch_sweep_for(const SweepArgs& a, int n, int batch, cudaStream_t stream) {
+    const int R = (n + 1 + T16 - 1) / T16;
+    if (R <= 4) return launch_sweep<4>(a, batch, stream);
+    if (R <= 6) return launch_sweep<6>(a, batch, stream);
+    if (R <= 8) return launch_sweep<8>(a, batch, stream);
+    if (R <= 10) return launch_sweep<10>(a, batch, stream);
+    if (R <= 11) return launch_sweep<11>(a, batch, stream);
+    return launch_sweep<13>(a, batch, stream);
+}
+
+// Batched SPD solve with the sweep kernel: A (batch, n+1, lda) holds lower(S) and the right-hand side as row n;
+// on return lower(S^-1) and (S^-1 z)' in row n.  Used by the device imputation (Schur systems of the missing entries).
+int spd_solve_small(int batch, int n, double* A, long lda, long strideA, double* logdet, int* info,
+                    cudaStream_t stream) {
+    SB_CHECK_ARG(batch > 0, "spd_solve_small: empty batch");
+    SB_CHECK_ARG(n >= 1 && n <= gp_nll_small_max_n(), "spd_solve_small: n=%d outside [1,%d]", n, gp_nll_small_max_n());
+    SB_CHECK_ARG(lda >= n && strideA >= (long)(n + 1) * lda, "spd_solve_small: bad layout");
+    SB_CHECK_ARG(info != nullptr, "spd_solve_small: info is NULL");
+    SweepArgs a{n, 0, A, lda, strideA, nullptr, nullptr, nullptr, 0.0, logdet, nullptr, info, nullptr};
+    return launch_sweep_for(a, n, batch, stream);
+}
+
 size_t gp_nll_small_workspace(int batch, int n, int want_grad) {
     Workspace w(nullptr, 0);
     w.take<double>((size_t)batch * (n + 1) * lda_small(n));
@@ -231,13 +256,7 @@ int gp_nll_grad_small(int batch, int n, int d, const double* theta, long strideT
     double* sig2hat = w.take<double>((size_t)batch);
     SB_TRY(gp_assemble(batch, n, d, theta, strideTheta, g, strideG, gvar, strideGvar, hyp, A, lda, strideA, stream));
     SweepArgs a{n, d, A, lda, strideA, hyp, regmean, regstd, s0, nll, sig2hat, info, stamps};
-    const int R = (n + 1 + T16 - 1) / T16;
-    if (R <= 4) SB_TRY(launch_sweep<4>(a, batch, stream));
-    else if (R <= 6) SB_TRY(launch_sweep<6>(a, batch, stream));
-    else if (R <= 8) SB_TRY(launch_sweep<8>(a, batch, stream));
-    else if (R <= 10) SB_TRY(launch_sweep<10>(a, batch, stream));
-    else if (R <= 11) SB_TRY(launch_sweep<11>(a, batch, stream));
-    else SB_TRY(launch_sweep<13>(a, batch, stream));
+    SB_TRY(launch_sweep_for(a, n, batch, stream));
     if (!want_grad) return 0;
     double* partial = w.take<double>((size_t)batch * grad_contract_tiles(n) * MAXP);
     return gp_grad_contract(batch, n, d, theta, strideTheta, gvar, strideGvar, hyp, regmean, regstd, A, lda, strideA,

@@ -212,6 +212,21 @@ def gp_nll_grad(data, hyp, regmean, regstd, sig2ofconst=0.01, want_grad=True, re
     return nll, grad, info
 
 
+def spd_solve_small(A, n):
+    """In-place batched SPD solve on the sweep kernel: A (batch, n+1, lda) = [lower(S); z'] -> [lower(S^-1); (S^-1 z)'].
+
+    Returns info (device int32, batch)."""
+    torch = _torch()
+    _need_cuda(A)
+    batch, rows, lda = A.shape
+    if rows != n + 1 or not A.is_contiguous():
+        raise ValueError('spd_solve_small: A must be a contiguous (batch, n+1, lda) tensor')
+    info = torch.empty(batch, dtype=torch.int32, device=A.device)
+    check(lib.sb200_spd_solve_small(batch, n, _ptr(A), lda, rows * lda, 0, _ptr(info), _stream(torch)),
+          'sb200_spd_solve_small')
+    return info
+
+
 def force_blocked_path(on):
     """Testing hook: send n <= small_max_n() problems through the blocked multi-launch path too."""
     lib.sb200_gp_force_blocked_path(int(bool(on)))

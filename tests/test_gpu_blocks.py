@@ -158,3 +158,33 @@ def test_large_factorisation_properties(ops):
     e2 = float(((Linv[0] @ L - torch.eye(n, dtype=torch.float64, device='cuda')).abs().max()).cpu())
     report('chol_large', n=n, LLt=e1, LinvL=e2)
     assert e1 < 1e-13 and e2 < 1e-9
+
+
+@pytest.mark.parametrize('n', [1, 7, 64, 130, 207])
+def test_spd_solve_small(ops, n):
+    """sb200_spd_solve_small (the sweep kernel as a batched SPD solver) against numpy."""
+    import torch
+    rng = np.random.default_rng(n)
+    batch = 5
+    X = rng.normal(size=(batch, n, n + 3))
+    S = X @ X.transpose(0, 2, 1) / (n + 3) + 0.1 * np.eye(n)
+    z = rng.normal(size=(batch, n))
+    lda = (n + 7) // 8 * 8
+    A = np.zeros((batch, n + 1, lda))
+    A[:, :n, :n] = S
+    A[:, n, :n] = z
+    Ad = dev(A)
+    info = ops.spd_solve_small(Ad, n)
+    torch.cuda.synchronize()
+    got = Ad.cpu().numpy()
+    assert not info.cpu().numpy().any()
+    want = np.linalg.solve(S, z[:, :, None])[:, :, 0]
+    Sinv = np.linalg.inv(S)
+    e_w = rel(got[:, n, :n], want)
+    e_i = max(rel(np.tril(got[b, :n, :n]), np.tril(Sinv[b])) for b in range(batch))
+    report('spd_solve_small', n=n, w=e_w, inv=e_i)
+    assert e_w < 1e-11 and e_i < 1e-11
+    bad = A.copy()
+    bad[0, 0, 0] = -1.0
+    info = ops.spd_solve_small(dev(bad), n)
+    assert info.cpu().numpy()[0] == 1 and not info.cpu().numpy()[1:].any()
