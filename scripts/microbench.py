@@ -118,6 +118,18 @@ for B in (1, 264, 2048, 16384):
         t, _ = timeit(lambda: C.loglik_device(cal, Emu, tn, y, x, return_grad=wg), reps=3, warm=1)
         flop = k * n * n * B * (2 if wg else 1)
         out[f'loglik_B{B}_grad{int(wg)}'] = {'s': t, 'theta_per_s': B / t, 'tflops': flop / t / 1e12}
+# standalone Matern covariance (HBM-write bound): R only, R + hyper-parameter gradient planes, R + d/dx1 planes
+for (n1, n2, dd) in ((8000, 8000, 10), (2000, 2000, 8), (2048, 2000, 8)):
+    x1 = torch.from_numpy(rng.uniform(size=(n1, dd))).cuda()
+    x2 = torch.from_numpy(rng.uniform(size=(n2, dd))).cuda()
+    gam = torch.from_numpy(np.append(rng.normal(size=dd) * 0.3, -0.5)).cuda()
+    for mode, planes in ((0, 0), (1, dd + 1), (2, dd)):
+        if n1 * n2 * (planes + 1) * 8 > 8e9:
+            continue
+        t, tb = timeit(lambda: ops.covmat_device(x1, x2, gam, mode), reps=5)
+        nbytes = 8.0 * n1 * n2 * (1 + planes) + 8.0 * dd * (n1 + n2)
+        out[f'covmat_{n1}x{n2}_d{dd}_mode{mode}'] = {'s': t, 'GBps': nbytes / t / 1e9, 'GBps_best': nbytes / tb / 1e9,
+                                                     'pairs_per_s': n1 * n2 / t}
 print(json.dumps(out, indent=1), flush=True)
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'microbench.json'), 'w'), indent=1)
