@@ -38,6 +38,8 @@ class Emu:
 
 
 tn = np.random.default_rng(1).uniform(size=(37, 3))
+pred_sharded = {}
+M.predict(pred_sharded, fi, x, tn, return_grad=True)       # factors came from their owner ranks
 full = C._packed({'yvar': yvar}, Emu, tn, y, x, True)
 shard = C._evaluate({'yvar': yvar, 'shard_theta': True}, Emu, tn, y, x, True)
 res = {'rank': rank, 'world': world, 'fit_identical_on_all_ranks': bool(same_everywhere),
@@ -51,5 +53,10 @@ if rank == 0:
     f1 = {'method': 'PCGPwM_B200'}
     M.fit(f1, x, theta, f, fit_mode='parallel')
     h1 = np.array([e['hyp'] for e in f1['emulist']])
+    p1 = {}
+    M.predict(p1, f1, x, tn, return_grad=True)
     print(json.dumps({'sharded_vs_single_rank_hyp_max_abs_diff': float(np.max(np.abs(h1 - hyp))),
+                      'sharded_factor_predict_max_abs_diff': float(max(np.max(np.abs(p1[k] - pred_sharded[k]))
+                                                                    for k in ('mean', 'var', 'mean_gradtheta'))),
+                      'distinct_factors': int(fi['_b200']['Linv'].shape[0]),
                       'same_hypind': bool(np.array_equal(inds, [e['hypind'] for e in f1['emulist']]))}), flush=True)

@@ -65,6 +65,23 @@ def block_partition(count, world):
     return sizes, starts
 
 
+def gather_blocks(comm, local, sizes, out):
+    """Assemble a batch whose contiguous blocks were computed by their owner ranks.
+
+    out: preallocated (sum(sizes), ...) tensor, same shape on every rank; `local` holds this rank's rows
+    [starts[rank], starts[rank+1]) (None if it owns nothing).  Every owner broadcasts its slice (NCCL over NVLink for
+    the full-data factors: C4 = 40 x 512 MB, against 0.5 s to factor them all on one GPU)."""
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    lo, hi = int(starts[comm.rank]), int(starts[comm.rank + 1])
+    if hi > lo:
+        out[lo:hi] = local
+    if comm.world > 1:
+        for r in range(comm.world):
+            if sizes[r]:
+                comm.dist.broadcast(out[int(starts[r]):int(starts[r + 1])], src=r)
+    return out
+
+
 def jacobi_sweeps(fit_one, k, p, comm, draw_rows, sweeps=3, start_hyps=None, start_inds=None, run_block=None):
     """Sharded variant of PCGPwM.__fitGPs (PCGPwM.py:678-722).
 

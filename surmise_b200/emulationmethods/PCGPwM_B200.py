@@ -277,7 +277,11 @@ class _GPFitter:
         hyps, hypinds, rows_used = _dist.jacobi_sweeps(one, k, self.p, comm, self._draw_rows,
                                                        start_hyps=start_hyps, start_inds=start_inds,
                                                        run_block=self._run_block_lockstep if self.lockstep else None)
-        return self._finalise(hyps, hypinds, rows_used)       # replicated on every rank (cheap next to the search)
+        self._comm = comm                                     # the distinct factors are sharded over the ranks as well
+        try:
+            return self._finalise(hyps, hypinds, rows_used)
+        finally:
+            self._comm = None
 
     lockstep = True      # batch the likelihood calls of this rank's PCs into one launch per optimiser step
 
@@ -324,7 +328,21 @@ class _GPFitter:
                 members.append(j)
             fidx[j] = keys[key]
         members = np.array(members)
-        Linv, clamped_f = self._factor_batch(members, hyps)
+        comm = getattr(self, '_comm', None)
+        if comm is not None and comm.world > 1 and len(members) > 1:
+            # each rank factors a contiguous block of the distinct problems; owners broadcast their factors
+            from .. import _dist
+            sizes, starts = _dist.block_partition(len(members), comm.world)
+            lo, hi = int(starts[comm.rank]), int(starts[comm.rank + 1])
+            ldl = (self.n + 7) // 8 * 8
+            Linv = torch.empty((len(members), self.n, ldl), dtype=torch.float64, device=self.theta_dev.device)
+            local, flags = (None, np.zeros(0, dtype=bool))
+            if hi > lo:
+                local, flags = self._factor_batch(members[lo:hi], hyps)
+            _dist.gather_blocks(comm, local, sizes, Linv)
+            clamped_f = comm.allgather_rows(flags.astype(np.float64).reshape(-1, 1), sizes).reshape(-1) > 0.5
+        else:
+            Linv, clamped_f = self._factor_batch(members, hyps)
         # pw and sig2 depend on the scores g_j, which differ between PCs sharing a factor
         fidx_dev = torch.from_numpy(fidx).to(self.theta_dev.device)
         pw, sig2 = ops.gp_weights(Linv, fidx_dev, self.pc_dev, SIG2_OF_CONST)

@@ -86,7 +86,15 @@ def worker(rank, world, port, outdir):
         from surmise_b200 import _dist
         comm = _dist.Comm()
         ragged = comm.allgather_rows(np.full((rank + 1, 3), float(rank)), [r + 1 for r in range(world)])
+        # gather_blocks: each rank owns a contiguous block of a batch of "factors" (here 5 blocks of 3 x 4 numbers)
+        import torch
+        sizes, starts = _dist.block_partition(5, world)
+        lo, hi = int(starts[rank]), int(starts[rank + 1])
+        full = torch.arange(5 * 12, dtype=torch.float64).reshape(5, 3, 4)
+        blocks = _dist.gather_blocks(comm, full[lo:hi].clone() if hi > lo else None, sizes,
+                                     torch.full((5, 3, 4), -1.0, dtype=torch.float64)).numpy()
         np.savez(os.path.join(outdir, 'rank%d.npz' % rank), hyps=hyps, inds=inds, rows=rows, ragged=ragged,
+                 blocks=blocks,
                  **{'got%d' % B: v[0] for B, v in shard.items()}, **{'want%d' % B: v[1] for B, v in shard.items()})
     finally:
         dist.destroy_process_group()

@@ -56,3 +56,10 @@ def test_ragged_allgather(two_rank_results):
     want = np.vstack([np.zeros((1, 3)), np.ones((2, 3))])
     for r in two_rank_results:
         assert np.array_equal(r['ragged'], want)
+
+
+def test_gather_blocks_assembles_owner_slices(two_rank_results):
+    """_dist.gather_blocks (the sharded final factorisation's exchange): every rank ends with the full batch."""
+    want = np.arange(5 * 12, dtype=np.float64).reshape(5, 3, 4)
+    for r in two_rank_results:
+        assert np.array_equal(r['blocks'], want)
