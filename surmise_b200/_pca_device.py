@@ -118,8 +118,12 @@ def standardize(f, eps_pc, eps_impute, n_iter=40):
     mof_np = ~np.isfinite(f_np)
     any_missing = bool(mof_np.any())
     # offset / scale exactly as the reference computes them (PCGPwM.py:553-557), on the host: O(n m)
-    offset_np = np.nanmean(f_np, axis=0)
-    scale_np = np.nanstd(f_np, axis=0) / np.sqrt(1 - np.isnan(f_np).mean(axis=0))
+    if any_missing:
+        offset_np = np.nanmean(f_np, axis=0)
+        scale_np = np.nanstd(f_np, axis=0) / np.sqrt(1 - np.isnan(f_np).mean(axis=0))
+    else:                           # same bits as the nan-versions on complete data, three times faster (C4: 0.2 s)
+        offset_np = np.mean(f_np, axis=0)
+        scale_np = np.std(f_np, axis=0)
     if np.any(scale_np == 0):
         raise ValueError("You have a row that is non-varying.")
     fs_np = (f_np - offset_np) / scale_np
