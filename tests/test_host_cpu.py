@@ -163,3 +163,34 @@ def test_supplementtheta_matches_reference_outputs():
             assert np.array_equal(info['obviatesugg'], g[name + '_obviate'])
     with pytest.raises(ValueError):
         M.supplementtheta(fitinfo, 4, None, g['choices'], np.ones(9), None)
+
+
+def test_sibling_methods_host_stages_match_reference_fixtures():
+    """Host-side stages of the sibling method modules against arrays produced by the reference (tests/golden):
+    PCSK's simsd-driven component selection, PCGPwImpute's completion, indGP's hyper-parameter layout."""
+    import os
+    from surmise_b200.emulationmethods import PCSK_B200, PCGPwImpute_B200, indGP_B200
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    g = np.load(os.path.join(here, 'pcsk.npz'))
+    fi = {'epsilonPC': 0.001, 'numpcs': -1, 'standardpcinfo': PCSK_B200.standardize(g['f'].T)}
+    PCSK_B200.principal_components(fi, g['simsd'])
+    assert fi['pc'].shape == g['pc'].shape
+    sign = np.sign(np.sum(fi['pc'] * g['pc'], 0))
+    assert np.allclose(fi['pc'] * sign, g['pc'], rtol=0, atol=1e-10 * np.abs(g['pc']).max())
+    assert np.allclose(fi['unscaled_pcstdvar'], g['pcstdvar'], rtol=1e-9, atol=0)
+    mean, lo, hi, std = PCSK_B200.hyper_prior(g['theta'])
+    assert mean.shape == (g['theta'].shape[1] + 3,) and mean[-1] == -17 and np.all(std == (hi - lo) / 4)
+
+    gi = np.load(os.path.join(here, 'impute.npz'))
+    for tag, method in (('knn', 'KNN'), ('br', 'BayesianRidge')):
+        fin = gi[tag + '_f'].T.copy()
+        assert np.isnan(fin).any()
+        done = PCGPwImpute_B200._complete(fin, method)
+        assert np.allclose(done, gi[tag + '_fcompleted'], rtol=1e-10, atol=1e-12)
+    with pytest.raises(ValueError):
+        PCGPwImpute_B200._complete(fin, 'nope')
+
+    mean, lo, hi, std = indGP_B200.hyper_prior(g['theta'], -10, -20)
+    assert mean.shape == (g['theta'].shape[1] + 2,) and std[-2] == 2 and std[-1] == 4 and mean[-1] == -10
+    wide = indGP_B200._widen(np.array([[1.0, 2.0, 3.0, 4.0]]), -1e-8)
+    assert np.array_equal(wide, [[1.0, 2.0, 3.0, -1e-8, 4.0]])
