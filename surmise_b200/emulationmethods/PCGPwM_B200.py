@@ -106,6 +106,97 @@ def fit(fitinfo, x, theta, f, epsilonPC=0.001, epsilonImpute=10e-6, lognugmean=-
     return
 
 
+class _LbfgsbCore:
+    """One bounded L-BFGS-B run driven step by step (reverse communication) through scipy's own core routine.
+
+    Same routine, parameters and stopping rules as scipy.optimize.minimize(method='L-BFGS-B', jac=True,
+    options={'gtol': gtol}) (scipy/optimize/_lbfgsb_py.py:_minimize_lbfgsb), so the iterates are the same; what is
+    gone is one Python thread per optimiser: many cores can be advanced by one scheduler that batches their function
+    requests into a single device launch.  `available()` is False when this scipy does not expose the routine with
+    the expected signature -- callers then fall back to threads around the public API."""
+    M, FTOL, MAXLS, MAXITER, MAXFUN = 10, 2.2204460492503131e-09, 20, 15000, 15000
+    _ok = None
+
+    @classmethod
+    def available(cls):
+        if cls._ok is None:
+            try:
+                core = cls(np.array([0.3, -0.2]), np.array([-1.0, -1.0]), np.array([1.0, 1.0]), 1e-8)
+                n = 0
+                while core.ask() is not None and n < 200:
+                    core.tell(float(np.sum((core.x - 0.1) ** 2)), 2 * (core.x - 0.1))
+                    n += 1
+                cls._ok = bool(np.allclose(core.x, 0.1, atol=1e-6))
+            except Exception:
+                cls._ok = False
+        return cls._ok
+
+    def __init__(self, x0, lo, hi, gtol):
+        from scipy.optimize import _lbfgsb
+        self._setulb = _lbfgsb.setulb
+        n = x0.shape[0]
+        it = np.int32
+        try:
+            from scipy.optimize._lbfgsb_py import HAS_ILP64
+            it = np.int64 if HAS_ILP64 else np.int32
+        except ImportError:
+            pass
+        self.x = np.array(np.clip(x0, lo, hi), dtype=np.float64)
+        self.lo, self.hi = np.array(lo, dtype=np.float64), np.array(hi, dtype=np.float64)
+        self.nbd = np.full(n, 2, dtype=it)                      # both bounds finite
+        self.f, self.g = np.array(0.0, dtype=np.float64), np.zeros(n, dtype=np.float64)
+        m = self.M
+        self.wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m, np.float64)
+        self.iwa = np.zeros(3 * n, dtype=it)
+        self.task, self.ln_task = np.zeros(2, dtype=it), np.zeros(2, dtype=it)
+        self.lsave, self.isave = np.zeros(4, dtype=it), np.zeros(44, dtype=it)
+        self.dsave = np.zeros(29, dtype=np.float64)
+        self.factr, self.pgtol = self.FTOL / np.finfo(float).eps, gtol
+        self.nit = self.nfev = 0
+
+    def ask(self):
+        """Advance to the next point at which value and gradient are needed; None when the run has finished."""
+        while True:
+            self.g = self.g.astype(np.float64)
+            self._setulb(self.M, self.x, self.lo, self.hi, self.nbd, self.f, self.g, self.factr, self.pgtol, self.wa,
+                         self.iwa, self.task, self.lsave, self.isave, self.dsave, self.MAXLS, self.ln_task)
+            if self.task[0] == 3:
+                return self.x
+            if self.task[0] == 1:
+                self.nit += 1
+                if self.nit >= self.MAXITER:
+                    self.task[0], self.task[1] = 5, 504
+                elif self.nfev > self.MAXFUN:
+                    self.task[0], self.task[1] = 5, 502
+            else:
+                return None
+
+    def tell(self, fval, grad):
+        self.nfev += 1
+        self.f, self.g = fval, np.asarray(grad, dtype=np.float64)
+
+
+def minimize_many(fun_batch, x0s, lo, hi, gtol):
+    """Bounded L-BFGS-B from every row of x0s, advanced together by one scheduler (requires _LbfgsbCore.available()).
+
+    fun_batch(idx (r,), X (r, p)) -> (values (r,), gradients (r, p)) for the problems idx that are waiting.
+    Returns (X (K, p), fun (K,), nfev (K,)) -- per problem what scipy.optimize.minimize(..., jac=True,
+    options={'gtol': gtol}) returns."""
+    cores = [_LbfgsbCore(np.asarray(x0, dtype=np.float64), lo, hi, gtol) for x0 in x0s]
+    live = list(range(len(cores)))
+    while live:
+        asks = [(i, cores[i].ask()) for i in live]
+        live = [i for i, xs in asks if xs is not None]
+        if not live:
+            break
+        X = np.array([xs for _, xs in asks if xs is not None])
+        vals, grads = fun_batch(np.array(live), X)
+        for r, i in enumerate(live):
+            cores[i].tell(float(vals[r]), grads[r])
+    return (np.array([c.x for c in cores]), np.array([float(c.f) for c in cores]),
+            np.array([c.nfev for c in cores]))
+
+
 def hyper_prior(theta, lognugmean, lognugLB, logvarc):
     """Regulariser mean / box / std for [gamma_0..gamma_d, h_v, h_nu] (PCGPwM.py:728-742)."""
     d = theta.shape[1]
@@ -231,6 +322,84 @@ class _GPFitter:
             return hyp, lead, rows
         return hypn, -1, rows
 
+    def fit_one_steps(self, j, cand, cand_ids, rows=None):
+        """fit_one as a generator: yields (data, hyps, want_grad, s0) whenever it needs likelihood values and receives
+        (val, grad); the L-BFGS-B run goes through _LbfgsbCore.  Returns (hyp, hypind or -1, rows)."""
+        rows, data = self._subsample(j, rows)
+        hyp = 1 * self.mean
+        lead = -1
+        s0 = self.s0_noleader if (cand is None and self.s0_noleader is not None) else SIG2_OF_CONST
+        trial = [self.mean] if cand is None else [self.mean] + [c for c in cand]
+        vals, _ = yield (data, np.asarray(trial), False, s0)
+        L0 = vals[0]
+        for c in range(1, len(trial)):
+            if vals[c] < L0:
+                hyp, L0, lead = trial[c], 1 * vals[c], cand_ids[c - 1]
+        skip = False
+        if self.skip_test and lead > -0.5 and cand.ndim > 1:
+            _, dL = yield (data, np.asarray([hyp]), True, s0)
+            nc = cand.shape[0]
+            scal = np.std(cand, 0) * nc / (1 + nc) + self.std / (1 + nc)
+            skip = np.sum((dL[0] * scal) ** 2) < self.share_bar
+        if not skip:
+            core = _LbfgsbCore((hyp - self.mean) / self.std, (self.lo - self.mean) / self.std,
+                               (self.hi - self.mean) / self.std, self.gtol)
+            while True:
+                xs = core.ask()
+                if xs is None:
+                    break
+                val, grad = yield (data, np.asarray([self.mean + xs * self.std]), True, s0)
+                core.tell(float(val[0]), grad[0] * self.std)
+            hypn = self.mean + core.x * self.std
+            likdiff = L0 - core.f
+        else:
+            likdiff = 0
+        if lead > -0.5 and (2 * likdiff) < self.share_bar:
+            return hyp, lead, rows
+        return hypn, -1, rows
+
+    def _run_block_coroutines(self, jobs):
+        """Advance the fit_one_steps generators of several PCs together: every round gathers the likelihood requests
+        of all live generators into ONE batched launch per (gradient flag, sig2ofconst).  One thread, no locks."""
+        ops, torch = self.ops, self.torch
+        gens = [job() for job in jobs]
+        results, pending = [None] * len(gens), {}
+
+        def advance(t, value=None):
+            try:
+                pending[t] = gens[t].send(value) if value is not None else next(gens[t])
+            except StopIteration as stop:
+                pending.pop(t, None)
+                results[t] = stop.value
+        for t in range(len(gens)):
+            advance(t)
+        while pending:
+            order = sorted(pending)
+            outs = {}
+            for key in sorted({(pending[t][2], pending[t][3]) for t in order}):
+                group = [t for t in order if (pending[t][2], pending[t][3]) == key]
+                counts = [pending[t][1].shape[0] for t in group]
+                datas = [pending[t][0] for t in group]
+                theta = torch.cat([dd.theta.expand(c, -1, -1) if dd.theta.dim() == 2 else dd.theta
+                                   for dd, c in zip(datas, counts)], 0)
+                g = torch.cat([dd.g.expand(c, -1) for dd, c in zip(datas, counts)], 0)
+                gv = torch.cat([dd.gvar.expand(c, -1) for dd, c in zip(datas, counts)], 0)
+                hyps = np.concatenate([pending[t][1] for t in group], 0)
+                self.nevals += hyps.shape[0]
+                val, grad, info = ops.gp_nll_grad(ops.GPData(theta, g, gv), hyps, self.mean_dev, self.std_dev,
+                                                  key[1], key[0])
+                bad = (info != 0) | ~np.isfinite(val)
+                val = np.where(bad, _INFEASIBLE, val)
+                if grad is not None:
+                    grad = np.where(bad[:, None], 0.0, grad)
+                lo = 0
+                for t, c in zip(group, counts):
+                    outs[t] = (val[lo:lo + c], None if grad is None else grad[lo:lo + c])
+                    lo += c
+            for t in order:
+                advance(t, outs[t])
+        return results
+
     # -- all PCs --------------------------------------------------------------------------------
     def run(self, previous=None):
         """Three Gauss-Seidel sweeps (PCGPwM.py:678-722) followed by ONE batched full-n factorisation."""
@@ -274,16 +443,30 @@ class _GPFitter:
         def one(j, cand, cand_ids, rows):
             hyp, hi, _ = self.fit_one(j, cand, cand_ids, rows)
             return hyp, hi
-        hyps, hypinds, rows_used = _dist.jacobi_sweeps(one, k, self.p, comm, self._draw_rows,
+
+        def one_steps(j, cand, cand_ids, rows):
+            hyp, hi, _ = yield from self.fit_one_steps(j, cand, cand_ids, rows)
+            return hyp, hi
+        mode = self.lockstep
+        if mode == 'coroutine' and not _LbfgsbCore.available():
+            mode = 'threads'
+        if mode == 'coroutine':
+            fit_fn, run_block = one_steps, self._run_block_coroutines
+        else:
+            fit_fn, run_block = one, (self._run_block_lockstep if mode else None)
+        hyps, hypinds, rows_used = _dist.jacobi_sweeps(fit_fn, k, self.p, comm, self._draw_rows,
                                                        start_hyps=start_hyps, start_inds=start_inds,
-                                                       run_block=self._run_block_lockstep if self.lockstep else None)
+                                                       run_block=run_block)
         self._comm = comm                                     # the distinct factors are sharded over the ranks as well
         try:
             return self._finalise(hyps, hypinds, rows_used)
         finally:
             self._comm = None
 
-    lockstep = True      # batch the likelihood calls of this rank's PCs into one launch per optimiser step
+    # how this rank's PCs are searched in parallel mode: 'coroutine' -- generators advanced by one scheduler that
+    # batches their likelihood requests (default); 'threads' (or True) -- one scipy.optimize.minimize per Python thread
+    # with a rendezvous (fallback when scipy's reverse-communication core is not usable); False -- one after the other
+    lockstep = 'coroutine'
 
     def _run_block_lockstep(self, jobs):
         """Run fit_one for several PCs concurrently (one Python thread each); their likelihood requests are

@@ -6,7 +6,7 @@ on the parameters at which that row was observed, with d + 2 hyper-parameters [g
 (no variance constant) and sig2ofconst = 1 (indGP.py:123-172).  SURVEY.md section 8(f) row 4: the covariance, the
 penalised likelihood + gradient, the factorisation and the prediction are the PCGPwM kernels --
   * rows with the same missing pattern share theta, so their likelihoods are ONE batched device call per optimiser
-    step (the L-BFGS-B runs of a group advance in lock step); the kernel's log-variance-constant slot is pinned at its
+    step (the L-BFGS-B runs of a group are advanced together by one scheduler over scipy's own L-BFGS-B core); the kernel's log-variance-constant slot is pinned at its
     prior mean, where it contributes nothing;
   * one batched factorisation per group gives Linv, pw and sig2; prediction reuses sb200_gp_predict per group.
 The reference's quirks are kept: `covxhalf` has shape (nx, B, B) with sqrt(var[k, b]) on the diagonal of its last two
@@ -79,25 +79,33 @@ def _fit_group(theta_g, G, lognugmean, lognugLB):
         g[bad] = 0.0
         return np.where(bad, 1e30, nll), g
 
-    for c0 in range(0, K, _MAX_LOCKSTEP):
-        members = list(range(c0, min(c0 + _MAX_LOCKSTEP, K)))
-        ev = _Lockstep(batched, len(members))
-        results = {}
+    from .PCGPwM_B200 import _LbfgsbCore, minimize_many
+    if _LbfgsbCore.available():
+        # all optimisers of the group advanced by one scheduler (scipy's own L-BFGS-B core, reverse communication)
+        X, _fun, nfev = minimize_many(lambda idx, Xs: batched(np.column_stack([idx.astype(np.float64), Xs])),
+                                      np.zeros((K, d + 2)), bounds.lb, bounds.ub, 0.1)
+        hyps[:] = mean + X * std
+        nevals += int(nfev.sum())
+    else:
+        for c0 in range(0, K, _MAX_LOCKSTEP):                       # fallback: one thread per optimiser
+            members = list(range(c0, min(c0 + _MAX_LOCKSTEP, K)))
+            ev = _Lockstep(batched, len(members))
+            results = {}
 
-        def work(j, ev=ev, results=results):
-            try:
-                results[j] = spo.minimize(lambda xs: ev(np.concatenate(([float(j)], xs))), np.zeros(d + 2),
-                                          method='L-BFGS-B', jac=True, bounds=bounds, options={'gtol': 0.1})
-            finally:
-                ev.retire()
-        threads = [threading.Thread(target=work, args=(j,)) for j in members]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        for j in members:
-            hyps[j] = mean + results[j].x * std
-            nevals += results[j].nfev
+            def work(j, ev=ev, results=results):
+                try:
+                    results[j] = spo.minimize(lambda xs: ev(np.concatenate(([float(j)], xs))), np.zeros(d + 2),
+                                              method='L-BFGS-B', jac=True, bounds=bounds, options={'gtol': 0.1})
+                finally:
+                    ev.retire()
+            threads = [threading.Thread(target=work, args=(j,)) for j in members]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            for j in members:
+                hyps[j] = mean + results[j].x * std
+                nevals += results[j].nfev
     # full factorisation of every GP of the group in one batch (indGP.py:158-171)
     data = ops.GPData(theta_dev, G_dev, None)
     Linv, pw, sig2, _ldh, info = ops.gp_factorize(data, _widen(hyps, 0.0), SIG2_OF_CONST)

@@ -218,17 +218,19 @@ def test_lockstep_batching_equals_sequential_jacobi():
     from surmise_b200.emulationmethods import PCGPwM_B200 as M
     x, theta, f, truth = make_simulator(260, 3, 30, 6, seed=17)
     outs = []
-    for lock in (True, False):
+    default = M._GPFitter.lockstep
+    assert default == 'coroutine' and M._LbfgsbCore.available()
+    for lock in ('coroutine', 'threads', False):     # generators + one scheduler / threads + rendezvous / sequential
         M._GPFitter.lockstep = lock
         try:
             np.random.seed(17)
             fi = _facade_fit(M, x, theta, f, fit_mode='parallel')
         finally:
-            M._GPFitter.lockstep = True
+            M._GPFitter.lockstep = default
         outs.append((np.array([e['hyp'] for e in fi['emulist']]), [e['hypind'] for e in fi['emulist']],
                      fi['_b200']['nevals']))
-    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
-    assert outs[0][2] == outs[1][2]
+    for other in outs[1:]:
+        assert np.array_equal(outs[0][0], other[0]) and outs[0][1] == other[1] and outs[0][2] == other[2]
 
 
 def test_device_pca_matches_host_pca(golden):

@@ -194,3 +194,37 @@ def test_sibling_methods_host_stages_match_reference_fixtures():
     assert mean.shape == (g['theta'].shape[1] + 2,) and std[-2] == 2 and std[-1] == 4 and mean[-1] == -10
     wide = indGP_B200._widen(np.array([[1.0, 2.0, 3.0, 4.0]]), -1e-8)
     assert np.array_equal(wide, [[1.0, 2.0, 3.0, -1e-8, 4.0]])
+
+
+def test_reverse_communication_lbfgsb_equals_scipy_minimize():
+    """_LbfgsbCore / minimize_many (the parallel fit's optimiser driver) against scipy.optimize.minimize: same
+    iterates, values and evaluation counts, problem by problem, also when the problems advance together."""
+    import scipy.optimize as spo
+    from surmise_b200.emulationmethods.PCGPwM_B200 import _LbfgsbCore, minimize_many
+    if not _LbfgsbCore.available():
+        pytest.skip("this scipy does not expose the L-BFGS-B core with the expected signature")
+    rng = np.random.default_rng(0)
+    centres = rng.uniform(-0.5, 0.5, size=(7, 4))
+
+    def fg(c, x):
+        f = 100 * (x[1] - x[0] ** 2) ** 2 + (1 - x[0]) ** 2 + 0.5 * np.sum((x[2:] - c[2:]) ** 4) + np.sum(c[:2] * x[:2])
+        g = np.zeros_like(x)
+        g[0] = -400 * x[0] * (x[1] - x[0] ** 2) - 2 * (1 - x[0]) + c[0]
+        g[1] = 200 * (x[1] - x[0] ** 2) + c[1]
+        g[2:] = 2 * (x[2:] - c[2:]) ** 3
+        return f, g
+    lo, hi = -2 * np.ones(4), np.array([0.8, 2.0, 2.0, 2.0])
+    x0s = rng.uniform(-1.5, 0.7, size=(7, 4))
+    calls = []
+
+    def batch(idx, X):
+        calls.append(len(idx))
+        out = [fg(centres[i], x) for i, x in zip(idx, X)]
+        return np.array([o[0] for o in out]), np.array([o[1] for o in out])
+    for gtol in (0.1, 1e-6):
+        X, F, nfev = minimize_many(batch, x0s, lo, hi, gtol)
+        for i in range(7):
+            r = spo.minimize(lambda x: fg(centres[i], x), x0s[i], method='L-BFGS-B', jac=True,
+                             bounds=spo.Bounds(lo, hi), options={'gtol': gtol})
+            assert np.array_equal(r.x, X[i]) and r.fun == F[i] and r.nfev == nfev[i]
+    assert max(calls) == 7 and min(calls) >= 1
