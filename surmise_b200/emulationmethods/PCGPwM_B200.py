@@ -289,7 +289,23 @@ class _GPFitter:
         return val, grad
 
     def fit_one(self, j, cand, cand_ids, rows=None):
-        """__fitGP1d without its full-n stage.  Returns (hyp, hypind or -1, subsample rows)."""
+        """__fitGP1d without its full-n stage.  Returns (hyp, hypind or -1, subsample rows).
+
+        Runs the fit_one_steps generator, answering each of its likelihood requests with a device call; when scipy's
+        reverse-communication L-BFGS-B entry point is not usable (or inside the threaded rendezvous) the search goes
+        through scipy.optimize.minimize instead -- the same iterates either way."""
+        if self._lockstep is not None or not _LbfgsbCore.available():
+            return self._fit_one_scipy(j, cand, cand_ids, rows)
+        steps = self.fit_one_steps(j, cand, cand_ids, rows)
+        try:
+            data, hyps, want_grad, s0 = next(steps)
+            while True:
+                data, hyps, want_grad, s0 = steps.send(self._nll(data, hyps, want_grad, s0))
+        except StopIteration as stop:
+            return stop.value
+
+    def _fit_one_scipy(self, j, cand, cand_ids, rows=None):
+        """fit_one with the L-BFGS-B run handed to scipy.optimize.minimize (PCGPwM.py:783-805 verbatim in structure)."""
         rows, data = self._subsample(j, rows)
         hyp = 1 * self.mean
         lead = -1
