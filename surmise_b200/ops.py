@@ -20,7 +20,11 @@ def _ptr(t):
 
 
 def _stream(torch):
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of torch's current stream (every launch passes it through the C ABI)."""
+    try:                                            # the Python Stream object costs ~13 us to build; this is ~0.3 us
+        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+    except AttributeError:
+        return torch.cuda.current_stream().cuda_stream
 
 
 _PIN_LIMIT = 4 << 30        # results above this size are copied through pageable memory
