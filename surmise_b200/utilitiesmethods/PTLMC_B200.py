@@ -90,6 +90,13 @@ def _preoptimise(theta0, value_and_grad, has_grad):
     bounds = spo.Bounds(lo, hi)
     kicks = np.random.standard_normal(size=(numopt, 8, d))        # drawn up-front: results independent of scheduling
     out = np.array(theta0, dtype=np.float64)
+    if has_grad:
+        try:
+            from ..emulationmethods.PCGPwM_B200 import _LbfgsbCore
+            if _LbfgsbCore.available():
+                return _preoptimise_steps(theta0, value_and_grad, cen, sca, lo, hi, kicks, out, _LbfgsbCore)
+        except ImportError:
+            pass
 
     def batch(thetas):
         v, g = value_and_grad(thetas)
@@ -127,6 +134,60 @@ def _preoptimise(theta0, value_and_grad, has_grad):
         th.start()
     for th in threads:
         th.join()
+    return out
+
+
+def _preoptimise_steps(theta0, value_and_grad, cen, sca, lo, hi, kicks, out, Core):
+    """_preoptimise without threads: every chain is a generator that yields the points it needs; one scheduler
+    evaluates all waiting points with a single batched closure call.  The L-BFGS-B runs go through scipy's own core
+    in reverse-communication form with scipy.optimize.minimize's default tolerances (same iterates)."""
+    numopt, d = theta0.shape
+
+    def chain(c):
+        core = Core((theta0[c] - cen) / sca, lo, hi, 1e-5)          # gtol: minimize's L-BFGS-B default
+        while True:
+            xs = core.ask()
+            if xs is None:
+                break
+            v, g = yield cen + sca * xs
+            core.tell(-v, -sca * g)
+        best = cen + sca * core.x
+        if c > 0:                                                  # the first chain stays on its optimum (PTLMC.py:160)
+            m, n = core.M, d
+            ncorr = int(min(core.isave[30], m))
+            H = spo.LbfgsInvHessProduct(core.wa[0:m * n].reshape(m, n)[:ncorr],
+                                        core.wa[m * n:2 * m * n].reshape(m, n)[:ncorr]) @ np.eye(d)
+            W, V = np.linalg.eigh(H)
+            v, _ = yield cen + sca * core.x
+            l0 = -v
+            step = 4.0
+            for t in range(8):
+                r = (V.T * np.sqrt(np.abs(W))) @ (V @ kicks[c, t])
+                v, _ = yield cen + sca * (step * r + core.x)
+                if -v - l0 < 3 * d:
+                    best = cen + sca * (step * r + core.x)
+                    break
+                step /= 2
+                if step < 1 / 16:
+                    break
+        return best
+    gens = [chain(c) for c in range(numopt)]
+    pending = {}
+
+    def advance(c, value=None):
+        try:
+            pending[c] = gens[c].send(value) if value is not None else next(gens[c])
+        except StopIteration as stop:
+            pending.pop(c, None)
+            out[c] = stop.value
+    for c in range(numopt):
+        advance(c)
+    while pending:
+        order = sorted(pending)
+        vals, grads = value_and_grad(np.array([pending[c] for c in order]))
+        vals = np.squeeze(vals, axis=1) if np.ndim(vals) > 1 else vals
+        for r, c in enumerate(order):
+            advance(c, (float(vals[r]), grads[r]))
     return out
 
 

@@ -124,3 +124,27 @@ def test_lmc_reproduces_reference_draws(with_grad):
     assert np.allclose(out['theta'], want, rtol=0, atol=1e-12)
     # the polishing stage is batched: ten optimisers per call until the first of them converges
     assert 10 in rows and rows.count(1) < rows.count(10)
+
+
+def test_ptlmc_preoptimiser_without_threads_equals_threaded_version(monkeypatch):
+    """_preoptimise through the reverse-communication L-BFGS-B core (generators, one scheduler) gives the same
+    starting points as one scipy.optimize.minimize per thread."""
+    from surmise_b200.utilitiesmethods import PTLMC_B200 as S
+    from surmise_b200.emulationmethods.PCGPwM_B200 import _LbfgsbCore
+    from synth import gaussian_logpost
+    if not _LbfgsbCore.available():
+        pytest.skip('scipy core not usable')
+    rows = []
+
+    def vg(th):
+        rows.append(th.shape[0])
+        return gaussian_logpost(th)
+    theta0 = np.random.default_rng(3).uniform(-1, 1, size=(24, 3))
+    np.random.seed(9)
+    a = S._preoptimise(theta0.copy(), vg, True)
+    batched = list(rows)
+    monkeypatch.setattr(_LbfgsbCore, 'available', classmethod(lambda cls: False))
+    np.random.seed(9)
+    b = S._preoptimise(theta0.copy(), vg, True)
+    assert np.array_equal(a, b)
+    assert max(batched) == 24 and np.mean(batched) > 8
