@@ -544,3 +544,24 @@ def test_pcsk_b200_matches_reference_fit(golden):
     assert errs['covx'] < 1e-5 and str(g['desc'])[:60] == fi['param_desc'][:60]
     with pytest.raises(AssertionError):
         M.fit({}, g['x'], g['theta'], g['f'])
+
+
+@pytest.mark.gpu
+def test_merge_leaders_option_reduces_distinct_factors():
+    """fit_mode='parallel' with merge_leaders=True: fewer full-data factors, same interface, comparable accuracy."""
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    x, theta, f, truth = make_simulator(400, 3, 40, 8, seed=3)
+    tn = np.random.default_rng(1).uniform(0.1, 0.9, size=(50, 3))
+    res = {}
+    for merge in (False, True):
+        np.random.seed(5)
+        fi = _facade_fit(M, x, theta, f, fit_mode='parallel', merge_leaders=merge)
+        p = {}
+        M.predict(p, fi, x, tn)
+        inds = np.array([e['hypind'] for e in fi['emulist']])
+        assert np.all(inds <= np.arange(len(inds))) and np.all(inds[inds] == inds)      # leaders point at themselves
+        for j, e in enumerate(fi['emulist']):
+            assert np.array_equal(e['hyp'], fi['emulist'][inds[j]]['hyp'])
+        res[merge] = (int(fi['_b200']['Linv'].shape[0]), float(np.sqrt(np.mean((p['mean'] - truth(tn)) ** 2)) / np.std(truth(tn))))
+    report('merge_leaders', factors_off=res[False][0], factors_on=res[True][0], rmse_off=res[False][1], rmse_on=res[True][1])
+    assert res[True][0] <= res[False][0] and res[True][1] < 2 * res[False][1] + 0.01
