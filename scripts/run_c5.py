@@ -13,7 +13,8 @@ start = sys.argv[2] if len(sys.argv) > 2 else 'prior'      # 'prior': the sample
 w = bench.workload()
 np.random.seed(0)
 fi = {'method': 'PCGPwM_B200'}
-t0 = time.perf_counter(); M.fit(fi, w['x'], w['theta'], w['f'], fit_mode='parallel'); t_fit = time.perf_counter() - t0
+merge = len(sys.argv) > 3 and sys.argv[3] == 'merge'      # fit option merge_leaders: fewer distinct factors
+t0 = time.perf_counter(); M.fit(fi, w['x'], w['theta'], w['f'], fit_mode='parallel', merge_leaders=merge); t_fit = time.perf_counter() - t0
 theta_true, y, yvar = make_observation(w['truth'], 8, seed=3)
 stats = {'calls': 0, 'rows': 0, 't_prior': 0.0}
 
