@@ -11,7 +11,7 @@ spc = int(sys.argv[1]) if len(sys.argv) > 1 else 600
 w = bench.workload()
 np.random.seed(0)
 fi = {'method': 'PCGPwM_B200'}
-M.fit(fi, w['x'], w['theta'], w['f'], fit_mode='parallel')
+M.fit(fi, w['x'], w['theta'], w['f'], fit_mode='parallel', merge_leaders=bool(os.environ.get('MERGE')))
 theta_true, y, yvar = make_observation(w['truth'], 8, seed=3)
 
 
