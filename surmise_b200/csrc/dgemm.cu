@@ -1,14 +1,15 @@
 // DMMA (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4) GEMM for sm_100a.
 //
 // tcgen05.mma has no f64 kind, so on B200 the FP64 tensor path is the warp-level DMMA.  The kernel
-// is a classic 3-stage cp.async pipeline: 128x128 (or 128x64) CTA tile, BK = 16, 8 warps, each warp
-// owning a 64x32 (32x32) accumulator block held in registers.  Operand tiles are staged in shared
+// is a classic 3-stage cp.async pipeline: 64x64 CTA tile (default; 128x64 and 128x128 kept as variants), BK = 16,
+// 4 (8) warps, each warp owning a 32x32 (64x32) accumulator block held in registers.  Operand tiles are staged in shared
 // memory in a fragment-friendly order so that every LDS.64 of a warp is bank-conflict free:
 //   k-contiguous operand : [k/4][row][k%4]  -> a warp's 8x4 fragment is 256 contiguous bytes
 //   row-contiguous operand: [k][row + pad 4] -> (4t + g) mod 16 distinct per half-warp
 // Algorithmic work: 2*M*N*Keff flop where Keff is the (possibly triangular) k-range per tile.
 #include "dgemm.cuh"
 #include <algorithm>
+#include <cstdlib>
 using std::min;
 using std::max;
 
@@ -332,10 +333,17 @@ int launch_dgemm(const GemmArgs& g, int batch, int tile, cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return 0;
     SB_CHECK_ARG(batch <= 65535, "dgemm: batch %d exceeds grid.z limit", batch);
     SB_CHECK_ARG(cdiv(g.M, 128) <= 65535, "dgemm: M %d too large", g.M);
-    // measured on B200: the 128x64 tile at 2 CTAs/SM beats the 128x128 tile at 1 CTA/SM on every shape of this
-    // path (prologue/epilogue of one CTA overlap the main loop of the other): 32.6 vs 31.1 TFLOP/s at 4096^3,
-    // 23.2 vs 20.7 on the batched trailing update, 19.4 vs 15.2 on the predict product
-    if (tile < 0) tile = 1;
+    // measured on B200 (scripts/gemm_launch_table.py, gemm_variants.py): 64x64 tiles with 4 warps at 4 CTAs/SM match the
+    // 128x64 tile at 2 CTAs/SM on a large square product (32.7 vs 32.3 TFLOP/s at 4096^3) and beat it on every
+    // triangular / mid-size batched shape of this path (less tile-granularity waste, better wave balance, more CTAs to
+    // hide each other's prologue / epilogue): -8 % GEMM time over a C2 NLL+grad step.  The 128x64 tile itself had
+    // replaced 128x128 at 1 CTA/SM for the same reasons (32.6 vs 31.1 TFLOP/s at 4096^3, 23.2 vs 20.7 on the batched
+    // trailing update, 19.4 vs 15.2 on the predict product).
+    if (tile < 0) {
+        const char* env = getenv("SB200_GEMM_TILE");              // experiments only
+        tile = env ? atoi(env) : 7;
+    }
+    if (tile == 7) return launch_layout<64, 64, 32, 32>(g, batch, stream);
     if (tile == 1) return launch_layout<128, 64, 32, 32>(g, batch, stream);
     if (tile == 2) return launch_layout<128, 128, 32, 32>(g, batch, stream);     // 16 warps
     if (tile == 3) return launch_layout<128, 64, 32, 16>(g, batch, stream);      // 16 warps, narrow

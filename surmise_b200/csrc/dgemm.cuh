@@ -33,7 +33,8 @@ struct GemmArgs {
     long strideA2, strideB2, strideC2;
 };
 
-// tile: 0 = 128x128 CTA tile (1 CTA/SM), 1 = 128x64 (2 CTAs/SM), 2-4 experimental variants, -1 = default (1)
+// tile: 7 = 64x64 CTA tile, 4 warps, 4 CTAs/SM (default, -1); 1 = 128x64 (2 CTAs/SM); 0 = 128x128 (1 CTA/SM);
+// 2-4 experimental variants
 int launch_dgemm(const GemmArgs& g, int batch, int tile, cudaStream_t stream);
 
 }  // namespace sb
