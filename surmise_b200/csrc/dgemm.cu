@@ -22,6 +22,9 @@ namespace {
 #ifndef SB_STAGES
 #define SB_STAGES 3
 #endif
+#ifndef SB_MIN64
+#define SB_MIN64 4
+#endif
 constexpr int BK = SB_BK;
 constexpr int STAGES = SB_STAGES;
 
@@ -93,7 +96,7 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
 }
 
 template <int BM, int BN, int WM, int WN, bool AKC, bool BKC>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 128) ? 2 : 1)
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 64) ? SB_MIN64 : ((BM * BN <= 64 * 128) ? 2 : 1))
     dgemm_dmma_kernel(GemmArgs p) {
     constexpr int A_TILE = BK * (BM + 4);
     constexpr int B_TILE = BK * (BN + 4);
