@@ -6,6 +6,7 @@
 // Rows n..mrows-1 are right-hand sides: after the call row n holds (L^-1 g)' when it held g'.
 #include "chol.cuh"
 #include "dgemm.cuh"
+#include <cstdlib>
 
 namespace sb {
 namespace {
@@ -21,6 +22,9 @@ constexpr int NB = CHOL_NB;
 //            __syncthreads per column (double-buffered column broadcast through shared memory);
 //   phase 2: X = L^-1 by forward substitution, 4 threads per column, rows interleaved, x_j by warp shuffle;
 //   phase 3: P <- P X' for this CTA's 128 rows on the FP64 tensor cores (DMMA) out of shared memory.
+// FUSE (first block of a two-block leaf): the rank-64 update of the NEXT block column, C -= P Q' with Q = the first
+//   64 solved rows, is applied to this CTA's rows in the same pass (every CTA solves those 64 rows redundantly),
+//   which removes the smallest trailing-update GEMM launch of the recursion.
 constexpr int PT = 128;          // rows per CTA in the panel solve
 constexpr int SLD = NB + 4;      // shared leading dimension: (4 g + t) mod 16 distinct -> conflict-free LDS.64
 
@@ -29,9 +33,10 @@ __device__ __forceinline__ void cp_async8_plain(double* smem, const double* gmem
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(valid ? 8 : 0) : "memory");
 }
 
+template <bool FUSE>
 __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ Abase, long lda, long strideA,
                                                           double* __restrict__ Dbase, long ldd, long strideD, int nb,
-                                                          int j0, int below, int rows_per_cta,
+                                                          int j0, int below, int rows_per_cta, int fuse_nc,
                                                           int* __restrict__ info, int* __restrict__ counters,
                                                           long long* stamps) {
     extern __shared__ double sm[];
@@ -40,6 +45,7 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
     double* T = X + NB * SLD;             // [PT][SLD]  this CTA's rows of the panel
     double* colbuf = T + PT * SLD;        // [2][NB]
     double* invd = colbuf + 2 * NB;       // [NB]
+    double* Q = invd + NB;                // [NB][SLD]  FUSE only: the first 64 rows below the block, then solved
     const int tid = threadIdx.x, z = blockIdx.y;
 #define SB_STAMP(slot) do { if (stamps && z == 0 && blockIdx.x == 0 && tid == 0) stamps[slot] = clock64(); } while (0)
     SB_STAMP(0);
@@ -58,6 +64,15 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
+    if (FUSE) {
+        const double* P = A + (long)nb * lda;
+        for (int idx = tid; idx < NB * NB; idx += 256) {
+            int r = idx >> 6, c = idx & 63;
+            bool ok = (r < below) && (c < nb);
+            cp_async8_plain(Q + r * SLD + c, ok ? P + (long)r * lda + c : A, ok);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
     if (cta_rows > 0) stage_tile(cta_r0);
 
     // ---- phase 1: Cholesky of the (identity padded) 64 x 64 block, register resident
@@ -77,6 +92,9 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
     // The block is factored in place by whichever CTA of this matrix loaded it LAST (all CTAs compute the
     // same L), so no CTA can still be reading A's block when it is overwritten.  No spinning: a counter.
     __shared__ int s_writer;
+    // the writer CTA below will overwrite the 64 rows under the block: this CTA's copies of them (Q, and T's
+    // first rows in CTA 0) must have landed before it counts as arrived
+    if (FUSE) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
     if (tid == 0) {
         __threadfence();
@@ -176,8 +194,42 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
     SB_STAMP(5);
     if (cta_rows <= 0) return;
 
-    // ---- phase 3: P <- P X'  (DMMA from shared memory), 128 rows at a time; warp w owns rows 16w .. 16w+15
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    if (FUSE) {
+        // Q <- Q X' (64 x 64 x 64, warp w owns rows 8w .. 8w+7, in place).  Every CTA gets the same bits; the
+        // writer CTA stores them (rows 0..63 below the block), so no CTA can still be loading the unsolved rows.
+        double acc[8][2];
+#pragma unroll
+        for (int ni = 0; ni < 8; ni++) acc[ni][0] = acc[ni][1] = 0.0;
+#pragma unroll
+        for (int k4 = 0; k4 < NB / 4; k4++) {
+            double av = Q[(8 * warp + g) * SLD + 4 * k4 + t];
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++)
+                if (4 * k4 <= 8 * ni + 7) {
+                    double bv = X[(8 * ni + g) * SLD + 4 * k4 + t];
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(acc[ni][0]), "+d"(acc[ni][1])
+                                 : "d"(av), "d"(bv));
+                }
+        }
+        __syncwarp();
+        const int r = 8 * warp + g;
+        double* P = A + (long)nb * lda;
+#pragma unroll
+        for (int ni = 0; ni < 8; ni++) {
+            int c = 8 * ni + 2 * t;
+            Q[r * SLD + c] = acc[ni][0];
+            Q[r * SLD + c + 1] = acc[ni][1];
+            if (writer && r < below) {
+                P[(long)r * lda + c] = acc[ni][0];
+                P[(long)r * lda + c + 1] = acc[ni][1];
+            }
+        }
+        // the barrier at the top of the phase-3 loop publishes Q
+    }
+
+    // ---- phase 3: P <- P X'  (DMMA from shared memory), 128 rows at a time; warp w owns rows 16w .. 16w+15
     const int m0 = warp * 16;
     for (int r0 = cta_r0; r0 < cta_r0 + cta_rows; r0 += PT) {
         const int rows_here = min(PT, cta_r0 + cta_rows - r0);
@@ -204,18 +256,74 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
                                      : "d"(av[mi]), "d"(bv));
                 }
         }
-        __syncthreads();                                         // everyone is done reading T
-        if (r0 + PT < cta_r0 + cta_rows) stage_tile(r0 + PT);    // prefetch the next 128 rows while storing
         double* P = A + (long)(nb + r0) * lda;
+        if (!FUSE) {
+            __syncthreads();                                         // everyone is done reading T
+            if (r0 + PT < cta_r0 + cta_rows) stage_tile(r0 + PT);    // prefetch the next 128 rows while storing
+        }
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) {
             int r = m0 + 8 * mi + g;
             if (r >= rows_here) continue;
+            if (FUSE && r0 + r < NB) continue;                       // those rows are Q: stored by the writer CTA
 #pragma unroll
             for (int ni = 0; ni < 8; ni++) {
                 int c = 8 * ni + 2 * t;
                 if (c < nb) P[(long)r * lda + c] = acc[mi][ni][0];
                 if (c + 1 < nb) P[(long)r * lda + c + 1] = acc[mi][ni][1];
+            }
+        }
+        if (FUSE) {
+            // C[rows, nb .. nb+fuse_nc) -= P Q'   (the solved rows go back into this warp's own rows of T as operand A)
+            __syncwarp();
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 8; ni++) {
+                    int r = m0 + 8 * mi + g, c = 8 * ni + 2 * t;
+                    T[r * SLD + c] = -acc[mi][ni][0];
+                    T[r * SLD + c + 1] = -acc[mi][ni][1];
+                }
+            __syncwarp();
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                int r = m0 + 8 * mi + g;
+#pragma unroll
+                for (int ni = 0; ni < 8; ni++) {
+                    int c = 8 * ni + 2 * t;
+                    bool ok = r < rows_here;
+                    acc[mi][ni][0] = (ok && c < fuse_nc) ? P[(long)r * lda + nb + c] : 0.0;
+                    acc[mi][ni][1] = (ok && c + 1 < fuse_nc) ? P[(long)r * lda + nb + c + 1] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < NB / 4; k4++) {
+                double av[2];
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++) av[mi] = T[(m0 + 8 * mi + g) * SLD + 4 * k4 + t];
+#pragma unroll
+                for (int ni = 0; ni < 8; ni++) {
+                    double bv = Q[(8 * ni + g) * SLD + 4 * k4 + t];
+#pragma unroll
+                    for (int mi = 0; mi < 2; mi++)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                     : "+d"(acc[mi][ni][0]), "+d"(acc[mi][ni][1])
+                                     : "d"(av[mi]), "d"(bv));
+                }
+            }
+            __syncthreads();                                         // everyone is done reading T
+            if (r0 + PT < cta_r0 + cta_rows) stage_tile(r0 + PT);
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                int r = m0 + 8 * mi + g;
+                if (r >= rows_here) continue;
+                const int rr = r0 + r;                               // row inside the next block column
+#pragma unroll
+                for (int ni = 0; ni < 8; ni++) {
+                    int c = 8 * ni + 2 * t;                          // strict upper part of the next diagonal block stays
+                    if (c < fuse_nc && (rr >= NB || c <= rr)) P[(long)r * lda + nb + c] = acc[mi][ni][0];
+                    if (c + 1 < fuse_nc && (rr >= NB || c + 1 <= rr)) P[(long)r * lda + nb + c + 1] = acc[mi][ni][1];
+                }
             }
         }
     }
@@ -225,13 +333,16 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
 
 long long* g_panel_stamps = nullptr;      // instrumentation (sb200_debug_panel_stamps)
 
-int panel(const CholBatch& c, int j0, int nb, cudaStream_t stream) {
+// fuse_nc > 0 (nb == NB only): also apply this block column's rank-64 update to the next fuse_nc columns
+int panel(const CholBatch& c, int j0, int nb, int fuse_nc, cudaStream_t stream) {
     constexpr size_t smem = (size_t)(2 * NB * SLD + PT * SLD + 3 * NB) * sizeof(double);
+    constexpr size_t smem_fuse = smem + (size_t)NB * SLD * sizeof(double);
     static bool configured[64] = {false};
     int dev = 0;
     SB_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !configured[dev]) {
-        SB_CUDA(cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(potrf_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(potrf_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fuse));
         configured[dev] = true;
     }
     int below = c.mrows - (j0 + nb);
@@ -241,11 +352,27 @@ int panel(const CholBatch& c, int j0, int nb, cudaStream_t stream) {
     if (ctas_per_matrix < 1) ctas_per_matrix = 1;
     int rows_per_cta = (int)round_up(cdiv(below > 0 ? below : 1, ctas_per_matrix), PT);
     dim3 grid(below > 0 ? cdiv(below, rows_per_cta) : 1, c.batch);
-    potrf_panel_kernel<<<grid, 256, smem, stream>>>(c.A + (long)j0 * c.lda + j0, c.lda, c.strideA,
-                                                    c.Dinv + (long)(j0 / NB) * c.blockD, c.ldd, c.strideD, nb, j0,
-                                                    below, rows_per_cta, c.info, c.counters, g_panel_stamps);
+    if (fuse_nc > 0)
+        potrf_panel_kernel<true><<<grid, 256, smem_fuse, stream>>>(c.A + (long)j0 * c.lda + j0, c.lda, c.strideA,
+                                                                   c.Dinv + (long)(j0 / NB) * c.blockD, c.ldd, c.strideD,
+                                                                   nb, j0, below, rows_per_cta, fuse_nc, c.info,
+                                                                   c.counters, g_panel_stamps);
+    else
+        potrf_panel_kernel<false><<<grid, 256, smem, stream>>>(c.A + (long)j0 * c.lda + j0, c.lda, c.strideA,
+                                                                c.Dinv + (long)(j0 / NB) * c.blockD, c.ldd, c.strideD,
+                                                                nb, j0, below, rows_per_cta, 0, c.info, c.counters,
+                                                                g_panel_stamps);
     SB_LAUNCH_CHECK();
     return 0;
+}
+
+bool fuse_leaf_pairs() {       // SB200_PANEL_FUSE=0 keeps the separate rank-64 GEMM (experiments only)
+    static int on = -1;
+    if (on < 0) {
+        const char* env = getenv("SB200_PANEL_FUSE");
+        on = (env && env[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
 }
 
 int split_point(int nn) {      // multiple of NB closest to nn/2 from above
@@ -254,8 +381,12 @@ int split_point(int nn) {      // multiple of NB closest to nn/2 from above
 }
 
 int potrf_rec(const CholBatch& c, int j0, int nn, cudaStream_t stream) {
-    if (nn <= NB) return panel(c, j0, nn, stream);      // factor the block and solve every row below it
+    if (nn <= NB) return panel(c, j0, nn, 0, stream);   // factor the block and solve every row below it
     int n1 = split_point(nn), n2 = nn - n1;
+    if (nn <= 2 * NB && fuse_leaf_pairs()) {            // two-block leaf: the first panel launch carries the update
+        SB_TRY(panel(c, j0, NB, n2, stream));
+        return panel(c, j0 + NB, n2, 0, stream);
+    }
     SB_TRY(potrf_rec(c, j0, n1, stream));
     {                                          // rows [j0+n1, mrows) x cols [j0+n1, j0+nn) -= P Pc'
         GemmArgs g{};
