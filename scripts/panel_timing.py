@@ -15,5 +15,5 @@ for _ in range(2):
 torch.cuda.synchronize()
 _lib.lib.sb200_debug_panel_stamps(None)
 s = st.cpu().numpy()
-names = ['stage+load regs', 'counter', 'phase1 factor', 'store S/X', 'phase2 inverse', 'writeback', 'phase3 apply']
-print({nm: int(s[i + 1] - s[i]) for i, nm in enumerate(names)}, 'total', int(s[6] - s[0]) if s[6] else int(s[5]-s[0]))
+names = ['stage + block load', 'phase1 factor', 'publish', 'phase2 inverse', 'writeback']   # slot 6 (phase 3) is not written by the last, row-less panel
+print({nm: int(s[i + 1] - s[i]) for i, nm in enumerate(names)}, 'total to writeback', int(s[5] - s[0]), 'cycles')

@@ -18,19 +18,33 @@ constexpr int NB = CHOL_NB;
 //   grid = (row tiles of 128 below the block (at least 1), batch), 256 threads.
 // Every CTA redundantly factors the 64x64 block (64^3/3 flop, ~6 us) and inverts it, so the panel solve
 // needs no second launch and no grid-wide dependency; the CTA that loaded the block last writes L, L^-1 back.
-//   phase 1: block -> registers (16x16 thread grid, 4x4 elements each), right-looking Cholesky with one
-//            __syncthreads per column (double-buffered column broadcast through shared memory);
-//   phase 2: X = L^-1 by forward substitution, 4 threads per column, rows interleaved, x_j by warp shuffle;
+//   phase 1: block -> registers (16x16 thread grid, 4x4 elements each), right-looking Cholesky, two columns per
+//            __syncthreads (double-buffered column-pair broadcast through shared memory);
+//   phase 2: X = L^-1: the four 16 x 16 diagonal inverses by substitution (one warp each), the rest by two levels
+//            of DMMA block merges;
 //   phase 3: P <- P X' for this CTA's 128 rows on the FP64 tensor cores (DMMA) out of shared memory.
 // FUSE (first block of a two-block leaf): the rank-64 update of the NEXT block column, C -= P Q' with Q = the first
 //   64 solved rows, is applied to this CTA's rows in the same pass (every CTA solves those 64 rows redundantly),
 //   which removes the smallest trailing-update GEMM launch of the recursion.
 constexpr int PT = 128;          // rows per CTA in the panel solve
 constexpr int SLD = NB + 4;      // shared leading dimension: (4 g + t) mod 16 distinct -> conflict-free LDS.64
+constexpr int WLD = 32 + 4;
 
 __device__ __forceinline__ void cp_async8_plain(double* smem, const double* gmem, bool valid) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(valid ? 8 : 0) : "memory");
+}
+
+// rsqrt for a normal positive double, branch free (MUFU.RSQ64H seed + one third-order step, the sequence the CUDA
+// library uses on its fast path) so that two of them interleave; anything else goes through rsqrt() below
+__device__ __forceinline__ double rsqrt_normal(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(x));
+    double e = fma(x, -(y * y), 1.0);
+    return fma(fma(e, 0.375, 0.5), y * e, y);
+}
+__device__ __forceinline__ bool normal_positive(double x) {
+    return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fe00000u;
 }
 
 template <bool FUSE>
@@ -43,8 +57,8 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
     double* S = sm;                       // [NB][SLD]  block, then L
     double* X = S + NB * SLD;             // [NB][SLD]  L^-1
     double* T = X + NB * SLD;             // [PT][SLD]  this CTA's rows of the panel
-    double* colbuf = T + PT * SLD;        // [2][NB]
-    double* invd = colbuf + 2 * NB;       // [NB]
+    double* W = T + PT * SLD;             // [32][WLD]  scratch of the inverse's block merges
+    double* invd = W + 32 * WLD;          // [NB]       reciprocals of L's diagonal
     double* Q = invd + NB;                // [NB][SLD]  FUSE only: the first 64 rows below the block, then solved
     const int tid = threadIdx.x, z = blockIdx.y;
 #define SB_STAMP(slot) do { if (stamps && z == 0 && blockIdx.x == 0 && tid == 0) stamps[slot] = clock64(); } while (0)
@@ -75,7 +89,11 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
     }
     if (cta_rows > 0) stage_tile(cta_r0);
 
-    // ---- phase 1: Cholesky of the (identity padded) 64 x 64 block, register resident
+    // ---- phase 1: Cholesky of the (identity padded) 64 x 64 block, register resident, TWO columns per barrier.
+    // FP64 results take ~50 cycles on B200, so the serial chain through the pivots is what this phase costs.  A pair
+    // of columns (j, j+1) is published together; every thread forms d = a_jj a_j+1,j+1 - a_j+1,j^2 (= p_j p_j+1)
+    // and takes rsqrt(p_j) and rsqrt(d) side by side: 1/sqrt(p_j+1) = rsqrt(d) sqrt(p_j), so the second pivot does
+    // not wait for the first column's reciprocal square root.
     const int ti = tid >> 4, tc = tid & 15;
     double a[4][4];
 #pragma unroll
@@ -104,44 +122,96 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
         __threadfence();
     }
     int bad_at = 0;
-    // Only the 16-column block index jb is unrolled (it selects registers); the column within the block is a
-    // real loop, so the code stays small (a fully unrolled 64-step version is instruction-fetch bound).
+    // Only the 16-column block index jb is unrolled (it selects registers); the column pair within the block is a
+    // real loop, so the code stays small (a fully unrolled version is instruction-fetch bound).
 #pragma unroll
     for (int jb = 0; jb < 4; jb++) {
 #pragma unroll 1
-        for (int jr = 0; jr < 16; jr++) {
+        for (int jr = 0; jr < 16; jr += 2) {
             const int j = jb * 16 + jr;
-            double* cb = colbuf + (j & 1) * NB;
+            double* cb0 = W + (jr & 2) * NB;          // double-buffered pair of columns (W is free until phase 2)
+            double* cb1 = cb0 + NB;
             if (tc == jr) {
 #pragma unroll
-                for (int ii = 0; ii < 4; ii++) cb[ti + 16 * ii] = a[ii][jb];
+                for (int ii = 0; ii < 4; ii++) cb0[ti + 16 * ii] = a[ii][jb];
+            } else if (tc == jr + 1) {
+#pragma unroll
+                for (int ii = 0; ii < 4; ii++) cb1[ti + 16 * ii] = a[ii][jb];
             }
             __syncthreads();
-            double ajj = cb[j];
-            bool bad = !(ajj > 0.0);
-            if (bad && bad_at == 0) bad_at = j0 + j + 1;
-            // one reciprocal square root instead of sqrt + divide on the per-column critical path
-            double inv = rsqrt(bad ? 1.0 : ajj);
-            double ljj = (bad ? 1.0 : ajj) * inv;
-            double li[4], lc[4];
+            double p0 = cb0[j];
+            const double q = cb0[j + 1], p1 = cb1[j + 1];
+            // this thread's rows / columns of the pair, fetched before the pivot arithmetic (in-order issue: loads
+            // placed after the reciprocal square roots would wait for them)
+            double x0i[4], x1i[4], x0c[4], x1c[4];
 #pragma unroll
-            for (int ii = 0; ii < 4; ii++) li[ii] = (ti + 16 * ii > j) ? cb[ti + 16 * ii] * inv : 0.0;
+            for (int e = 0; e < 4; e++) {
+                x0i[e] = cb0[ti + 16 * e];
+                x1i[e] = cb1[ti + 16 * e];
+                x0c[e] = cb0[tc + 16 * e];
+                x1c[e] = cb1[tc + 16 * e];
+            }
+            double det = fma(p0, p1, -(q * q));
+            double r0 = rsqrt_normal(p0), rd = rsqrt_normal(det);
+            if (!(normal_positive(p0) && normal_positive(det))) {   // block-uniform and rare: bad or denormal pivot;
+                                                                    // LAPACK-style report, bad pivot replaced by 1
+                if (!(p0 > 0.0)) {
+                    if (bad_at == 0) bad_at = j0 + j + 1;
+                    p0 = 1.0;
+                }
+                r0 = rsqrt(p0);
+                double l = q * r0, p1n = p1 - l * l;
+                if (!(p1n > 0.0)) {
+                    if (bad_at == 0) bad_at = j0 + j + 2;
+                    p1n = 1.0;
+                }
+                det = p0 * p1n;
+                rd = rsqrt(det);
+            }
+            const double s0 = p0 * r0;                // l(j, j)
+            const double inv1 = rd * s0;              // 1 / l(j+1, j+1)
+            const double l11 = det * rd * r0;         // l(j+1, j+1) = sqrt(det) / sqrt(p0)
+            const double l10 = q * r0;                // l(j+1, j)
+            double ui[4], vi[4], uc[4], vc[4];
 #pragma unroll
-            for (int cc = 0; cc < 4; cc++) lc[cc] = (tc + 16 * cc > j) ? cb[tc + 16 * cc] * inv : 0.0;
+            for (int ii = 0; ii < 4; ii++) {
+                const int i = ti + 16 * ii;
+                ui[ii] = (i > j) ? x0i[ii] * r0 : 0.0;
+                vi[ii] = (i > j + 1) ? (x1i[ii] - ui[ii] * l10) * inv1 : 0.0;
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) {
+                const int c = tc + 16 * cc;
+                uc[cc] = (c > j) ? x0c[cc] * r0 : 0.0;
+                vc[cc] = (c > j + 1) ? (x1c[cc] - uc[cc] * l10) * inv1 : 0.0;
+            }
 #pragma unroll
             for (int ii = 0; ii < 4; ii++)
 #pragma unroll
                 for (int cc = 0; cc < 4; cc++)
-                    if (ii >= jb && cc >= jb && cc <= ii) a[ii][cc] -= li[ii] * lc[cc];   // zero factors mask i<=j, c<=j
+                    if (ii >= jb && cc >= jb && cc <= ii) {       // zero factors mask the rows / columns already done
+                        a[ii][cc] -= ui[ii] * uc[cc];
+                        a[ii][cc] -= vi[ii] * vc[cc];
+                    }
             if (tc == jr) {
 #pragma unroll
                 for (int ii = 0; ii < 4; ii++) {
                     int i = ti + 16 * ii;
-                    if (i > j) a[ii][jb] = li[ii];
-                    else if (i == j) a[ii][jb] = ljj;
+                    if (i > j) a[ii][jb] = ui[ii];
+                    else if (i == j) a[ii][jb] = s0;
+                }
+            } else if (tc == jr + 1) {
+#pragma unroll
+                for (int ii = 0; ii < 4; ii++) {
+                    int i = ti + 16 * ii;
+                    if (i > j + 1) a[ii][jb] = vi[ii];
+                    else if (i == j + 1) a[ii][jb] = l11;
                 }
             }
-            if (ti == jr && tc == jr) invd[j] = inv;
+            if (tid == 0) {
+                invd[j] = r0;
+                invd[j + 1] = inv1;
+            }
         }
     }
     SB_STAMP(2);
@@ -158,27 +228,59 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
     if (writer && tid == 0 && bad_at != 0 && info[z] == 0) info[z] = bad_at;
 
     SB_STAMP(3);
-    // ---- phase 2: X = L^-1; thread (c, q) owns rows q, q+4, ... of column c
+    // ---- phase 2: X = L^-1.  (a) warps 0-3 invert one 16 x 16 diagonal sub-block each by forward substitution on the
+    // identity, lane (r, h) holding columns 8h .. 8h+7 of row r, rows unscaled until the end so that a step's chain
+    // is one shuffle and one FMA; (b) the off-diagonal blocks bottom-up like trtri_levels, X21 = -X22 (L21 X11) for
+    // the pairs of 16-blocks and then for the pair of 32-blocks, all on DMMA.
+    if (tid < 128) {
+        const int lane = tid & 31, k0 = 16 * (tid >> 5), r = lane & 15, h = lane >> 4;
+        double b[8], m[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) m[j] = (r > j) ? S[(k0 + r) * SLD + k0 + j] * invd[k0 + j] : 0.0;
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) b[cc] = (8 * h + cc == r) ? 1.0 : 0.0;
+#pragma unroll
+        for (int j = 0; j < 15; j++)
+#pragma unroll
+            for (int cc = 0; cc < 8; cc++) b[cc] -= m[j] * __shfl_sync(0xffffffffu, b[cc], j + 16 * h);
+        const double invr = invd[k0 + r];
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) X[(k0 + r) * SLD + k0 + 8 * h + cc] = (8 * h + cc <= r) ? b[cc] * invr : 0.0;
+    }
+    __syncthreads();
     {
-        const int c = tid >> 2, q = tid & 3, lane = tid & 31;
-        double bcol[16];
-#pragma unroll
-        for (int r = 0; r < 16; r++) bcol[r] = (q + 4 * r == c) ? 1.0 : 0.0;
-#pragma unroll
-        for (int jr = 0; jr < 16; jr++) {
+        const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll 1
-            for (int jq = 0; jq < 4; jq++) {
-                const int j = jr * 4 + jq;
-                double xj = __shfl_sync(0xffffffffu, bcol[jr] * invd[j], (lane & ~3) | jq);
-                if (q == jq) X[j * SLD + c] = xj;
-#pragma unroll
-                for (int r = 0; r < 16; r++)
-                    if (r >= jr) {
-                        int i = q + 4 * r;
-                        double lij = (i > j) ? S[i * SLD + j] : 0.0;
-                        bcol[r] -= lij * xj;
-                    }
+        for (int sz = 16; sz < NB; sz *= 2) {
+            const int tps = sz / 8, per_pair = tps * tps, total = (NB / (2 * sz)) * per_pair;
+            for (int tix = warp; tix < total; tix += 8) {             // W = L21 X11
+                const int pair = tix / per_pair, rem = tix % per_pair, mi = rem / tps, ni = rem % tps, b0 = pair * 2 * sz;
+                double c0 = 0.0, c1 = 0.0;
+                for (int k4 = 0; k4 < sz / 4; k4++) {
+                    double av = S[(b0 + sz + 8 * mi + g) * SLD + b0 + 4 * k4 + t];
+                    double bv = X[(b0 + 4 * k4 + t) * SLD + b0 + 8 * ni + g];
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(c0), "+d"(c1)
+                                 : "d"(av), "d"(bv));
+                }
+                W[(pair * sz + 8 * mi + g) * WLD + 8 * ni + 2 * t] = c0;
+                W[(pair * sz + 8 * mi + g) * WLD + 8 * ni + 2 * t + 1] = c1;
             }
+            __syncthreads();
+            for (int tix = warp; tix < total; tix += 8) {             // X21 = -X22 W
+                const int pair = tix / per_pair, rem = tix % per_pair, mi = rem / tps, ni = rem % tps, b0 = pair * 2 * sz;
+                double c0 = 0.0, c1 = 0.0;
+                for (int k4 = 0; k4 < sz / 4; k4++) {
+                    double av = -X[(b0 + sz + 8 * mi + g) * SLD + b0 + sz + 4 * k4 + t];
+                    double bv = W[(pair * sz + 4 * k4 + t) * WLD + 8 * ni + g];
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(c0), "+d"(c1)
+                                 : "d"(av), "d"(bv));
+                }
+                X[(b0 + sz + 8 * mi + g) * SLD + b0 + 8 * ni + 2 * t] = c0;
+                X[(b0 + sz + 8 * mi + g) * SLD + b0 + 8 * ni + 2 * t + 1] = c1;
+            }
+            __syncthreads();
         }
     }
     __syncthreads();
@@ -335,7 +437,7 @@ long long* g_panel_stamps = nullptr;      // instrumentation (sb200_debug_panel_
 
 // fuse_nc > 0 (nb == NB only): also apply this block column's rank-64 update to the next fuse_nc columns
 int panel(const CholBatch& c, int j0, int nb, int fuse_nc, cudaStream_t stream) {
-    constexpr size_t smem = (size_t)(2 * NB * SLD + PT * SLD + 3 * NB) * sizeof(double);
+    constexpr size_t smem = (size_t)(2 * NB * SLD + PT * SLD + 32 * WLD + NB) * sizeof(double);
     constexpr size_t smem_fuse = smem + (size_t)NB * SLD * sizeof(double);
     static bool configured[64] = {false};
     int dev = 0;
