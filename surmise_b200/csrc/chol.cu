@@ -151,27 +151,31 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
                 x0c[e] = cb0[tc + 16 * e];
                 x1c[e] = cb1[tc + 16 * e];
             }
-            double det = fma(p0, p1, -(q * q));
-            double r0 = rsqrt_normal(p0), rd = rsqrt_normal(det);
-            if (!(normal_positive(p0) && normal_positive(det))) {   // block-uniform and rare: bad or denormal pivot;
-                                                                    // LAPACK-style report, bad pivot replaced by 1
+            const double det = fma(p0, p1, -(q * q));
+            double r0 = rsqrt_normal(p0);
+            const double rd = rsqrt_normal(det);
+            double s0 = p0 * r0;                      // l(j, j)
+            double l10 = q * r0;                      // l(j+1, j)
+            double inv1 = rd * s0;                    // 1 / l(j+1, j+1)
+            double l11 = det * rd * r0;               // l(j+1, j+1) = sqrt(det) / sqrt(p0)
+            if (!(normal_positive(p0) && normal_positive(det))) {
+                // block-uniform and rare: a pivot that is not positive (LAPACK-style report, pivot replaced by 1) or
+                // a pair whose product left the normal range; one column after the other with the library rsqrt
                 if (!(p0 > 0.0)) {
                     if (bad_at == 0) bad_at = j0 + j + 1;
                     p0 = 1.0;
                 }
                 r0 = rsqrt(p0);
-                double l = q * r0, p1n = p1 - l * l;
+                s0 = p0 * r0;
+                l10 = q * r0;
+                double p1n = p1 - l10 * l10;
                 if (!(p1n > 0.0)) {
                     if (bad_at == 0) bad_at = j0 + j + 2;
                     p1n = 1.0;
                 }
-                det = p0 * p1n;
-                rd = rsqrt(det);
+                inv1 = rsqrt(p1n);
+                l11 = p1n * inv1;
             }
-            const double s0 = p0 * r0;                // l(j, j)
-            const double inv1 = rd * s0;              // 1 / l(j+1, j+1)
-            const double l11 = det * rd * r0;         // l(j+1, j+1) = sqrt(det) / sqrt(p0)
-            const double l10 = q * r0;                // l(j+1, j)
             double ui[4], vi[4], uc[4], vc[4];
 #pragma unroll
             for (int ii = 0; ii < 4; ii++) {

@@ -128,17 +128,43 @@ def test_potrf_trtri_lauum(ops, n, extra):
         assert e_l < 1e-11 and e_y < 1e-10 and e_i < 1e-9 and e_r < 1e-8
 
 
-def test_potrf_reports_indefinite(ops):
+@pytest.mark.parametrize('bad', [100, 101, 63, 64, 0, 1, 149])
+def test_potrf_reports_indefinite(ops, bad):
+    """LAPACK convention: info = order of the first leading minor that is not positive definite.  The panel kernel
+    factors two columns per step, so the first (even) and the second (odd) column of a pair take different paths."""
     import torch
     rng = np.random.default_rng(5)
     n = 150
     A = _spd(rng, n)
-    A[100, 100] = -5.0
-    buf = np.zeros((1, n, 152))
+    A[bad, bad] = -5.0
+    buf = np.zeros((2, n, 152))
     buf[0, :, :n] = np.tril(A)
+    buf[1, :, :n] = np.tril(_spd(rng, n))                # a healthy neighbour in the same batch stays healthy
     _, info = ops.potrf_batched(dev(buf), n, n)
     torch.cuda.synchronize()
-    assert int(info.cpu().numpy()[0]) == 101
+    got = info.cpu().numpy()
+    assert int(got[0]) == bad + 1 and int(got[1]) == 0
+
+
+def test_potrf_tiny_pivots(ops):
+    """Pivots far below 1 (down to 1e-280: d = p_j p_j+1 underflows to a denormal or zero there, which must send the
+    pair down the careful path, not into a wrong factor)."""
+    import torch
+    n = 70
+    scales = np.array([1.0, 1e-100, 1e-140, 1e-155, 1e-300])
+    rng = np.random.default_rng(11)
+    base = _spd(rng, n)
+    buf = np.zeros((len(scales), n, 72))
+    for z, sc in enumerate(scales):
+        buf[z, :, :n] = np.tril(base * sc)
+    Ad = dev(buf)
+    _, info = ops.potrf_batched(Ad, n, n)
+    torch.cuda.synchronize()
+    assert np.all(info.cpu().numpy() == 0)
+    out = Ad.cpu().numpy()
+    L = np.linalg.cholesky(base)
+    for z, sc in enumerate(scales):
+        assert rel(np.tril(out[z, :, :n]), L * np.sqrt(sc)) < 1e-11, sc
 
 
 def test_large_factorisation_properties(ops):
