@@ -131,12 +131,14 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
             const int j = jb * 16 + jr;
             double* cb0 = W + (jr & 2) * NB;          // double-buffered pair of columns (W is free until phase 2)
             double* cb1 = cb0 + NB;
-            if (tc == jr) {
+            if (tc == jr) {                           // rows of the 16-blocks above jb are finished: never read again
 #pragma unroll
-                for (int ii = 0; ii < 4; ii++) cb0[ti + 16 * ii] = a[ii][jb];
+                for (int ii = 0; ii < 4; ii++)
+                    if (ii >= jb) cb0[ti + 16 * ii] = a[ii][jb];
             } else if (tc == jr + 1) {
 #pragma unroll
-                for (int ii = 0; ii < 4; ii++) cb1[ti + 16 * ii] = a[ii][jb];
+                for (int ii = 0; ii < 4; ii++)
+                    if (ii >= jb) cb1[ti + 16 * ii] = a[ii][jb];
             }
             __syncthreads();
             double p0 = cb0[j];
@@ -145,12 +147,13 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
             // placed after the reciprocal square roots would wait for them)
             double x0i[4], x1i[4], x0c[4], x1c[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                x0i[e] = cb0[ti + 16 * e];
-                x1i[e] = cb1[ti + 16 * e];
-                x0c[e] = cb0[tc + 16 * e];
-                x1c[e] = cb1[tc + 16 * e];
-            }
+            for (int e = 0; e < 4; e++)
+                if (e >= jb) {                        // (compile time)
+                    x0i[e] = cb0[ti + 16 * e];
+                    x1i[e] = cb1[ti + 16 * e];
+                    x0c[e] = cb0[tc + 16 * e];
+                    x1c[e] = cb1[tc + 16 * e];
+                }
             const double det = fma(p0, p1, -(q * q));
             double r0 = rsqrt_normal(p0);
             const double rd = rsqrt_normal(det);
@@ -176,40 +179,51 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
                 inv1 = rsqrt(p1n);
                 l11 = p1n * inv1;
             }
+            // Rows / columns in 16-blocks below jb are all still active (no mask), those of block jb are masked by
+            // position, those above are finished and skipped -- all decided at compile time (jb is unrolled).
             double ui[4], vi[4], uc[4], vc[4];
 #pragma unroll
-            for (int ii = 0; ii < 4; ii++) {
-                const int i = ti + 16 * ii;
-                ui[ii] = (i > j) ? x0i[ii] * r0 : 0.0;
-                vi[ii] = (i > j + 1) ? (x1i[ii] - ui[ii] * l10) * inv1 : 0.0;
-            }
-#pragma unroll
-            for (int cc = 0; cc < 4; cc++) {
-                const int c = tc + 16 * cc;
-                uc[cc] = (c > j) ? x0c[cc] * r0 : 0.0;
-                vc[cc] = (c > j + 1) ? (x1c[cc] - uc[cc] * l10) * inv1 : 0.0;
+            for (int e = 0; e < 4; e++) {
+                if (e < jb) continue;
+                ui[e] = x0i[e] * r0;
+                vi[e] = (x1i[e] - ui[e] * l10) * inv1;
+                uc[e] = x0c[e] * r0;
+                vc[e] = (x1c[e] - uc[e] * l10) * inv1;
+                if (e == jb) {
+                    const int i = ti + 16 * e, c = tc + 16 * e;
+                    if (i <= j) ui[e] = 0.0;
+                    if (i <= j + 1) vi[e] = 0.0;
+                    if (c <= j) uc[e] = 0.0;
+                    if (c <= j + 1) vc[e] = 0.0;
+                }
             }
 #pragma unroll
             for (int ii = 0; ii < 4; ii++)
 #pragma unroll
                 for (int cc = 0; cc < 4; cc++)
-                    if (ii >= jb && cc >= jb && cc <= ii) {       // zero factors mask the rows / columns already done
+                    if (ii >= jb && cc >= jb && cc <= ii) {
                         a[ii][cc] -= ui[ii] * uc[cc];
                         a[ii][cc] -= vi[ii] * vc[cc];
                     }
             if (tc == jr) {
 #pragma unroll
                 for (int ii = 0; ii < 4; ii++) {
-                    int i = ti + 16 * ii;
-                    if (i > j) a[ii][jb] = ui[ii];
-                    else if (i == j) a[ii][jb] = s0;
+                    if (ii > jb) a[ii][jb] = ui[ii];
+                    else if (ii == jb) {
+                        const int i = ti + 16 * ii;
+                        if (i > j) a[ii][jb] = ui[ii];
+                        else if (i == j) a[ii][jb] = s0;
+                    }
                 }
             } else if (tc == jr + 1) {
 #pragma unroll
                 for (int ii = 0; ii < 4; ii++) {
-                    int i = ti + 16 * ii;
-                    if (i > j + 1) a[ii][jb] = vi[ii];
-                    else if (i == j + 1) a[ii][jb] = l11;
+                    if (ii > jb) a[ii][jb] = vi[ii];
+                    else if (ii == jb) {
+                        const int i = ti + 16 * ii;
+                        if (i > j + 1) a[ii][jb] = vi[ii];
+                        else if (i == j + 1) a[ii][jb] = l11;
+                    }
                 }
             }
             if (tid == 0) {
