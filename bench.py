@@ -130,6 +130,17 @@ def cpu_nll_grad_sample(w, npcs=1):
     return npcs / (time.perf_counter() - t0), out
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core it can, so the
+    BLAS/LAPACK pools behind numpy are raised to the cores this process may run on."""
+    try:
+        from threadpoolctl import threadpool_limits
+        n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+
+
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -147,6 +158,7 @@ def run_reference(args):
         return
     w = workload()
     kind = cpu_functions()[2]
+    use_all_host_threads()
     for _ in range(args.warmup if args.warmup < 2 else 1):      # one untimed pass is enough to page LAPACK in
         cpu_nll_grad_sample(w, 1)
     t0 = time.perf_counter()
@@ -321,12 +333,14 @@ def main():
         ach = (g_fl.value / (g_ms.value * 1e-3) / 1e12) if g_ms.value > 0 else None
         cpu = None
         if world == 1:
+            use_all_host_threads()
+            cpu_nll_grad_sample(w, 1)                   # untimed: pages the reference and LAPACK in
             v, ref_out = cpu_nll_grad_sample(w, 1)
             got = res[0].cpu().numpy()
             nerr = abs(got[0] - ref_out[0][0]) / (abs(ref_out[0][0]) + n)
             gerr = float(np.max(np.abs(got[1:1 + p] - ref_out[0][1])) / np.max(np.abs(ref_out[0][1])))
             cpu = {'value': v, 'unit': UNIT, 'cores': host_threads(), 'kind': cpu_functions()[2],
-                   'sample': '1 of %d components, one NLL+grad evaluation (eigh form, numpy/LAPACK)' % k,
+                   'sample': '1 of %d components, one NLL+grad evaluation after one untimed call (eigh form, numpy/LAPACK)' % k,
                    'parity_vs_gpu': {'nll_rel': nerr, 'grad_rel': gerr}}
         line = {
             'metric': METRIC, 'value': evals / (ms_dev * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': K,
