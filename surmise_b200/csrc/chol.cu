@@ -527,8 +527,9 @@ struct TrtriCtx {
     double* tmp; long tmp_stride;
 };
 
-// X21 = -X22 (L21 X11) for `pairs` adjacent (s, s2) block pairs starting at block offset j0, spaced 2s apart
-int trtri_merge(const TrtriCtx& t, int j0, int s, int s2, int pairs, cudaStream_t stream) {
+// X21 = -X22 (L21 X11) for `pairs` adjacent (s, s2) block pairs starting at block offset j0, spaced 2s apart;
+// last_s2 > 0: the last of them is ragged, its lower block has last_s2 < s2 rows
+int trtri_merge(const TrtriCtx& t, int j0, int s, int s2, int pairs, int last_s2, cudaStream_t stream) {
     const long step_i = (long)2 * s * (t.ldi + 1), step_x = (long)2 * s * (t.ldl + 1), step_t = (long)s * s;
     {                                          // T = L21 * X11          (s2 x s per pair)
         GemmArgs g{};
@@ -537,7 +538,7 @@ int trtri_merge(const TrtriCtx& t, int j0, int s, int s2, int pairs, cudaStream_
         g.B = t.X + (long)j0 * t.ldl + j0; g.ldb = t.ldl; g.strideB = t.strideL; g.b_kc = false;
         g.C = t.tmp; g.ldc = s; g.strideC = t.tmp_stride;
         g.alpha = 1.0; g.beta = 0.0; g.flags = GEMM_B_UPPER;     // X11[k][n] == 0 for k < n
-        g.inner_batch = t.batch; g.strideA2 = step_i; g.strideB2 = step_x; g.strideC2 = step_t;
+        g.inner_batch = t.batch; g.strideA2 = step_i; g.strideB2 = step_x; g.strideC2 = step_t; g.last_M = last_s2;
         SB_TRY(launch_dgemm(g, t.batch * pairs, -1, stream));
     }
     {                                          // X21 = -X22 * T
@@ -547,21 +548,23 @@ int trtri_merge(const TrtriCtx& t, int j0, int s, int s2, int pairs, cudaStream_
         g.B = t.tmp; g.ldb = s; g.strideB = t.tmp_stride; g.b_kc = false;
         g.C = t.X + (long)(j0 + s) * t.ldl + j0; g.ldc = t.ldl; g.strideC = t.strideL;
         g.alpha = -1.0; g.beta = 0.0; g.flags = GEMM_A_LOWER;
-        g.inner_batch = t.batch; g.strideA2 = step_x; g.strideB2 = step_t; g.strideC2 = step_x;
+        g.inner_batch = t.batch; g.strideA2 = step_x; g.strideB2 = step_t; g.strideC2 = step_x; g.last_M = last_s2;
         SB_TRY(launch_dgemm(g, t.batch * pairs, -1, stream));
     }
     return 0;
 }
 
 // Bottom-up: at level s all pairs of adjacent s-blocks are independent, so one (two-level batched) launch pair
-// handles every full pair of every matrix; a ragged last pair (right block shorter) gets its own launches.
+// handles every pair of every matrix, the ragged last pair (right block shorter) included as a shorter last group.
 int trtri_levels(const TrtriCtx& t, int n, cudaStream_t stream) {
     for (long s = NB; s < n; s *= 2) {
         int full = (int)(n / (2 * s));                 // pairs with two complete s-blocks
         long rest = n - (long)full * 2 * s;            // columns after the last full pair
-        SB_CHECK_ARG((long)t.batch * (full > 0 ? full : 1) <= 65535, "trtri: batch x pairs exceeds grid.z");
-        if (full > 0) SB_TRY(trtri_merge(t, 0, (int)s, (int)s, full, stream));
-        if (rest > s) SB_TRY(trtri_merge(t, (int)(full * 2 * s), (int)s, (int)(rest - s), 1, stream));
+        const bool ragged = rest > s;
+        SB_CHECK_ARG((long)t.batch * (full + 1) <= 65535, "trtri: batch x pairs exceeds grid.z");
+        if (full > 0 && ragged) SB_TRY(trtri_merge(t, 0, (int)s, (int)s, full + 1, (int)(rest - s), stream));
+        else if (full > 0) SB_TRY(trtri_merge(t, 0, (int)s, (int)s, full, 0, stream));
+        else if (ragged) SB_TRY(trtri_merge(t, 0, (int)s, (int)(rest - s), 1, 0, stream));
     }
     return 0;
 }

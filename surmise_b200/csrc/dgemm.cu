@@ -111,6 +111,10 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 6
 
     const int tid = threadIdx.x;
     const int z = blockIdx.z;
+    const int z1 = p.inner_batch > 0 ? z % p.inner_batch : z;
+    const long z2 = p.inner_batch > 0 ? z / p.inner_batch : 0;
+    // two-level batches may end with a shorter group (the ragged last block pair of a trtri level)
+    const int M = (p.last_M > 0 && p.inner_batch > 0 && z2 == (long)gridDim.z / p.inner_batch - 1) ? p.last_M : p.M;
     // longest-k tiles first: with a lower-triangular A the k-range grows with m, so walk the row tiles backwards
     // (lower-triangular B / upper-triangular A and B already start with their longest tiles)
     const int tile_m = (p.flags & GEMM_A_LOWER) ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y;
@@ -119,11 +123,9 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 6
     // lower-only output: row tiles of column block J start ON the diagonal (row n0), so only the first tile of each
     // column block straddles it (25 % of one tile wasted per block instead of 50 % of two)
     const int m0 = (p.flags & GEMM_C_LOWER) ? n0 + tile_m * BM : tile_m * BM;
-    if (m0 >= p.M) return;
-    const int m_end = min(p.M, m0 + BM), n_end = min(p.N, n0 + BN);
+    if (m0 >= M) return;
+    const int m_end = min(M, m0 + BM), n_end = min(p.N, n0 + BN);
 
-    const int z1 = p.inner_batch > 0 ? z % p.inner_batch : z;
-    const long z2 = p.inner_batch > 0 ? z / p.inner_batch : 0;
     const double* A = p.A + (long)(p.idxA ? p.idxA[z1] : z1) * p.strideA + z2 * p.strideA2;
     const double* B = p.B + (long)(p.idxB ? p.idxB[z1] : z1) * p.strideB + z2 * p.strideB2;
     double* C = p.C + (long)z1 * p.strideC + z2 * p.strideC2;
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 6
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
         if (s < ktiles) {
-            load_tile<BM, AKC, NTHREADS>(As + s * A_TILE, A, p.lda, m0, p.M, k_lo + s * BK, k_hi, a16, tid);
+            load_tile<BM, AKC, NTHREADS>(As + s * A_TILE, A, p.lda, m0, M, k_lo + s * BK, k_hi, a16, tid);
             load_tile<BN, BKC, NTHREADS>(Bs + s * B_TILE, B, p.ldb, n0, p.N, k_lo + s * BK, k_hi, b16, tid);
         }
         cp_async_commit();
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 6
         for (int j = 0; j < NI; j++) {
             const int col = n0 + wn0 + j * 8 + 2 * t;
             double c0 = 0.0, c1 = 0.0;
-            if (fold && row < p.M) {
+            if (fold && row < M) {
                 const double* ptr = C + (long)row * p.ldc + col;
                 if (c16 && col + 1 < p.N) {
                     double2 o = *reinterpret_cast<const double2*>(ptr);
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 6
         if (p.flags & GEMM_B_LOWER) wk_hi = min(wk_hi, wc0 + WN);
         if (p.flags & GEMM_B_UPPER) wk_lo = max(wk_lo, wc0);
         if ((p.flags & GEMM_C_LOWER) && wc0 > wr0 + WM - 1) wk_hi = wk_lo;
-        if (wr0 >= p.M || wc0 >= p.N) wk_hi = wk_lo;
+        if (wr0 >= M || wc0 >= p.N) wk_hi = wk_lo;
         wkt_lo = (wk_lo - k_lo) / BK;
         wkt_hi = wk_hi > wk_lo ? (wk_hi - k_lo + BK - 1) / BK : 0;
     }
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 6
             int nx = kt + STAGES - 1;
             if (nx < ktiles) {
                 int slot = nx % STAGES;
-                load_tile<BM, AKC, NTHREADS>(As + slot * A_TILE, A, p.lda, m0, p.M, k_lo + nx * BK, k_hi, a16, tid);
+                load_tile<BM, AKC, NTHREADS>(As + slot * A_TILE, A, p.lda, m0, M, k_lo + nx * BK, k_hi, a16, tid);
                 load_tile<BN, BKC, NTHREADS>(Bs + slot * B_TILE, B, p.ldb, n0, p.N, k_lo + nx * BK, k_hi, b16, tid);
             }
             cp_async_commit();
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN <= 64 * 6
 #pragma unroll
     for (int i = 0; i < MI; i++) {
         int row = m0 + wm0 + i * 8 + g;
-        if (row >= p.M) continue;
+        if (row >= M) continue;
 #pragma unroll
         for (int j = 0; j < NI; j++) {
             int col = n0 + wn0 + j * 8 + 2 * t;
@@ -311,7 +313,13 @@ int launch_one(const GemmArgs& g, int batch, cudaStream_t stream) {
         SB_CUDA(cudaEventRecord(e0, stream));
         kern<<<grid, NTHREADS, smem, stream>>>(g);
         SB_CUDA(cudaEventRecord(e1, stream));
-        gemm_profile_add(e0, e1, algorithmic_flops(g, BM, BN) * batch);
+        double fl = algorithmic_flops(g, BM, BN) * batch;
+        if (g.last_M > 0 && g.inner_batch > 0) {             // the last group of a two-level batch is shorter
+            GemmArgs gl = g;
+            gl.M = g.last_M;
+            fl += (algorithmic_flops(gl, BM, BN) - algorithmic_flops(g, BM, BN)) * g.inner_batch;
+        }
+        gemm_profile_add(e0, e1, fl);
         SB_LAUNCH_CHECK();
         return 0;
     }

@@ -31,6 +31,7 @@ struct GemmArgs {
     // apply to z1, these to z2 (e.g. z1 = matrix of the batch, z2 = diagonal block pair within the matrix)
     int inner_batch;
     long strideA2, strideB2, strideC2;
+    int last_M;     // > 0: the last z2 group has this many rows instead of M (0 = all groups alike)
 };
 
 // tile: 7 = 64x64 CTA tile, 4 warps, 4 CTAs/SM (default, -1); 1 = 128x64 (2 CTAs/SM); 0 = 128x128 (1 CTA/SM);
