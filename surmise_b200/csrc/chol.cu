@@ -16,7 +16,7 @@ constexpr int NB = CHOL_NB;
 // ------------------------------------------------------------------------------------------------
 // Panel kernel: factor one 64-wide diagonal block AND solve the rows below it, in one launch.
 //   grid = (row tiles of 128 below the block (at least 1), batch), 256 threads.
-// Every CTA redundantly factors the 64x64 block (64^3/3 flop, ~6 us) and inverts it, so the panel solve
+// Every CTA redundantly factors the 64x64 block (64^3/3 flop, ~13 us) and inverts it (~3 us), so the panel solve
 // needs no second launch and no grid-wide dependency; the CTA that loaded the block last writes L, L^-1 back.
 //   phase 1: block -> registers (16x16 thread grid, 4x4 elements each), right-looking Cholesky, two columns per
 //            __syncthreads (double-buffered column-pair broadcast through shared memory);
