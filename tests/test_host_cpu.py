@@ -27,6 +27,34 @@ def test_library_exports_every_declared_symbol():
     assert L.lib.sb200_launch_count() == 0
 
 
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: the header must compile as C99 (no C++ or torch types in the signatures) and a
+    C program must be able to load the library and call it (a cgo / JNI / ctypes stub does nothing more)."""
+    import shutil
+    import subprocess
+    import surmise_b200._lib as L
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('gcc not available')
+    hdr = os.path.join(ROOT, 'include', 'surmise_b200.h')
+    subprocess.check_call([gcc, '-std=c99', '-Wall', '-Werror', '-fsyntax-only', '-x', 'c', hdr])
+    src = tmp_path / 'abi.c'
+    src.write_text(
+        '#include <stdio.h>\n#include <dlfcn.h>\n#include "surmise_b200.h"\n'
+        'int main(int argc, char** argv) {\n'
+        '  void* h = dlopen(argv[1], RTLD_NOW);\n'
+        '  if (!h) { fprintf(stderr, "%s\\n", dlerror()); return 2; }\n'
+        '  int (*ver)(void) = (int (*)(void))dlsym(h, "sb200_version");\n'
+        '  const char* (*err)(void) = (const char* (*)(void))dlsym(h, "sb200_last_error");\n'
+        '  if (!ver || !err) return 3;\n'
+        '  printf("%d\\n", ver());\n'
+        '  return 0;\n}\n')
+    exe = tmp_path / 'abi'
+    subprocess.check_call([gcc, '-std=c99', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe), '-ldl'])
+    out = subprocess.check_output([str(exe), L.LIB_PATH], text=True)
+    assert int(out.strip()) >= 100
+
+
 def test_no_cpu_fallback_without_cuda():
     import torch
     if torch.cuda.is_available():
