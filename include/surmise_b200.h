@@ -7,8 +7,12 @@
  * Conventions
  *   - every array pointer is a DEVICE pointer to fp64 (or int32 where typed so), row-major;
  *   - the caller owns all memory, including workspaces (size them with the *_workspace queries);
- *     the library never allocates or frees device memory and keeps no global mutable state
- *     apart from a thread-local last-error string and one-time kernel attribute set-up;
+ *     the library never allocates or frees device memory.  The compute entry points keep no mutable state of their
+ *     own: what exists process-wide is (a) a thread-local last-error string, (b) the one-time per-device kernel
+ *     attribute set-up (mutex-guarded, safe for concurrent first calls from several host threads), and (c) the
+ *     instrumentation / testing switches declared below -- an atomic launch counter, the optional GEMM timing record
+ *     (mutex-guarded), sb200_gp_force_blocked_path and sb200_debug_panel_stamps (atomics; set them only while no
+ *     call is in flight).  None of (c) changes a numerical result;
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); outputs are valid
  *     after the stream is synchronised;
  *   - return value: 0 success, < 0 invalid argument, > 0 a cudaError_t; sb200_last_error() explains;
@@ -89,7 +93,10 @@ int sb200_gp_weights(int k, int n, const double* Linv, long ldl, long stride_lin
                      double sig2ofconst, double* pw, double* sig2, double* ytmp, void* stream);
 
 /* Replaces the per-PC loop of PCGPwM.predict (PCGPwM.py:219-270): predvecs/predvars (B,k) and, if
- * want_grad, their gradients (B,k,d) at thetanew (B,d).
+ * want_grad, their gradients (B,k,d) at thetanew (B,d).  want_grad: 0 none, 1 gradients, 2 gradients for a caller whose
+ * WHOLE population is one theta with d == 1 -- there the reference applies (1-nug) to predvecs_gradtheta once instead
+ * of twice (PCGPwM.py:236 and 262-268); the caller decides this from its full population, so chunks and per-rank
+ * slices of a larger population (B == 1 locally) keep the B > 1 behaviour.
  *   hypcov (nu, d+1): the distinct covariance hyper-parameter sets;  fu (nf): set used by factor f;
  *   Linv (nf, n, ldl): distinct factors;  fidx (k): factor used by PC j;  nug, sig2 (k);  pw (k, n). */
 size_t sb200_gp_predict_workspace(int k, int nf, int nu, int n, int d, int B, int want_grad);

@@ -124,7 +124,20 @@ def jacobi_sweeps(fit_one, k, p, comm, draw_rows, sweeps=3, start_hyps=None, sta
         table = comm.allgather_rows(local, sizes)
         hyps, hypinds = table[:, :p].copy(), table[:, p].copy()
         rows_used = drawn
-    return hyps, hypinds.astype(int), rows_used
+    return hyps, canonical_hypinds(hyps), rows_used
+
+
+def canonical_hypinds(hyps):
+    """hypind[j] = the smallest index whose hyper-parameter row is byte-identical to row j.
+
+    In a Jacobi sweep component j can adopt leader L's hyper-parameters of the PREVIOUS sweep while L itself moves on
+    in the same sweep, which would leave hypind[j] == L with hyp[j] != hyp[L].  The reference's consumers rely on
+    emulist[j]['hyp'] == emulist[hypind[j]]['hyp'] (PCGPwM.predict indexes rsave by hypind, PCGPwM.py:219-230), so the
+    indices are recomputed from the final table -- identically on every rank."""
+    first, out = {}, np.zeros(len(hyps), dtype=int)
+    for j, row in enumerate(np.ascontiguousarray(hyps, dtype=np.float64)):
+        out[j] = first.setdefault(row.tobytes(), j)
+    return out
 
 
 def sharded_rows(fn, theta, comm):

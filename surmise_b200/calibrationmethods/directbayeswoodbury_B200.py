@@ -43,9 +43,12 @@ def woodbury_constants(fitinfo, emu, x, y):
     info = _device_state(emu)
     st = info['_b200']
     # fast path for the sampler loop: the same x / y / yvar objects (with unchanged sums, in case they were edited in
-    # place) as last time -> skip row matching and the byte-wise comparison
-    ident = (id(x), id(y), id(fitinfo['yvar']), id(st['Linv']), float(np.sum(y)), float(np.sum(fitinfo['yvar'])))
-    if cache is not None and cache.get('ident') == ident and cache['refs'][0] is x and cache['refs'][1] is y:
+    # place) as last time -> skip row matching and the byte-wise comparison.  The emulator's device state carries a
+    # process-wide fit-generation token (a refit / update / adopt gets a new one), and the cache keeps a strong
+    # reference to the state it was built from, so a recycled id() can never alias a previous fit.
+    ident = (id(x), id(y), id(fitinfo['yvar']), st.get('generation'), float(np.sum(y)), float(np.sum(fitinfo['yvar'])))
+    if (cache is not None and cache.get('ident') == ident and cache['refs'][0] is x and cache['refs'][1] is y
+            and cache.get('state') is st):
         return cache
     ops = _ops()
     torch = ops._torch()
@@ -56,8 +59,8 @@ def woodbury_constants(fitinfo, emu, x, y):
     nx = info['x'].shape[0] if x is None else x.shape[0]
     if xind.shape[0] != nx or not np.array_equal(xnewind, np.arange(nx)):
         raise ValueError('Every calibration x must match exactly one row of the emulator x.')
-    key = (xind.tobytes(), y.tobytes(), yvar.tobytes(), id(st['Linv']))
-    if cache is not None and cache['key'] == key:
+    key = (xind.tobytes(), y.tobytes(), yvar.tobytes(), st.get('generation'))
+    if cache is not None and cache['key'] == key and cache.get('state') is st:
         cache['ident'], cache['refs'] = ident, (x, y_in, fitinfo['yvar'])
         return cache
     dev = st['phi'].device
@@ -69,7 +72,7 @@ def woodbury_constants(fitinfo, emu, x, y):
     sinv = np.stack([1 / yv, 1 / (yv + np.abs(extravar))])                   # dbw.py:280-284 when triggered
     G = np.stack([phi.T @ (phi * s[:, None]) for s in sinv])
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    cache = {'key': key, 'ident': ident, 'refs': (x, y_in, fitinfo['yvar']), 'phiT': t(phi.T), 'resid0': t(y - offset),
+    cache = {'key': key, 'ident': ident, 'refs': (x, y_in, fitinfo['yvar']), 'state': st, 'phiT': t(phi.T), 'resid0': t(y - offset),
              'extravar': t(extravar), 'sinv': t(sinv), 'G': t(G), 'xind': xind}
     fitinfo['_b200cal'] = cache
     return cache
@@ -168,7 +171,7 @@ def _evaluate_sharded(fitinfo, emu, theta, y, x, return_grad, comm):
     fired = torch.zeros(1, dtype=torch.int32, device=dev)
     pred = None
     if hi > lo:
-        pred = _emu_method.predict_pcspace(info, theta[lo:hi], return_grad)
+        pred = _emu_method.predict_pcspace(info, theta[lo:hi], return_grad, population=theta.shape[0])
         fired = ops.woodbury_trigger(consts, pred[1])
     comm.dist.all_reduce(fired, op=comm.dist.ReduceOp.MAX)
     width = 1 + (theta.shape[1] if return_grad else 0)

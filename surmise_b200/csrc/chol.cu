@@ -451,20 +451,18 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
 #undef SB_STAMP
 }
 
-long long* g_panel_stamps = nullptr;      // instrumentation (sb200_debug_panel_stamps)
+static std::atomic<long long*> g_panel_stamps{nullptr};      // instrumentation (sb200_debug_panel_stamps)
 
 // fuse_nc > 0 (nb == NB only): also apply this block column's rank-64 update to the next fuse_nc columns
 int panel(const CholBatch& c, int j0, int nb, int fuse_nc, cudaStream_t stream) {
     constexpr size_t smem = (size_t)(2 * NB * SLD + PT * SLD + 32 * WLD + NB) * sizeof(double);
     constexpr size_t smem_fuse = smem + (size_t)NB * SLD * sizeof(double);
-    static bool configured[64] = {false};
-    int dev = 0;
-    SB_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && !configured[dev]) {
+    static DeviceOnce once;
+    SB_TRY(once.run([&]() -> int {
         SB_CUDA(cudaFuncSetAttribute(potrf_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SB_CUDA(cudaFuncSetAttribute(potrf_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fuse));
-        configured[dev] = true;
-    }
+        return 0;
+    }));
     int below = c.mrows - (j0 + nb);
     // every CTA repeats the 64x64 factorisation, so keep the grid within one wave of the 148 SMs (1 CTA/SM):
     // each CTA takes as many 128-row sub-tiles as that needs
@@ -476,12 +474,12 @@ int panel(const CholBatch& c, int j0, int nb, int fuse_nc, cudaStream_t stream) 
         potrf_panel_kernel<true><<<grid, 256, smem_fuse, stream>>>(c.A + (long)j0 * c.lda + j0, c.lda, c.strideA,
                                                                    c.Dinv + (long)(j0 / NB) * c.blockD, c.ldd, c.strideD,
                                                                    nb, j0, below, rows_per_cta, fuse_nc, c.info,
-                                                                   c.counters, g_panel_stamps);
+                                                                   c.counters, g_panel_stamps.load());
     else
         potrf_panel_kernel<false><<<grid, 256, smem, stream>>>(c.A + (long)j0 * c.lda + j0, c.lda, c.strideA,
                                                                 c.Dinv + (long)(j0 / NB) * c.blockD, c.ldd, c.strideD,
                                                                 nb, j0, below, rows_per_cta, 0, c.info, c.counters,
-                                                                g_panel_stamps);
+                                                                g_panel_stamps.load());
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -613,7 +611,7 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(int n, const double* __
 
 }  // namespace
 
-void debug_panel_stamps(long long* p) { g_panel_stamps = p; }
+void debug_panel_stamps(long long* p) { g_panel_stamps.store(p); }
 
 size_t trtri_tmp_elems(int n) {
     // level s uses full_pairs * s * s (+ rest * s for a ragged pair) <= n^2 / 4 (+ slack for block rounding)

@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdint>
 #include <cstddef>
+#include <atomic>
+#include <mutex>
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "surmise_b200 kernels are written for sm_100a (B200) only"
@@ -50,6 +52,34 @@ void gemm_profile_add(cudaEvent_t start, cudaEvent_t stop, double flops);
         int rc__ = (expr);      \
         if (rc__ != 0) return rc__; \
     } while (0)
+
+
+// One-time, per-device kernel attribute set-up (cudaFuncSetAttribute for > 48 KB of dynamic shared memory) that is
+// safe when several host threads make their first call on a fresh device at the same moment: double-checked under
+// a mutex; devices beyond the table are simply configured on every call (the attribute call is idempotent).
+struct DeviceOnce {
+    std::atomic<int> done[64];
+    std::mutex mu;
+    DeviceOnce() {
+        for (auto& d : done) d.store(0, std::memory_order_relaxed);
+    }
+    template <class F>
+    int run(F&& configure) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) {
+            set_last_error("cudaGetDevice failed: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        if (dev < 0 || dev >= 64) return configure();
+        if (done[dev].load(std::memory_order_acquire)) return 0;
+        std::lock_guard<std::mutex> lk(mu);
+        if (done[dev].load(std::memory_order_relaxed)) return 0;
+        int rc = configure();
+        if (rc == 0) done[dev].store(1, std::memory_order_release);
+        return rc;
+    }
+};
 
 static inline long round_up(long v, long a) { return (v + a - 1) / a * a; }
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }

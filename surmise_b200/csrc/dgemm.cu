@@ -297,13 +297,11 @@ template <int BM, int BN, int WM, int WN, bool AKC, bool BKC>
 int launch_one(const GemmArgs& g, int batch, cudaStream_t stream) {
     constexpr size_t smem = (size_t)STAGES * (BK * (BM + 4) + BK * (BN + 4)) * sizeof(double);
     auto kern = dgemm_dmma_kernel<BM, BN, WM, WN, AKC, BKC>;
-    static bool configured[64] = {false};
-    int dev = 0;
-    SB_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && !configured[dev]) {
+    static DeviceOnce once;
+    SB_TRY(once.run([&]() -> int {
         SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[dev] = true;
-    }
+        return 0;
+    }));
     constexpr int NTHREADS = (BM / WM) * (BN / WN) * 32;
     dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), batch);
     if (gemm_profile_enabled()) {

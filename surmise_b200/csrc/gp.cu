@@ -243,8 +243,8 @@ long lda_for(int n) { return round_up(n, 8); }
 }  // namespace
 
 // testing hook: route small problems through the blocked (multi-launch) path as well
-static bool g_force_blocked = false;
-void gp_force_blocked_path(int on) { g_force_blocked = on != 0; }
+static std::atomic<bool> g_force_blocked{false};      // testing switch (sb200_gp_force_blocked_path)
+void gp_force_blocked_path(int on) { g_force_blocked.store(on != 0); }
 
 // ------------------------------------------------------------------------------------------------
 size_t gp_nll_grad_workspace(int batch, int n, int d, int want_grad) {
@@ -404,6 +404,11 @@ int gp_predict(int K, int nf, int nu, int n, int d, int B, const double* theta, 
     SB_CHECK_ARG(d >= 1 && d <= MAXD, "gp_predict: d=%d outside [1,%d]", d, MAXD);
     SB_CHECK_ARG(workspace_bytes >= gp_predict_workspace(K, nf, nu, n, d, B, want_grad), "gp_predict: workspace too small");
     SB_CHECK_ARG(!want_grad || (dpv && dpvar), "gp_predict: gradient outputs are NULL");
+    // want_grad == 2: the caller's WHOLE population is one theta with d == 1, where the reference applies (1-nug) to
+    // predvecs_gradtheta once instead of twice (PCGPwM.py:236, 262-268).  Decided by the caller from the full
+    // population, never from the size of a chunk or of a rank's slice.
+    const int single_quirk = (want_grad == 2) ? 1 : 0;
+    want_grad = want_grad ? 1 : 0;
     Workspace w(workspace, workspace_bytes);
     const long ldb = ldb_for(B);
     const int Q = 2 + (want_grad ? 2 * d : 0);
@@ -449,7 +454,7 @@ int gp_predict(int K, int nf, int nu, int n, int d, int B, const double* theta, 
         SB_LAUNCH_CHECK();
         dim3 grid2(cdiv(B, 128), K);
         predict_reduce_kernel<<<grid2, 128, 0, stream>>>(K, d, B, ldb, nchunks, Q, partial, nug, sig2, want_grad,
-                                                         (B == 1 && d == 1) ? 1 : 0, predvecs, predvars, dpv, dpvar);
+                                                         single_quirk, predvecs, predvars, dpv, dpvar);
         SB_LAUNCH_CHECK();
     }
     return 0;

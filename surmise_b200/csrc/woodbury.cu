@@ -178,13 +178,11 @@ int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const do
     SB_CHECK_ARG(!want_grad || (dpv && dpvar && dll), "woodbury: gradient buffers are NULL");
     size_t smem = (size_t)(2 * K * K + m + 7 * K + 32) * sizeof(double);
     SB_CHECK_ARG(smem <= 227 * 1024, "woodbury: k=%d, m=%d need %zu B of shared memory", K, m, smem);
-    static bool configured[64] = {false};
-    int dev = 0;
-    SB_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && !configured[dev]) {
+    static DeviceOnce once;
+    SB_TRY(once.run([&]() -> int {
         SB_CUDA(cudaFuncSetAttribute(woodbury_loglik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured[dev] = true;
-    }
+        return 0;
+    }));
     if (variant < 0) {
         SB_CUDA(cudaMemsetAsync(fired, 0, sizeof(int), stream));
         woodbury_trigger_kernel<<<B, WT, K * sizeof(double), stream>>>(B, K, m, predvars, phiT, extravar, fired);

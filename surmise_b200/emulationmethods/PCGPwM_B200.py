@@ -20,6 +20,7 @@ Differences from the reference that a user can observe (all documented in DESIGN
   * the full-n factorisation is done once after the three sweeps, batched over PCs, instead of after
     every __fitGP1d call (the intermediate ones are never read by the reference either).
 """
+import itertools
 import warnings
 from pprint import pformat
 
@@ -29,6 +30,7 @@ import scipy.optimize as spo
 from .. import _pca
 
 SIG2_OF_CONST = 0.01        # PCGPwM.py:705 / 719
+_GENERATION = itertools.count(1)   # fit-generation token of a device state (caches downstream key on it)
 _INFEASIBLE = 1e30          # value handed to L-BFGS-B when the factorisation breaks down
 
 
@@ -283,7 +285,7 @@ class _GPFitter:
     def _nll(self, data, hyps, want_grad, s0=SIG2_OF_CONST):
         self.nevals += len(hyps)
         if self._lockstep is not None:
-            val, grad, info = self._lockstep.evaluate(data, np.asarray(hyps), want_grad)
+            val, grad, info = self._lockstep.evaluate(data, np.asarray(hyps), want_grad, s0)
         else:
             val, grad, info = self.ops.gp_nll_grad(data, np.asarray(hyps), self.mean_dev, self.std_dev,
                                                    s0, want_grad)
@@ -300,7 +302,9 @@ class _GPFitter:
         reverse-communication L-BFGS-B entry point is not usable (or inside the threaded rendezvous) the search goes
         through scipy.optimize.minimize instead -- the same iterates either way."""
         if self._lockstep is not None or not _LbfgsbCore.available():
+            self.driver_used = 'scipy.optimize.minimize'
             return self._fit_one_scipy(j, cand, cand_ids, rows)
+        self.driver_used = 'scipy _lbfgsb.setulb, reverse communication'
         steps = self.fit_one_steps(j, cand, cand_ids, rows)
         try:
             data, hyps, want_grad, s0 = next(steps)
@@ -472,6 +476,7 @@ class _GPFitter:
         if mode == 'coroutine' and not _LbfgsbCore.available():
             mode = 'threads'
         if mode == 'coroutine':
+            self.driver_used = 'scipy _lbfgsb.setulb, reverse communication (lock-step generators)'
             fit_fn, run_block = one_steps, self._run_block_coroutines
         else:
             fit_fn, run_block = one, (self._run_block_lockstep if mode else None)
@@ -637,7 +642,8 @@ class _GPFitter:
             fu[fi] = ukeys[key]
         phi = pcti * spc['scale'][:, None]                           # PCGPwM.py:275
         t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
-        return {'theta': self.theta_dev, 'Linv': self._Linv, 'pw': self._pw, 'sig2': self._sig2,
+        return {'generation': next(_GENERATION), 'lbfgsb_driver': getattr(self, 'driver_used', None),
+                'theta': self.theta_dev, 'Linv': self._Linv, 'pw': self._pw, 'sig2': self._sig2,
                 'nug': t(np.array([e['nug'] for e in emulist])), 'hypcov': t(np.array(ulist)),
                 'fu': t(fu, torch.int32), 'fidx': t(self._fidx, torch.int32),
                 'phi': t(phi), 'offset': t(spc['offset']), 'extravar': t(spc['extravar']),
@@ -655,8 +661,8 @@ class _LockstepEvaluator:
         self.live = nthreads
         self.pending = []
 
-    def evaluate(self, data, hyps, want_grad):
-        req = {'data': data, 'hyps': hyps, 'grad': bool(want_grad), 'out': None}
+    def evaluate(self, data, hyps, want_grad, s0=SIG2_OF_CONST):
+        req = {'data': data, 'hyps': hyps, 'grad': bool(want_grad), 's0': float(s0), 'out': None}
         with self.cv:
             self.pending.append(req)
             if len(self.pending) >= self.live:
@@ -676,14 +682,13 @@ class _LockstepEvaluator:
                 self._flush()
 
     def _flush(self):
-        """Caller holds the lock.  One launch per gradient flag over all pending problems."""
+        """Caller holds the lock.  One launch per (gradient flag, sig2ofconst) over all pending problems -- the same
+        grouping as _GPFitter._run_block_coroutines."""
         f, torch = self.f, self.f.torch
         reqs, self.pending = self.pending, []
         try:
-            for flag in (False, True):
-                group = [r for r in reqs if r['grad'] == flag]
-                if not group:
-                    continue
+            for flag, s0 in sorted({(r['grad'], r['s0']) for r in reqs}):
+                group = [r for r in reqs if r['grad'] == flag and r['s0'] == s0]
                 counts = [r['hyps'].shape[0] for r in group]
                 theta = torch.cat([r['data'].theta.expand(c, -1, -1) if r['data'].theta.dim() == 2
                                    else r['data'].theta for r, c in zip(group, counts)], 0)
@@ -691,7 +696,7 @@ class _LockstepEvaluator:
                 gv = torch.cat([r['data'].gvar.expand(c, -1) for r, c in zip(group, counts)], 0)
                 data = f.ops.GPData(theta, g, gv)
                 hyps = np.concatenate([r['hyps'] for r in group], 0)
-                val, grad, info = f.ops.gp_nll_grad(data, hyps, f.mean_dev, f.std_dev, SIG2_OF_CONST, flag)
+                val, grad, info = f.ops.gp_nll_grad(data, hyps, f.mean_dev, f.std_dev, s0, flag)
                 lo = 0
                 for r, c in zip(group, counts):
                     r['out'] = (val[lo:lo + c], None if grad is None else grad[lo:lo + c], info[lo:lo + c])
@@ -763,16 +768,19 @@ def match_rows(x, xfit):
     return pairs[:, 1], pairs[:, 0]
 
 
-def predict_pcspace(fitinfo, theta, return_grad=False, chunk=4096):
-    """Device tensors predvecs, predvars (B,k) [+ gradients (B,k,d)] for theta (B,d) numpy/tensor."""
+def predict_pcspace(fitinfo, theta, return_grad=False, chunk=4096, population=None):
+    """Device tensors predvecs, predvars (B,k) [+ gradients (B,k,d)] for theta (B,d) numpy/tensor.
+
+    population: size of the whole population when theta is one rank's slice of it (see ops.gp_predict)."""
     ops = _ops()
     torch = ops._torch()
     st = fitinfo['_b200']
     tn = ops._f64(torch, np.atleast_2d(theta) if not isinstance(theta, torch.Tensor) else theta)
     B = tn.shape[0]
+    population = B if population is None else population
     if B <= chunk:
-        return ops.gp_predict(st, tn, return_grad)
-    parts = [ops.gp_predict(st, tn[s:s + chunk], return_grad) for s in range(0, B, chunk)]
+        return ops.gp_predict(st, tn, return_grad, population=population)
+    parts = [ops.gp_predict(st, tn[s:s + chunk], return_grad, population=population) for s in range(0, B, chunk)]
     return tuple(None if parts[0][i] is None else torch.cat([p[i] for p in parts], 0) for i in range(4))
 
 

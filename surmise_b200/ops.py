@@ -279,11 +279,14 @@ def gp_weights(Linv, fidx, g, sig2ofconst=0.01):
     return pw, sig2
 
 
-def gp_predict(state, thetanew, want_grad=False, out=None):
+def gp_predict(state, thetanew, want_grad=False, out=None, population=None):
     """PC-space prediction (PCGPwM.py:219-270) from a device state dict (see emulation module).
 
     Returns device tensors predvecs, predvars (B,k) and, if want_grad, gradients (B,k,d).
     out: optional (pv, pvar, dpv, dpvar) to write into (callers that evaluate the same shape repeatedly).
+    population: size of the caller's WHOLE theta population when thetanew is a chunk or a rank's slice of it (default:
+    thetanew itself).  Only a population of one theta with d == 1 takes the reference's single-(1-nug) gradient
+    (PCGPwM.py:236, 262-268), so results do not depend on chunking or on the number of ranks.
     """
     torch = _torch()
     tn = _f64(torch, thetanew)
@@ -301,9 +304,11 @@ def gp_predict(state, thetanew, want_grad=False, out=None):
         dpvar = torch.empty((B, K, d), dtype=torch.float64, device=dev) if want_grad else None
     nbytes = lib.sb200_gp_predict_workspace(K, nf, nu, n, d, B, int(want_grad))
     ws = workspace(nbytes)
+    total = B if population is None else int(population)
+    grad_mode = (2 if (total == 1 and d == 1) else 1) if want_grad else 0
     check(lib.sb200_gp_predict(K, nf, nu, n, d, B, _ptr(state['theta']), _ptr(tn), _ptr(state['hypcov']),
                                _ptr(state['fu']), _ptr(state['fidx']), _ptr(state['nug']), _ptr(state['sig2']),
-                               _ptr(state['Linv']), ldl, n * ldl, _ptr(state['pw']), int(want_grad), _ptr(pv),
+                               _ptr(state['Linv']), ldl, n * ldl, _ptr(state['pw']), grad_mode, _ptr(pv),
                                _ptr(pvar), _ptr(dpv), _ptr(dpvar), _ptr(ws), ws.numel(), _stream(torch)),
           'sb200_gp_predict')
     return pv, pvar, dpv, dpvar

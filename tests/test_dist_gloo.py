@@ -43,6 +43,17 @@ def test_sharded_fit_equals_single_process(two_rank_results):
     assert np.array_equal(r0['inds'], inds) and np.array_equal(r0['rows'], rows)
     assert set(inds.tolist()) <= set(range(len(inds)))
     assert all(inds[j] <= j for j in range(len(inds)))             # hypind = min(j, leader)  (PCGPwM.py:717)
+    # the invariant PCGPwM.predict relies on (rsave[hypind], PCGPwM.py:219-230): a component's hyper-parameters ARE
+    # its hypind's hyper-parameters, also when its leader moved on in the same Jacobi sweep
+    assert all(np.array_equal(hyps[j], hyps[inds[j]]) for j in range(len(inds)))
+
+
+def test_canonical_hypinds():
+    from surmise_b200._dist import canonical_hypinds
+    h = np.array([[1.0, 2.0], [3.0, 4.0], [1.0, 2.0], [3.0, 4.0 + 1e-16], [5.0, 6.0], [3.0, 4.0]])
+    assert canonical_hypinds(h).tolist() == [0, 1, 0, 1, 4, 1]
+    h[3, 1] = np.nextafter(4.0, 5.0)                                # one ulp away is a different leader
+    assert canonical_hypinds(h).tolist() == [0, 1, 0, 3, 4, 1]
 
 
 @pytest.mark.parametrize('B', [1, 2, 7, 64])
