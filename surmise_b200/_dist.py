@@ -47,6 +47,23 @@ class Comm:
         self.dist.all_gather(out, buf)
         return np.concatenate([out[r][:counts[r]].cpu().numpy() for r in range(self.world)], axis=0)
 
+    def allgather_tensor(self, local, counts):
+        """allgather_rows for tensors that stay where they are (device tensors over NCCL, CPU tensors over gloo):
+        rank r contributes local (counts[r], w); returns the (sum(counts), w) concatenation in rank order."""
+        if self.world == 1:
+            return local
+        import torch
+        pad = max(max(counts), 1)
+        buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        if local.shape[0]:
+            buf[:local.shape[0]] = local
+        out = torch.empty((self.world * pad,) + tuple(buf.shape[1:]), dtype=local.dtype, device=local.device)
+        self.dist.all_gather_into_tensor(out, buf)              # concatenated along dim 0 (NCCL and gloo agree on this)
+        out = out.view((self.world, pad) + tuple(buf.shape[1:]))
+        if all(c == pad for c in counts):
+            return out.reshape((-1,) + tuple(local.shape[1:]))
+        return torch.cat([out[r, :counts[r]] for r in range(self.world)], 0)
+
     def broadcast_array(self, arr, src=0):
         """Rank src's int64 array to everyone (used to agree on the random sub-samples)."""
         if self.world == 1:
@@ -63,6 +80,28 @@ def block_partition(count, world):
     sizes = [base + (1 if r < extra else 0) for r in range(world)]
     starts = np.concatenate([[0], np.cumsum(sizes)])
     return sizes, starts
+
+
+def owner_plan(fidx, starts, rank):
+    """PC sharding that follows factor ownership ("factors stay on their owner").
+
+    fidx (k,): distinct-factor index of every component; starts: block_partition boundaries of the factors over the
+    ranks.  Component j lives on the rank that owns factor fidx[j].  Returns
+      owner (k,)      rank of every component,
+      counts          components per rank,
+      order (k,)      component ids in gathered order (rank-major, component order within a rank),
+      inverse (k,)    position of component j in the gathered order (gathered[inverse] is in component order),
+      pcs_local       this rank's components, ascending."""
+    fidx = np.asarray(fidx)
+    world = len(starts) - 1
+    owner = np.searchsorted(np.asarray(starts), fidx, side='right') - 1
+    owner = np.minimum(owner, world - 1)
+    counts = np.bincount(owner, minlength=world).astype(int).tolist()
+    order = np.argsort(owner, kind='stable')
+    inverse = np.empty_like(order)
+    inverse[order] = np.arange(len(order))
+    return {'owner': owner, 'counts': counts, 'order': order, 'inverse': inverse,
+            'pcs_local': np.where(owner == rank)[0]}
 
 
 def gather_blocks(comm, local, sizes, out):

@@ -130,6 +130,13 @@ def _packed(fitinfo, emu, theta, y, x, return_grad, chunk=4096):
         return ll.cpu().numpy().reshape(-1, 1)
     consts = woodbury_constants(fitinfo, emu, x, y)
     st = _device_state(emu)['_b200']
+    if st.get('shard') is not None:
+        # factors live on their owner ranks (PCGPwM_B200 fit option factors='owner'): collective PC-sharded predict,
+        # then every rank evaluates the cheap k-space Woodbury for the whole population ("by PC")
+        ll, dll, _ = loglik_device(fitinfo, emu, theta, y, x, return_grad=return_grad, chunk=chunk)
+        if return_grad:
+            return ops.to_host([torch.cat([ll[:, None], dll], dim=1)])[0]
+        return ops.to_host([ll])[0].reshape(-1, 1)
     K = st['pw'].shape[0]
     buf = _buffers(torch, consts['phiT'].device, B, d, K, return_grad)
     buf['theta_h'].numpy()[...] = theta
@@ -151,7 +158,7 @@ def _evaluate(fitinfo, emu, theta, y, x, return_grad):
     evaluates its slice, the batch-wide unmodelled-variance flag (dbw.py:277-284) is OR-reduced so that it is
     still decided over the whole population, and the (B, 1+d) table is all-gathered (NCCL).
     """
-    if fitinfo.get('shard_theta'):
+    if fitinfo.get('shard_theta') and _device_state(emu)['_b200'].get('shard') is None:
         from .. import _dist
         comm = _dist.Comm()
         if comm.world > 1:

@@ -44,7 +44,7 @@ def _ops():
 # ------------------------------------------------------------------------------------------------
 def fit(fitinfo, x, theta, f, epsilonPC=0.001, epsilonImpute=10e-6, lognugmean=-10, lognugLB=-20,
         varconstant=None, dampalpha=0.3, eta=10, standardpcinfo=None, verbose=0, nhyptrain=None,
-        fit_mode='reference', pca='device', distributed=True, merge_leaders=False, **kwargs):
+        fit_mode='reference', pca='device', distributed=True, merge_leaders=False, factors='owner', **kwargs):
     """Same arguments as PCGPwM.fit (PCGPwM.py:12-137) plus
     nhyptrain : None (reference rule min(20 d, n), PCGPwM.py:744), an int, or 'all'.
     fit_mode  : 'reference' -- the reference's sequential Gauss-Seidel sweeps (PCGPwM.py:691-721), one GPU;
@@ -57,12 +57,18 @@ def fit(fitinfo, x, theta, f, epsilonPC=0.001, epsilonImpute=10e-6, lognugmean=-
                 after the sweeps so that components adopt an earlier leader's hyper-parameters where that costs
                 little likelihood: fewer full-data factors (C2: 20 -> 9), faster prediction / calibration, slightly
                 larger hold-out error (0.065 -> 0.075 sd at C2).  Default False.
+    factors   : with fit_mode='parallel' on more than one rank: 'owner' (default) -- every full-data factor Linv stays
+                on the rank that computed it; predict then runs PC-sharded (each rank produces
+                predvecs / predvars of the components whose factor it owns, one all-gather of B x k x (2+2d) doubles)
+                and must be called by every rank with the same theta.  'replicated' -- owners broadcast their
+                factors so that every rank holds all of them (needed for theta-sharded calibration, shard_theta).
     pca       : 'device' (default) -- standardisation / imputation / PCA on the GPU (_pca_device.py: Gram-matrix
                 eigendecomposition and batched ridge solves); 'host' -- the numpy implementation (_pca.py), which
                 takes the SVD exactly as the reference does.
     """
     ops = _ops()
     ops._torch()                                   # fail loudly without CUDA before any work
+    clock = _PhaseClock(ops._torch())
     f = np.asarray(f, dtype=np.float64).T          # (n, m)
     theta = np.asarray(theta, dtype=np.float64)
     fitinfo['epsilonImpute'] = epsilonImpute
@@ -75,6 +81,8 @@ def fit(fitinfo, x, theta, f, epsilonPC=0.001, epsilonImpute=10e-6, lognugmean=-
 
     if pca not in ('device', 'host'):
         raise ValueError("pca must be 'device' or 'host'")
+    if factors not in ('owner', 'replicated'):
+        raise ValueError("factors must be 'owner' or 'replicated'")
     if standardpcinfo is None and pca == 'device':
         from .. import _pca_device
         spc, mof, mofrows = _pca_device.standardize(f, epsilonPC, epsilonImpute)
@@ -93,6 +101,7 @@ def fit(fitinfo, x, theta, f, epsilonPC=0.001, epsilonImpute=10e-6, lognugmean=-
         fitinfo.update(_pca.principal_components(spc['fs'], U, S, mof, mofrows, epsilonPC, epsilonImpute))
     fitinfo['mof'], fitinfo['mofrows'] = mof, mofrows
     fitinfo['standardpcinfo'] = spc
+    clock.lap('pca')
     numpcs = fitinfo['pc'].shape[1]
     if verbose > 0:
         print(fitinfo.get('method', 'PCGPwM_B200'), 'considering ', numpcs, 'PCs')
@@ -101,6 +110,9 @@ def fit(fitinfo, x, theta, f, epsilonPC=0.001, epsilonImpute=10e-6, lognugmean=-
     fitter = _GPFitter(fitinfo, theta, lognugmean, lognugLB, logvarc, nhyptrain)
     fitter.distributed = bool(distributed)
     fitter.merge_leaders = bool(merge_leaders)
+    fitter.factors = factors
+    fitter.clock = clock
+    clock.lap('setup')
     if fit_mode not in ('reference', 'parallel'):
         raise ValueError("fit_mode must be 'reference' or 'parallel'")
     emulist = (fitter.run if fit_mode == 'reference' else fitter.run_parallel)(previous=fitinfo.get('emulist'))
@@ -110,7 +122,32 @@ def fit(fitinfo, x, theta, f, epsilonPC=0.001, epsilonImpute=10e-6, lognugmean=-
     fitinfo['emulist'] = emulist
     fitinfo['_b200'] = fitter.device_state(emulist, spc, fitinfo['pcti'])
     fitinfo['param_desc'] = _param_desc(fitinfo)
+    clock.lap('state')
+    fitinfo['_b200']['timing'] = clock.report()
     return
+
+
+class _PhaseClock:
+    """Wall-clock seconds per phase of a fit (device synchronised at every lap), kept in fitinfo['_b200']['timing']:
+    'pca' (standardise / impute / PCA), 'setup', 'search' (the sweeps), 'factor' (full-data factorisations),
+    'exchange' (collectives after the factorisations), 'weights', 'state'."""
+
+    def __init__(self, torch):
+        import time
+        self._now, self._torch = time.perf_counter, torch
+        self.t0 = self.last = self._now()
+        self.phases = {}
+
+    def lap(self, name):
+        self._torch.cuda.synchronize()
+        t = self._now()
+        self.phases[name] = self.phases.get(name, 0.0) + (t - self.last)
+        self.last = t
+
+    def report(self):
+        out = dict(self.phases)
+        out['total'] = self._now() - self.t0
+        return out
 
 
 class _LbfgsbCore:
@@ -453,6 +490,8 @@ class _GPFitter:
                 starts[j] = hyp
                 hypinds[j] = j if hi < -0.5 else hi
                 hyps[j], rows_used[j] = hyp, rows
+        if getattr(self, 'clock', None) is not None:
+            self.clock.lap('search')
         return self._finalise(np.array(hyps), hypinds.astype(int), rows_used)
 
     def run_parallel(self, previous=None):
@@ -485,6 +524,8 @@ class _GPFitter:
                                                        run_block=run_block)
         if self.merge_leaders:
             hyps, hypinds = self._merge_leaders(hyps, hypinds, rows_used)
+        if getattr(self, 'clock', None) is not None:
+            self.clock.lap('search')
         self._comm = comm                                     # the distinct factors are sharded over the ranks as well
         try:
             return self._finalise(hyps, hypinds, rows_used)
@@ -571,23 +612,51 @@ class _GPFitter:
             fidx[j] = keys[key]
         members = np.array(members)
         comm = getattr(self, '_comm', None)
+        clock = getattr(self, 'clock', None)
+        lap = clock.lap if clock is not None else (lambda name: None)
+        dev = self.theta_dev.device
+        self._shard = None
         if comm is not None and comm.world > 1 and len(members) > 1:
-            # each rank factors a contiguous block of the distinct problems; owners broadcast their factors
+            # each rank factors a contiguous block of the distinct problems
             from .. import _dist
             sizes, starts = _dist.block_partition(len(members), comm.world)
             lo, hi = int(starts[comm.rank]), int(starts[comm.rank + 1])
             ldl = (self.n + 7) // 8 * 8
-            Linv = torch.empty((len(members), self.n, ldl), dtype=torch.float64, device=self.theta_dev.device)
-            local, flags = (None, np.zeros(0, dtype=bool))
+            local, flags = (torch.empty((0, self.n, ldl), dtype=torch.float64, device=dev), np.zeros(0, dtype=bool))
             if hi > lo:
                 local, flags = self._factor_batch(members[lo:hi], hyps)
-            _dist.gather_blocks(comm, local, sizes, Linv)
+            lap('factor')
             clamped_f = comm.allgather_rows(flags.astype(np.float64).reshape(-1, 1), sizes).reshape(-1) > 0.5
+            if getattr(self, 'factors', 'owner') == 'owner':
+                # factors stay with their owner: the owner also produces pw / sig2 of the components that
+                # use its factors; only those (k, n+1) doubles travel
+                plan = _dist.owner_plan(fidx, starts, comm.rank)
+                mine = plan['pcs_local']
+                pw_l = torch.empty((len(mine), self.n), dtype=torch.float64, device=dev)
+                s2_l = torch.empty(len(mine), dtype=torch.float64, device=dev)
+                if len(mine):
+                    idx = torch.from_numpy(mine).to(dev)
+                    fl = torch.from_numpy((fidx[mine] - lo).astype(np.int32)).to(dev)
+                    pw_l, s2_l = ops.gp_weights(local, fl, self.pc_dev[idx].contiguous(), SIG2_OF_CONST)
+                lap('weights')
+                table = comm.allgather_tensor(torch.cat([pw_l, s2_l[:, None]], 1), plan['counts'])
+                table = table[torch.from_numpy(plan['inverse']).to(dev)]                 # gathered order -> PC order
+                pw, sig2 = table[:, :self.n].contiguous(), table[:, self.n].contiguous()
+                Linv = local
+                self._shard = dict(plan, world=comm.world, rank=comm.rank, lo=lo, hi=hi)
+                lap('exchange')
+            else:
+                Linv = torch.empty((len(members), self.n, ldl), dtype=torch.float64, device=dev)
+                _dist.gather_blocks(comm, local if hi > lo else None, sizes, Linv)
+                lap('exchange')
         else:
             Linv, clamped_f = self._factor_batch(members, hyps)
-        # pw and sig2 depend on the scores g_j, which differ between PCs sharing a factor
-        fidx_dev = torch.from_numpy(fidx).to(self.theta_dev.device)
-        pw, sig2 = ops.gp_weights(Linv, fidx_dev, self.pc_dev, SIG2_OF_CONST)
+            lap('factor')
+        if self._shard is None:
+            # pw and sig2 depend on the scores g_j, which differ between PCs sharing a factor
+            fidx_dev = torch.from_numpy(fidx).to(dev)
+            pw, sig2 = ops.gp_weights(Linv, fidx_dev, self.pc_dev, SIG2_OF_CONST)
+            lap('weights')
         nug = np.exp(hyps[:, -1]) / (1 + np.exp(hyps[:, -1]))        # PCGPwM.py:813
         pw_h, sig2_h = pw.cpu().numpy(), sig2.cpu().numpy()
         emulist = []
@@ -629,25 +698,44 @@ class _GPFitter:
         """Everything predict needs, as device tensors (kept in fitinfo['_b200'])."""
         torch = self.torch
         dev = self.theta_dev.device
-        k = len(emulist)
         hypcov = np.array([e['hypcov'] for e in emulist])
-        # distinct covariance hyper-parameter sets (cross-covariances are shared between factors)
-        ukeys, fu = {}, np.zeros(len(self._members), dtype=np.int32)
-        ulist = []
-        for fi, j in enumerate(self._members):
-            key = hypcov[j].tobytes()
-            if key not in ukeys:
-                ukeys[key] = len(ulist)
-                ulist.append(hypcov[j])
-            fu[fi] = ukeys[key]
+
+        def cov_sets(members):
+            """distinct covariance hyper-parameter sets among these factors (cross-covariances are shared between factors)"""
+            ukeys, fu, ulist = {}, np.zeros(len(members), dtype=np.int32), []
+            for fi, j in enumerate(members):
+                key = hypcov[j].tobytes()
+                if key not in ukeys:
+                    ukeys[key] = len(ulist)
+                    ulist.append(hypcov[j])
+                fu[fi] = ukeys[key]
+            return np.array(ulist).reshape(len(ulist), hypcov.shape[1]), fu
         phi = pcti * spc['scale'][:, None]                           # PCGPwM.py:275
         t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
-        return {'generation': next(_GENERATION), 'lbfgsb_driver': getattr(self, 'driver_used', None),
-                'theta': self.theta_dev, 'Linv': self._Linv, 'pw': self._pw, 'sig2': self._sig2,
-                'nug': t(np.array([e['nug'] for e in emulist])), 'hypcov': t(np.array(ulist)),
-                'fu': t(fu, torch.int32), 'fidx': t(self._fidx, torch.int32),
-                'phi': t(phi), 'offset': t(spc['offset']), 'extravar': t(spc['extravar']),
-                'nevals': self.nevals}
+        nug = t(np.array([e['nug'] for e in emulist]))
+        state = {'generation': next(_GENERATION), 'lbfgsb_driver': getattr(self, 'driver_used', None),
+                 'theta': self.theta_dev, 'pw': self._pw, 'sig2': self._sig2, 'nug': nug,
+                 'phi': t(phi), 'offset': t(spc['offset']), 'extravar': t(spc['extravar']),
+                 'nevals': self.nevals, 'nf_total': int(len(self._members))}
+        sh = getattr(self, '_shard', None)
+        if sh is None:
+            ulist, fu = cov_sets(self._members)
+            state.update({'Linv': self._Linv, 'hypcov': t(ulist), 'fu': t(fu, torch.int32),
+                          'fidx': t(self._fidx, torch.int32)})
+            return state
+        # factors stay with their owner: this rank predicts the components whose factor it holds ('local'), the
+        # others arrive by all-gather (predict_pcspace); 'pw' / 'sig2' / 'nug' above cover all components
+        lo, hi, pcs = sh['lo'], sh['hi'], sh['pcs_local']
+        ulist, fu = cov_sets(self._members[lo:hi])
+        sel = torch.from_numpy(pcs).to(dev)
+        state['Linv'] = self._Linv                                   # (hi - lo, n, ldl): the factors this rank owns
+        state['local'] = {'theta': self.theta_dev, 'Linv': self._Linv, 'pw': self._pw[sel].contiguous(),
+                          'sig2': self._sig2[sel].contiguous(), 'nug': nug[sel].contiguous(), 'hypcov': t(ulist),
+                          'fu': t(fu, torch.int32), 'fidx': t((self._fidx[pcs] - lo).astype(np.int32), torch.int32)}
+        state['shard'] = {'world': sh['world'], 'rank': sh['rank'], 'counts': list(sh['counts']),
+                          'inverse': torch.from_numpy(sh['inverse'].astype(np.int64)).to(dev),
+                          'pcs_local': pcs, 'owner': sh['owner']}
+        return state
 
 
 class _LockstepEvaluator:
@@ -778,10 +866,45 @@ def predict_pcspace(fitinfo, theta, return_grad=False, chunk=4096, population=No
     tn = ops._f64(torch, np.atleast_2d(theta) if not isinstance(theta, torch.Tensor) else theta)
     B = tn.shape[0]
     population = B if population is None else population
+    if st.get('shard') is not None:
+        return _predict_pcspace_sharded(st, tn, return_grad, chunk, population)
     if B <= chunk:
         return ops.gp_predict(st, tn, return_grad, population=population)
     parts = [ops.gp_predict(st, tn[s:s + chunk], return_grad, population=population) for s in range(0, B, chunk)]
     return tuple(None if parts[0][i] is None else torch.cat([p[i] for p in parts], 0) for i in range(4))
+
+
+def _predict_pcspace_sharded(st, tn, return_grad, chunk, population):
+    """PC-sharded prediction for a fit whose factors stayed with their owners (fit option factors='owner').
+
+    COLLECTIVE: every rank of the fit's process group calls with the same theta.  Each rank evaluates the components
+    whose factor it owns; one all-gather of B x k x (2 + 2d) doubles gives every rank the full tables."""
+    from .. import _dist
+    ops = _ops()
+    torch = ops._torch()
+    sh, loc = st['shard'], st['local']
+    comm = _dist.Comm()
+    if comm.world != sh['world'] or comm.rank != sh['rank']:
+        raise RuntimeError('this emulator was fitted with its factors sharded over %d ranks (this is rank %d of it); '
+                           'predict must run in the same torch.distributed group (or refit with factors="replicated")'
+                           % (sh['world'], sh['rank']))
+    B, d = tn.shape
+    kl = int(loc['pw'].shape[0])
+    Q = 2 + (2 * d if return_grad else 0)
+    packed = torch.empty((kl, B, Q), dtype=torch.float64, device=tn.device)
+    if kl:
+        for s0 in range(0, B, chunk):
+            pv, pvar, dpv, dpvar = ops.gp_predict(loc, tn[s0:s0 + chunk], return_grad, population=population)
+            blk = packed[:, s0:s0 + chunk]
+            blk[:, :, 0], blk[:, :, 1] = pv.T, pvar.T
+            if return_grad:
+                blk[:, :, 2:2 + d] = dpv.permute(1, 0, 2)
+                blk[:, :, 2 + d:] = dpvar.permute(1, 0, 2)
+    full = comm.allgather_tensor(packed, sh['counts'])[st['shard']['inverse']]          # (k, B, Q), component order
+    pv, pvar = full[:, :, 0].T.contiguous(), full[:, :, 1].T.contiguous()
+    if not return_grad:
+        return pv, pvar, None, None
+    return pv, pvar, full[:, :, 2:2 + d].permute(1, 0, 2).contiguous(), full[:, :, 2 + d:].permute(1, 0, 2).contiguous()
 
 
 def predict(predinfo, fitinfo, x, theta, **kwargs):

@@ -93,8 +93,14 @@ def worker(rank, world, port, outdir):
         full = torch.arange(5 * 12, dtype=torch.float64).reshape(5, 3, 4)
         blocks = _dist.gather_blocks(comm, full[lo:hi].clone() if hi > lo else None, sizes,
                                      torch.full((5, 3, 4), -1.0, dtype=torch.float64)).numpy()
+        # owner layout: components follow the rank that owns their factor; every rank contributes rows for its own
+        # components (here the component id repeated) and the gathered table, re-ordered, must be in component order
+        fidx = np.array([0, 1, 0, 2, 3, 1, 4, 4, 2, 0, 3])
+        plan = _dist.owner_plan(fidx, starts, rank)
+        mine = torch.from_numpy(plan['pcs_local'].astype(np.float64))[:, None].repeat(1, 3)
+        owner_table = comm.allgather_tensor(mine, plan['counts'])[torch.from_numpy(plan['inverse'])].numpy()
         np.savez(os.path.join(outdir, 'rank%d.npz' % rank), hyps=hyps, inds=inds, rows=rows, ragged=ragged,
-                 blocks=blocks,
+                 blocks=blocks, owner_table=owner_table,
                  **{'got%d' % B: v[0] for B, v in shard.items()}, **{'want%d' % B: v[1] for B, v in shard.items()})
     finally:
         dist.destroy_process_group()

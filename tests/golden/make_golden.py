@@ -196,7 +196,16 @@ def golden_standardize():
           'pcstdvar', rel(fo['unscaled_pcstdvar'], fi['unscaled_pcstdvar']))
 
 
+def golden_d8():
+    """A C2-like case (d = 8): cond(R) ~ 1e5-1e6, the conditioning SURVEY measured at C2 -- here BASELINE.json's 1e-9 bar on
+    the per-theta log-likelihood must hold end to end (tests/test_gpu_path.py)."""
+    golden_emulator('d8', n=300, d=8, m=40, k=10, seed=21, missing=0.0, nB=16)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'd8':      # PYTHONPATH=baseline/_ref python tests/golden/make_golden.py d8
+        golden_d8()
+        sys.exit(0)
     golden_covmat()
     golden_nll()
     golden_standardize()
@@ -210,3 +219,4 @@ if __name__ == '__main__':
     golden_emulator('trig', n=100, d=2, m=24, k=6, seed=9, missing=0.0, nB=12,
                     fit_args={'epsilonPC': 0.5}, yvar_scale=1.0)
     golden_emulator('d1', n=60, d=1, m=21, k=3, seed=13, missing=0.0, nB=10)
+    golden_d8()

@@ -74,3 +74,25 @@ def test_gather_blocks_assembles_owner_slices(two_rank_results):
     want = np.arange(5 * 12, dtype=np.float64).reshape(5, 3, 4)
     for r in two_rank_results:
         assert np.array_equal(r['blocks'], want)
+
+
+def test_owner_layout_gathers_in_component_order(two_rank_results):
+    """_dist.owner_plan + Comm.allgather_tensor (factors stay with their owner; results travel): rank-major gathered rows,
+    re-ordered by plan['inverse'], come out in component order on every rank."""
+    want = np.arange(11, dtype=np.float64)[:, None].repeat(3, 1)
+    for r in two_rank_results:
+        assert np.array_equal(r['owner_table'], want)
+
+
+def test_owner_plan_partitions_components():
+    from surmise_b200._dist import owner_plan, block_partition
+    fidx = np.array([0, 1, 0, 2, 3, 1, 4, 4, 2])
+    sizes, starts = block_partition(5, 3)
+    plans = [owner_plan(fidx, starts, r) for r in range(3)]
+    assert sorted(np.concatenate([p['pcs_local'] for p in plans]).tolist()) == list(range(9))
+    assert plans[0]['counts'] == [4, 3, 2]
+    for r, p in enumerate(plans):                      # a component lives where its factor lives
+        assert all(starts[r] <= fidx[j] < starts[r + 1] for j in p['pcs_local'])
+    sizes, starts = block_partition(2, 4)              # more ranks than factors: the late ranks own nothing
+    p = owner_plan(np.array([0, 1, 1, 0]), starts, 3)
+    assert p['counts'] == [2, 2, 0, 0] and p['pcs_local'].size == 0

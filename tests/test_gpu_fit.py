@@ -248,7 +248,8 @@ def test_device_pca_matches_host_pca(golden):
     e_ev = float(np.max(np.abs(spc_d['extravar'] - g['extravar'])) / np.max(g['extravar']))
     e_sv = float(np.max(np.abs(pcs_d['unscaled_pcstdvar'] - g['unscaled_pcstdvar'])))
     report('device_pca_missing', fs=e_fs, pc=e_pc, extravar=e_ev, pcstdvar=e_sv)
-    assert e_fs < 1e-3 and e_pc < 1e-3 and e_ev < 1e-3 and e_sv < 1e-2
+    # 5 x the discrepancies measured on a B200 (profiles/parity_report_r1.txt: 9.8e-6, 8.2e-7, 3.2e-5, 1.8e-4)
+    assert e_fs < 5e-5 and e_pc < 5e-6 and e_ev < 2e-4 and e_sv < 1e-3
     c = golden('emu_c1')
     spc_c, mof, rows = _pca_device.standardize(c['in_f'].T, 0.001, 10e-6)
     assert mof is None
@@ -258,7 +259,7 @@ def test_device_pca_matches_host_pca(golden):
     e_ti = float(np.max(np.abs(pcs_c['pcti'] * sign - c['st_pcti'])) / np.max(np.abs(c['st_pcti'])))
     e_ev = float(np.max(np.abs(spc_c['extravar'] - c['st_extravar'])) / np.max(c['st_extravar']))
     report('device_pca_complete', pc=e_pc, pcti=e_ti, extravar=e_ev)
-    assert e_pc < 1e-9 and e_ti < 1e-9 and e_ev < 1e-6
+    assert e_pc < 1e-13 and e_ti < 3e-12 and e_ev < 3e-11        # measured 1.3e-15, 4.2e-13, 5.7e-12
 
 
 def test_fit_host_pca_option_agrees_with_device_pca():
@@ -272,6 +273,7 @@ def test_fit_host_pca_option_agrees_with_device_pca():
         p = {}
         M.predict(p, fi, x, tn)
         means.append(p['mean'])
+    report('fit_host_vs_device_pca', mean=rel(means[0], means[1]))
     assert rel(means[0], means[1]) < 1e-2
     with pytest.raises(ValueError):
         _facade_fit(M, x, theta, f, pca='nowhere')

@@ -61,12 +61,17 @@ def test_nll_grad_golden(ops, golden, tag):
     nll0, _, info0 = ops.gp_nll_grad(data, hyps, g[f'{tag}_mean'], g[f'{tag}_std'], 0.01, False)
     assert np.all(info == 0) and np.all(info0 == 0)
     assert np.array_equal(nll, nll0)                       # value-only path is the same arithmetic
+    # The distance to the reference's stored values must be explained by the reference's OWN distance from the exact
+    # value (40-digit evaluation, tests/golden/arbiter.npz; its eigh-based inverse loses cond * eps), times 5, above a
+    # floor of 1e-11 / 1e-10 -- never by a function of cond(R).  The bar itself (1e-9 against the exact value) is
+    # asserted in test_gpu_arbiter.py.
+    arb = golden('arbiter')
     for i in range(hyps.shape[0]):
-        tol = max(1e-9, 20 * EPS * g[f'{tag}_cond'][i])
         e_v = abs(nll[i] - g[f'{tag}_nll'][i]) / (abs(g[f'{tag}_nll'][i]) + n)
         e_g = rel(grad[i], g[f'{tag}_grad'][i])
         report('nll_golden_' + tag, i=i, nll=e_v, grad=e_g, cond=g[f'{tag}_cond'][i])
-        assert e_v < tol and e_g < 10 * tol
+        assert e_v < max(1e-11, 5 * arb[f'nll_{tag}_ref_err'][i]), (tag, i, e_v)
+        assert e_g < max(1e-10, 5 * arb[f'nllgrad_{tag}_ref_err'][i]), (tag, i, e_g)
 
 
 @pytest.mark.parametrize('n,d,nb', [(160, 8, 7), (200, 10, 3), (61, 3, 4), (700, 8, 2)])
@@ -85,10 +90,9 @@ def test_nll_grad_vs_oracle_batched(ops, n, d, nb):
         v = po.negloglik_eigh(hyps[i], info)
         dv = po.negloglikgrad_eigh(hyps[i], info)
         cond = np.linalg.cond(po.assemble_gp_matrix(theta, hyps[i], gvar)[0])
-        tol = max(1e-9, 20 * EPS * cond)
         e_v, e_g = abs(nll[i] - v) / (abs(v) + n), rel(grad[i], dv)
         report('nll_oracle', n=n, d=d, i=i, nll=e_v, grad=e_g, cond=cond)
-        assert e_v < tol and e_g < 10 * tol
+        assert e_v < 1e-9 and e_g < 1e-9                    # the north-star bar (measured: <= 3e-12 / 4e-11)
 
 
 @pytest.mark.parametrize('n,d', [(30, 2), (63, 3), (64, 5), (160, 8), (200, 10), (207, 16)])
@@ -148,12 +152,34 @@ def _load_state(golden_npz):
     return M, fitinfo
 
 
-@pytest.mark.parametrize('tag', ['c1', 'misspd', 'trig', 'd1'])
+# Discrepancy against the REFERENCE's stored outputs, measured on a B200 (profiles/parity_report_r1.txt), per fixture
+# and quantity.  The asserted bound is 5 x these (a regression of one digit fails), not a function of cond(R).  They are
+# dominated by the reference's own eigh-based inverse: tests/golden/arbiter.npz (40-digit evaluation of the same
+# formulas) puts the reference itself at exactly these distances from the exact values -- see test_gpu_arbiter.py.
+# 'd8' (cond 9e4, the conditioning of config C2) carries BASELINE.json's bars themselves: 1e-9 on the log-likelihood.
+MEASURED_VS_REFERENCE = {
+    'c1': dict(pw=1.93e-8, sig2=8.2e-12, predvecs=6.4e-10, predvars=2.7e-9, dpv=9.4e-11, dpvar=3.1e-10, mean=4.1e-10,
+               var=1.5e-10, dmean=7.0e-11, cxh=2.5e-10, dcxh=6.7e-10, ll=3.2e-9, dll=7.8e-10),
+    'misspd': dict(pw=9.4e-10, sig2=2.3e-12, predvecs=5.3e-10, predvars=5.0e-10, dpv=3.2e-11, dpvar=6.6e-10,
+                   mean=2.6e-10, var=2.4e-10, dmean=3.3e-11, cxh=7.3e-11, dcxh=7.7e-10, ll=3.1e-9, dll=6.7e-10),
+    'trig': dict(pw=6.7e-8, sig2=9.9e-11, predvecs=3.8e-9, predvars=5.1e-8, dpv=1.3e-9, dpvar=2.7e-9, mean=3.0e-9,
+                 var=8.5e-11, dmean=1.1e-9, cxh=1.8e-9, dcxh=6.8e-9, ll=3.4e-8, dll=3.1e-9),
+    'd1': dict(pw=6.3e-6, sig2=2.5e-8, predvecs=3.4e-7, predvars=2.5e-6, dpv=4.2e-9, dpvar=1.7e-7, mean=1.7e-7,
+               var=2.7e-7, dmean=3.8e-9, cxh=2.3e-7, dcxh=9.6e-7, ll=3.0e-6, dll=2.7e-7),
+}
+BARS_D8 = dict(pw=2e-10, sig2=2e-10, predvecs=2e-10, predvars=2e-10, dpv=2e-10, dpvar=2e-10, mean=2e-10, var=2e-10,
+               dmean=2e-10, cxh=2e-10, dcxh=2e-10, ll=2e-10, dll=2e-10)      # asserted at 5 x = 1e-9, the north-star bar
+
+
+def _bound(tag, key):
+    return 5 * (BARS_D8 if tag == 'd8' else MEASURED_VS_REFERENCE[tag])[key]
+
+
+@pytest.mark.parametrize('tag', ['c1', 'misspd', 'trig', 'd1', 'd8'])
 def test_factorise_and_predict_golden(ops, golden, tag):
     g = golden('emu_' + tag)
     M, fitinfo = _load_state(g)
     cond = float(g['st_condR'].max())
-    tol = max(1e-9, 100 * EPS * cond)
     pw = np.array([e['pw'] for e in fitinfo['emulist']]).T
     sig2 = np.array([e['sig2'] for e in fitinfo['emulist']])
     e_pw, e_s2 = rel(pw, g['st_pw']), rel(sig2, g['st_sig2'])
@@ -168,12 +194,10 @@ def test_factorise_and_predict_golden(ops, golden, tag):
                 cxh=rel(pred['covxhalf'][:, :2, :], g['covxhalf_sample']),
                 dcxh=rel(pred['covxhalf_gradtheta'][:, :2, :, :], g['covxhalf_grad_sample']))
     report('predict_golden_' + tag, cond=cond, **errs)
-    assert errs['sig2'] < tol and errs['pw'] < 100 * tol
-    # BASELINE bar: fitted predictive mean / variance within 1e-6 relative
-    assert errs['mean'] < max(1e-6, tol) and errs['var'] < max(1e-6, 10 * tol)
-    assert errs['predvecs'] < 10 * tol and errs['predvars'] < 100 * tol
-    assert errs['dpv'] < 100 * tol and errs['dpvar'] < 100 * tol and errs['dmean'] < 100 * tol
-    assert errs['cxh'] < 100 * tol and errs['dcxh'] < 100 * tol
+    for key, err in errs.items():
+        assert err < _bound(tag, key), (tag, key, err, _bound(tag, key))
+    # BASELINE bar: fitted predictive mean / variance within 1e-6 relative -- on every fixture
+    assert errs['mean'] < 1e-6 and errs['var'] < 1e-6
     assert pred['mean'].shape == g['mean'].shape and pred['covxhalf'].shape[2] == g['st_hyp'].shape[0]
     # no-gradient call gives the same mean/variance
     pred2 = {}
@@ -182,9 +206,10 @@ def test_factorise_and_predict_golden(ops, golden, tag):
     # at the design points the variance is a cancellation: looser, reported
     pd = {}
     M.predict(pd, fitinfo, g['in_x'], g['st_theta'][:8])
-    report('predict_design_' + tag, predvecs=rel(pd['predvecs'], g['design_predvecs']),
+    e_dp = rel(pd['predvecs'], g['design_predvecs'])
+    report('predict_design_' + tag, predvecs=e_dp,
            predvars_abs=float(np.max(np.abs(pd['predvars'] - g['design_predvars']))))
-    assert rel(pd['predvecs'], g['design_predvecs']) < max(1e-6, 100 * tol)
+    assert e_dp < 5 * {'c1': 1.3e-9, 'misspd': 5.9e-10, 'trig': 2.9e-9, 'd1': 2.9e-7, 'd8': 2e-10}[tag]
 
 
 def test_predict_row_subset_and_edge_shapes(ops, golden):
@@ -212,7 +237,7 @@ class _Emu:
         self.method, self._info = method, fitinfo
 
 
-@pytest.mark.parametrize('tag', ['c1', 'misspd', 'trig', 'd1'])
+@pytest.mark.parametrize('tag', ['c1', 'misspd', 'trig', 'd1', 'd8'])
 def test_woodbury_loglik_golden(ops, golden, tag):
     from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
     g = golden('emu_' + tag)
@@ -223,14 +248,13 @@ def test_woodbury_loglik_golden(ops, golden, tag):
     ll2, dll = C.loglik_grad(cal, emu, g['thetanew'], g['y'], g['in_x'])
     _, _, fired = C.loglik_device(cal, emu, g['thetanew'], g['y'], g['in_x'])
     cond = float(g['st_condR'].max())
-    tol = max(1e-9, 100 * EPS * cond)
     e_l = float(np.max(np.abs(ll - g['loglik']) / np.abs(g['loglik'])))
     e_d = rel(dll, g['dloglik'])
     report('loglik_golden_' + tag, ll=e_l, dll=e_d, fired=int(fired.cpu()[0]), cond=cond)
     assert bool(int(fired.cpu()[0])) == bool(g['fired'])
     assert ll.shape == g['loglik'].shape and dll.shape == g['dloglik'].shape
     assert np.allclose(ll, ll2, rtol=1e-12, atol=0)
-    assert e_l < 10 * tol and e_d < 100 * tol
+    assert e_l < _bound(tag, 'll') and e_d < _bound(tag, 'dll'), (tag, e_l, e_d)
 
 
 @pytest.mark.parametrize('tag', ['c1', 'misspd'])
@@ -248,10 +272,9 @@ def test_calibration_adopts_reference_fitted_emulator(ops, golden, tag):
     emu = _Emu(M, fitinfo)
     ll, dll = C.loglik_grad({'yvar': g['yvar']}, emu, g['thetanew'], g['y'], g['in_x'])
     assert '_b200' in fitinfo
-    tol = max(1e-9, 100 * EPS * float(g['st_condR'].max()))
     e_l = float(np.max(np.abs(ll - g['loglik']) / np.abs(g['loglik'])))
     report('loglik_adopted_' + tag, ll=e_l, dll=rel(dll, g['dloglik']))
-    assert e_l < 10 * tol and rel(dll, g['dloglik']) < 100 * tol
+    assert e_l < _bound(tag, 'll') and rel(dll, g['dloglik']) < _bound(tag, 'dll')
     pred = {}
     M.predict(pred, fitinfo, g['in_x'], g['thetanew'])
     assert rel(pred['mean'], g['mean']) < 1e-6 and rel(pred['var'], g['var']) < 1e-6

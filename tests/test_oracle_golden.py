@@ -111,3 +111,21 @@ def test_seeded_fit_reproduces_reference_hyperparameters(golden):
     po.fit(fi, g['in_x'], g['in_theta'], g['in_f'])
     assert rel(np.array([e['hyp'] for e in fi['emulist']]), g['st_hyp']) < 1e-8
     assert [int(e['hypind']) for e in fi['emulist']] == [int(v) for v in g['st_hypind']]
+
+
+@pytest.mark.parametrize('tag', ['c1', 'misspd', 'trig', 'd1', 'd8'])
+def test_arbiter_fixture_is_consistent_with_the_goldens(golden, tag):
+    """tests/golden/arbiter.npz (40-digit evaluation of the reference's formulas, make_golden_arbiter.py): the stored
+    reference-vs-exact errors are what the goldens give, both Cholesky-form and reference stay within cond * eps of
+    the exact values, and the batch-wide variance flag agrees."""
+    g, a = golden('emu_' + tag), golden('arbiter')
+    cond = float(g['st_condR'].max())
+    e_ll = float(np.max(np.abs(g['loglik'] - a[tag + '_loglik']) / np.abs(a[tag + '_loglik'])))
+    assert abs(e_ll - float(a[tag + '_ref_err_loglik'])) <= 1e-3 * e_ll + 1e-18
+    assert bool(a[tag + '_fired']) == bool(g['fired'])
+    assert e_ll < 20 * 2.2e-16 * cond
+    states = [po.factor_state_chol(g['st_theta'], g['st_pc'][:, j], po.damp_gvar(g['st_unscaled_pcstdvar'][:, j], 10, 0.3),
+                                   g['st_hyp'][j]) for j in range(g['st_hyp'].shape[0])]
+    pv, pvar = po.predict_pcspace_chol(g['st_theta'], states, g['st_hypind'], g['thetanew'])[:2]
+    assert np.max(np.abs(pv - a[tag + '_predvecs'])) / np.max(np.abs(a[tag + '_predvecs'])) < 20 * 2.2e-16 * cond
+    assert np.max(np.abs(pvar - a[tag + '_predvars']) / a[tag + '_predvars']) < 50 * 2.2e-16 * cond
