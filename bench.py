@@ -41,6 +41,7 @@ C4 = dict(n=8000, d=10, m=2000, k=64)
 METRIC = 'PCGPwM NLL+grad evals/s'
 UNIT = 'evals/s'
 REF_CACHE = os.path.join(ROOT, '.bench_reference.json')
+REF_EMU = os.path.join(ROOT, '.bench_reference_emu.npz')
 
 
 def workload(seed=0, **shape):
@@ -227,6 +228,22 @@ def reference_plugin_metrics(w):
     t2 = time.perf_counter()
     out['theta_loglik_evals_per_s_B264_nograd'] = {'value': 264 / (t1 - t0), 'unit': 'theta/s'}
     out['theta_loglik_evals_per_s_B264_grad'] = {'value': 264 / (t2 - t1), 'unit': 'theta/s'}
+    # leave the reference-FITTED C2 emulator (what PCGPwM_B200.adopt needs) and the reference's own outputs at the 264
+    # proposals on disk: the b200 arm adopts it and reports config-size parity (secondary.c2_adopted_parity)
+    try:
+        ll = dbw.loglik(cal, emu, th, y, w['x'])
+        ll2, dll = dbw.loglik_grad(cal, emu, th, y, w['x'])
+        pr = emu.predict(w['x'], th)._info
+        fi, spc = emu._info, emu._info['standardpcinfo']
+        np.savez(REF_EMU, theta=fi['theta'], pc=fi['pc'], pcti=fi['pcti'], unscaled_pcstdvar=fi['unscaled_pcstdvar'],
+                 eta=fi['eta'], dampalpha=fi['dampalpha'], offset=spc['offset'], scale=spc['scale'],
+                 extravar=spc['extravar'], hyp=np.array([e['hyp'] for e in fi['emulist']]),
+                 hypind=np.array([e['hypind'] for e in fi['emulist']]).astype(int),
+                 condR=np.array([np.linalg.cond(fi['emulist'][j]['R']) for j in sorted({e['hypind'] for e in fi['emulist']})]),
+                 thetanew=th, y=y, yvar=yvar, loglik=ll, loglik_g=ll2, dloglik=dll, mean=pr['mean'], var=pr['var'],
+                 predvecs=pr['predvecs'], predvars=pr['predvars'])
+    except Exception as exc:
+        out['emulator_dump_error'] = repr(exc)
     return out
 
 
@@ -675,6 +692,40 @@ def c5_run(C, fi, w, y, yvar, torch, sampperchain, sampler='PTLMC_B200', **extra
             'distinct_factors': int(fi['_b200'].get('nf_total', fi['_b200']['Linv'].shape[0]))}
 
 
+def adopted_parity(M, C, w):
+    """Config-size parity on this box: the C2 emulator FITTED BY THE REFERENCE (left on disk by `--impl reference`, which
+    the driver runs right before this arm) is adopted onto the device; prediction and log-likelihoods at the C5
+    population (B = 264) are compared with the reference's own outputs.  None when the dump is absent or stale."""
+    if not os.path.exists(REF_EMU) or time.time() - os.path.getmtime(REF_EMU) > 6 * 3600:
+        return None
+    g = dict(np.load(REF_EMU))
+    k = g['hyp'].shape[0]
+    fi = {'method': 'PCGPwM', 'theta': g['theta'], 'x': w['x'], 'pc': g['pc'], 'pcti': g['pcti'],
+          'unscaled_pcstdvar': g['unscaled_pcstdvar'], 'eta': float(g['eta']), 'dampalpha': float(g['dampalpha']),
+          'standardpcinfo': {'offset': g['offset'], 'scale': g['scale'], 'extravar': g['extravar']},
+          'emulist': [{'hyp': g['hyp'][j], 'hypind': int(g['hypind'][j])} for j in range(k)]}
+    M.adopt(fi)
+
+    class Emu:
+        _info = fi
+    cal = {'yvar': g['yvar']}
+    pred = {}
+    M.predict(pred, fi, w['x'], g['thetanew'])
+    ll = C.loglik(cal, Emu, g['thetanew'], g['y'], w['x'])
+    ll2, dll = C.loglik_grad(cal, Emu, g['thetanew'], g['y'], w['x'])
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    return {'what': 'reference-fitted C2 emulator (n=2000, k=%d, %d distinct hyper-parameter sets) adopted with '
+                    'PCGPwM_B200.adopt; B=264 proposals; relative to the reference outputs computed on this box' % (k, len(set(g['hypind'].tolist()))),
+            'cond_R_max': float(g['condR'].max()),
+            'mean_rel': rel(pred['mean'], g['mean']), 'var_rel': rel(pred['var'], g['var']),
+            'predvecs_rel': rel(pred['predvecs'], g['predvecs']),
+            'predvars_rel': float(np.max(np.abs(pred['predvars'] - g['predvars']) / g['predvars'])),
+            'loglik_rel_per_theta_max': float(np.max(np.abs(ll - g['loglik']) / np.abs(g['loglik']))),
+            'loglik_gradcall_rel_max': float(np.max(np.abs(ll2 - g['loglik_g']) / np.abs(g['loglik_g']))),
+            'dloglik_rel': rel(dll, g['dloglik']),
+            'bars': 'north_star: mean/var 1e-6, log-likelihood per theta 1e-9'}
+
+
 def secondary_single(w, dev, torch, ops, peak):
     """BASELINE.json's other metrics on one GPU: plugin fit wall-seconds at C2 / C3 / C4, calibration theta
     log-likelihood evals/s, the C5 sampler run, potrf / trtri at n = 8000."""
@@ -721,6 +772,12 @@ def secondary_single(w, dev, torch, ops, peak):
     out['calibration_note'] = ('C2 emulator fitted above with the reference defaults (k=%d PCs, %d distinct factors); '
                                'B=264 is the PTLMC population of config C5 (256 chains + 8 temperatures)'
                                % (len(fi['emulist']), int(fi['_b200']['Linv'].shape[0])))
+    try:
+        par = adopted_parity(M, C, w)
+        if par is not None:
+            out['c2_adopted_parity'] = par
+    except Exception as exc:
+        out['c2_adopted_parity'] = {'error': repr(exc)}
     # (iii) C5 through the calibrator plugin (bounded: 1000 kept draws per chain = 1500 MCMC steps of 264 chains)
     try:
         out['c5_ptlmc'] = c5_run(C, fi, w, y, yvar, torch, 1000)
