@@ -98,11 +98,14 @@ int sb200_gp_weights(int k, int n, const double* Linv, long ldl, long stride_lin
  * of twice (PCGPwM.py:236 and 262-268); the caller decides this from its full population, so chunks and per-rank
  * slices of a larger population (B == 1 locally) keep the B > 1 behaviour.
  *   hypcov (nu, d+1): the distinct covariance hyper-parameter sets;  fu (nf): set used by factor f;
- *   Linv (nf, n, ldl): distinct factors;  fidx (k): factor used by PC j;  nug, sig2 (k);  pw (k, n). */
+ *   Linv (nf, n, ldl): distinct factors;  fidx (k): factor used by PC j;  nug, sig2 (k);  pw (k, n).
+ *   out_ld: row length of the outputs in components, (B, out_ld) and (B, out_ld, d); 0 or k = dense.  A caller that
+ *   assembles the components of several ranks side by side (PC-sharded prediction) passes the padded
+ *   width and this call fills its k columns of every row. */
 size_t sb200_gp_predict_workspace(int k, int nf, int nu, int n, int d, int B, int want_grad);
 int sb200_gp_predict(int k, int nf, int nu, int n, int d, int B, const double* theta, const double* thetanew,
                      const double* hypcov, const int* fu, const int* fidx, const double* nug, const double* sig2,
-                     const double* Linv, long ldl, long stride_linv, const double* pw, int want_grad,
+                     const double* Linv, long ldl, long stride_linv, const double* pw, int want_grad, long out_ld,
                      double* predvecs, double* predvars, double* predvecs_grad, double* predvars_grad,
                      void* workspace, size_t workspace_bytes, void* stream);
 
@@ -120,13 +123,37 @@ int sb200_pc_backproject(int m, int k, int B, int d, const double* phi, const do
  *   G (2,k,k) = Phi' diag(sinv[v]) Phi.  Outputs ll (B), dll (B,d; if want_grad) and *fired (device int):
  *   1 when the batch-wide unmodelled-variance test (dbw.py:277-284) selected the second variant.
  *   variant < 0: run that test over this batch; 0 / 1: use the given variant (a theta population sharded over
- *   several GPUs evaluates sb200_woodbury_trigger per shard, OR-reduces the flags and passes the result). */
+ *   several GPUs evaluates sb200_woodbury_trigger per shard, OR-reduces the flags and passes the result).
+ *   row_valid (B ints, may be NULL): rows with 0 take no part in the batch-wide test -- the reference only ever
+ *   evaluates the proposals with finite prior (dbw.py:100-129), so a caller that keeps the whole population on the
+ *   device masks the others here; their ll / dll are still written and are the caller's to discard. */
 int sb200_woodbury_loglik(int B, int k, int m, int d, const double* predvecs, const double* predvars,
                           const double* predvecs_grad, const double* predvars_grad, const double* phiT,
                           const double* resid0, const double* extravar, const double* sinv, const double* G,
-                          int want_grad, int variant, double* ll, double* dll, int* fired, void* stream);
+                          int want_grad, int variant, double* ll, double* dll, int* fired, const int* row_valid,
+                          void* stream);
 int sb200_woodbury_trigger(int B, int k, int m, const double* predvars, const double* phiT, const double* extravar,
-                           int* fired, void* stream);
+                           int* fired, const int* row_valid, void* stream);
+
+/* One step of the device-resident PT-LMC sampler: what surmise's PTLMC (utilitiesmethods/PTLMC.py:203-273) does between
+ * two evaluations of the log-posterior, for a population of B = numtemps + numchain chains kept on the device.
+ *   mode bit 0: accept / reject the pending proposal thetap given its log-likelihood ll (B) and gradient dll (B,d)
+ *               (:214-237), 5 B temperature-exchange proposals (:239-246, 259-273), then while k < tune and k % 10 == 0
+ *               the step-size adaptation (:247-254), or for k >= tune save thetac[numtemps:] as draw k - tune (:255-257);
+ *   mode bit 1: draw the Langevin proposal of the next step into thetap (:205-213) and mark in row_valid (B ints)
+ *               which proposals lie inside the prior box [lo, hi] (d) -- the others are never accepted.
+ *   First call: mode 2; then gp_predict + woodbury_loglik(thetap, row_valid) and mode 3, repeatedly; last call: mode 1.
+ * State (device, caller-owned): thetac (B,d), fval (B) = log-posterior / temperature, dfval (B,d) likewise, z (B,d),
+ * adjrho (B), scal (8): [0] tau [1] accepted fraction since the last adaptation [2] accepted moves [3] accepted swaps
+ * [4] rho [5] proposals outside the box; kstep (1, 64-bit): index of the pending step; save (numchain, nsave, d).
+ * Constants: temps (B) as PTLMC.py:75-82, hc / cov0 (d,d) the proposal factors (:192-201).  Randomness: Philox4x32-10
+ * keyed by seed with counter (step, stream, index), so replicated ranks that run the same launches hold identical
+ * chains.  The prior is uniform on the box; a constant log-density cancels in every acceptance ratio. */
+int sb200_ptlmc_step(int B, int d, int numtemps, int tune, int nsave, int mode, unsigned long long seed, double taracc,
+                     double* thetac, double* fval, double* dfval, double* thetap, double* z, double* adjrho,
+                     const double* ll, const double* dll, const double* temps, const double* lo, const double* hi,
+                     const double* hc, const double* cov0, double* scal, long long* kstep, double* save,
+                     int* row_valid, void* stream);
 
 /* Host-side helper (no device work) for the PTLMC_B200 sampler plugin: the temperature-exchange sweep of
  * utilitiesmethods/PTLMC.py:259-273 (tempexchange), with the random draws supplied by the caller.  lpost, temps (B);

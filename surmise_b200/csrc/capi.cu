@@ -163,13 +163,13 @@ size_t sb200_gp_predict_workspace(int k, int nf, int nu, int n, int d, int B, in
 }
 int sb200_gp_predict(int k, int nf, int nu, int n, int d, int B, const double* theta, const double* thetanew,
                      const double* hypcov, const int* fu, const int* fidx, const double* nug, const double* sig2,
-                     const double* Linv, long ldl, long stride_linv, const double* pw, int want_grad,
+                     const double* Linv, long ldl, long stride_linv, const double* pw, int want_grad, long out_ld,
                      double* predvecs, double* predvars, double* predvecs_grad, double* predvars_grad,
                      void* workspace, size_t workspace_bytes, void* stream) {
     SB_CHECK_ARG(theta && thetanew && hypcov && fu && fidx && nug && sig2 && Linv && pw && predvecs && predvars &&
                      workspace, "gp_predict: NULL pointer");
     return gp_predict(k, nf, nu, n, d, B, theta, thetanew, hypcov, fu, fidx, nug, sig2, Linv, ldl, stride_linv, pw,
-                      want_grad, predvecs, predvars, predvecs_grad, predvars_grad, workspace, workspace_bytes,
+                      want_grad, out_ld, predvecs, predvars, predvecs_grad, predvars_grad, workspace, workspace_bytes,
                       ST(stream));
 }
 
@@ -185,17 +185,31 @@ int sb200_pc_backproject(int m, int k, int B, int d, const double* phi, const do
 int sb200_woodbury_loglik(int B, int k, int m, int d, const double* predvecs, const double* predvars,
                           const double* predvecs_grad, const double* predvars_grad, const double* phiT,
                           const double* resid0, const double* extravar, const double* sinv, const double* G,
-                          int want_grad, int variant, double* ll, double* dll, int* fired, void* stream) {
+                          int want_grad, int variant, double* ll, double* dll, int* fired, const int* row_valid,
+                          void* stream) {
     SB_CHECK_ARG(predvecs && predvars && phiT && resid0 && extravar && sinv && G && ll && fired,
                  "woodbury_loglik: NULL pointer");
     return woodbury_loglik(B, k, m, d, predvecs, predvars, predvecs_grad, predvars_grad, phiT, resid0, extravar, sinv,
-                           G, want_grad, variant, ll, dll, fired, ST(stream));
+                           G, want_grad, variant, ll, dll, fired, row_valid, ST(stream));
 }
 
 int sb200_woodbury_trigger(int B, int k, int m, const double* predvars, const double* phiT, const double* extravar,
-                           int* fired, void* stream) {
+                           int* fired, const int* row_valid, void* stream) {
     SB_CHECK_ARG(predvars && phiT && extravar && fired, "woodbury_trigger: NULL pointer");
-    return woodbury_trigger(B, k, m, predvars, phiT, extravar, fired, ST(stream));
+    return woodbury_trigger(B, k, m, predvars, phiT, extravar, fired, row_valid, ST(stream));
+}
+
+int sb200_ptlmc_step(int B, int d, int numtemps, int tune, int nsave, int mode, unsigned long long seed, double taracc,
+                     double* thetac, double* fval, double* dfval, double* thetap, double* z, double* adjrho,
+                     const double* ll, const double* dll, const double* temps, const double* lo, const double* hi,
+                     const double* hc, const double* cov0, double* scal, long long* kstep, double* save,
+                     int* row_valid, void* stream) {
+    SB_CHECK_ARG(thetac && fval && dfval && thetap && z && adjrho && temps && lo && hi && hc && cov0 && scal && kstep &&
+                     row_valid, "ptlmc_step: NULL pointer");
+    SB_CHECK_ARG(!(mode & 1) || (ll && dll), "ptlmc_step: ll / dll are NULL");
+    SB_CHECK_ARG(nsave == 0 || save, "ptlmc_step: save is NULL");
+    return ptlmc_step(B, d, numtemps, tune, nsave, mode, seed, taracc, thetac, fval, dfval, thetap, z, adjrho, ll, dll,
+                      temps, lo, hi, hc, cov0, scal, kstep, save, row_valid, ST(stream));
 }
 
 int sb200_dgemm(int a_kc, int b_kc, int M, int N, int K, double alpha, const double* A, long lda, long stride_a,

@@ -160,24 +160,26 @@ __global__ void __launch_bounds__(256, 2) predict_partial_kernel(
 
 __global__ void predict_reduce_kernel(int K, int d, int B, long ldb, int nchunks, int Q, const double* __restrict__ partial,
                                       const double* __restrict__ nug, const double* __restrict__ sig2, int want_grad,
-                                      int single_quirk, double* __restrict__ predvecs, double* __restrict__ predvars,
-                                      double* __restrict__ dpv, double* __restrict__ dpvar) {
+                                      int single_quirk, long ldk, double* __restrict__ predvecs,
+                                      double* __restrict__ predvars, double* __restrict__ dpv, double* __restrict__ dpvar) {
+    // outputs are (B, ldk[, d]) with ldk >= K: a caller that assembles the components of several ranks side by side
+    // (PC-sharded prediction) hands in a wider row than this launch fills
     const int b = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
     if (b >= B) return;
     const double omn = 1.0 - nug[k], s2k = sig2[k];
     for (int q = 0; q < Q; q++) {
         double s = 0.0;
         for (int c = 0; c < nchunks; c++) s += partial[((((long)k * nchunks + c) * Q) + q) * ldb + b];
-        if (q == 0) predvars[(long)b * K + k] = s2k * fabs(1.0 - omn * omn * s);           // PCGPwM.py:270
-        else if (q == 1) predvecs[(long)b * K + k] = omn * s;                               // PCGPwM.py:246
+        if (q == 0) predvars[(long)b * ldk + k] = s2k * fabs(1.0 - omn * omn * s);           // PCGPwM.py:270
+        else if (q == 1) predvecs[(long)b * ldk + k] = omn * s;                               // PCGPwM.py:246
         else if (want_grad) {
             int i = (q - 2) >> 1;
             if ((q - 2) & 1) {
                 // the reference applies (1-nug) twice here (PCGPwM.py:236,268) except when B == 1 and d == 1
                 double extra = single_quirk ? 1.0 : omn;
-                dpv[((long)b * K + k) * d + i] = extra * omn * s;
+                dpv[((long)b * ldk + k) * d + i] = extra * omn * s;
             } else {
-                dpvar[((long)b * K + k) * d + i] = -2.0 * s2k * omn * omn * s;              // PCGPwM.py:269
+                dpvar[((long)b * ldk + k) * d + i] = -2.0 * s2k * omn * omn * s;              // PCGPwM.py:269
             }
         }
     }
@@ -397,13 +399,15 @@ size_t gp_predict_workspace(int K, int nf, int nu, int n, int d, int B, int want
 
 int gp_predict(int K, int nf, int nu, int n, int d, int B, const double* theta, const double* thetanew,
                const double* hypcov, const int* fu, const int* fidx, const double* nug, const double* sig2,
-               const double* Linv, long ldl, long strideL, const double* pw, int want_grad, double* predvecs,
-               double* predvars, double* dpv, double* dpvar, void* workspace, size_t workspace_bytes,
+               const double* Linv, long ldl, long strideL, const double* pw, int want_grad, long out_ld,
+               double* predvecs, double* predvars, double* dpv, double* dpvar, void* workspace, size_t workspace_bytes,
                cudaStream_t stream) {
     SB_CHECK_ARG(K > 0 && nf > 0 && nu > 0 && n > 0 && B > 0, "gp_predict: empty problem");
     SB_CHECK_ARG(d >= 1 && d <= MAXD, "gp_predict: d=%d outside [1,%d]", d, MAXD);
     SB_CHECK_ARG(workspace_bytes >= gp_predict_workspace(K, nf, nu, n, d, B, want_grad), "gp_predict: workspace too small");
     SB_CHECK_ARG(!want_grad || (dpv && dpvar), "gp_predict: gradient outputs are NULL");
+    if (out_ld <= 0) out_ld = K;
+    SB_CHECK_ARG(out_ld >= K, "gp_predict: out_ld=%ld < k=%d", out_ld, K);
     // want_grad == 2: the caller's WHOLE population is one theta with d == 1, where the reference applies (1-nug) to
     // predvecs_gradtheta once instead of twice (PCGPwM.py:236, 262-268).  Decided by the caller from the full
     // population, never from the size of a chunk or of a rank's slice.
@@ -454,7 +458,7 @@ int gp_predict(int K, int nf, int nu, int n, int d, int B, const double* theta, 
         SB_LAUNCH_CHECK();
         dim3 grid2(cdiv(B, 128), K);
         predict_reduce_kernel<<<grid2, 128, 0, stream>>>(K, d, B, ldb, nchunks, Q, partial, nug, sig2, want_grad,
-                                                         single_quirk, predvecs, predvars, dpv, dpvar);
+                                                         single_quirk, out_ld, predvecs, predvars, dpv, dpvar);
         SB_LAUNCH_CHECK();
     }
     return 0;

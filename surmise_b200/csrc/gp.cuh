@@ -34,8 +34,8 @@ int gp_weights(int K, int n, const double* Linv, long ldl, long strideL, const i
 size_t gp_predict_workspace(int K, int nf, int nu, int n, int d, int B, int want_grad);
 int gp_predict(int K, int nf, int nu, int n, int d, int B, const double* theta, const double* thetanew,
                const double* hypcov, const int* fu, const int* fidx, const double* nug, const double* sig2,
-               const double* Linv, long ldl, long strideL, const double* pw, int want_grad, double* predvecs,
-               double* predvars, double* dpv, double* dpvar, void* workspace, size_t workspace_bytes,
+               const double* Linv, long ldl, long strideL, const double* pw, int want_grad, long out_ld,
+               double* predvecs, double* predvars, double* dpv, double* dpvar, void* workspace, size_t workspace_bytes,
                cudaStream_t stream);
 
 int pc_backproject(int m, int K, int B, int d, const double* phi, const double* offset, const double* extravar,
@@ -48,8 +48,15 @@ constexpr int WOODBURY_MAXK = 112;
 int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const double* predvars, const double* dpv,
                     const double* dpvar, const double* phiT, const double* resid0, const double* extravar,
                     const double* sinv, const double* G, int want_grad, int variant, double* ll, double* dll,
-                    int* fired, cudaStream_t stream);
+                    int* fired, const int* row_valid, cudaStream_t stream);
 int woodbury_trigger(int B, int K, int m, const double* predvars, const double* phiT, const double* extravar,
-                     int* fired, cudaStream_t stream);
+                     int* fired, const int* row_valid, cudaStream_t stream);
+
+
+// sampler.cu: one step of the device-resident PT-LMC sampler (surmise utilitiesmethods/PTLMC.py:203-273)
+int ptlmc_step(int B, int d, int numtemps, int tune, int nsave, int mode, unsigned long long seed, double taracc,
+               double* thetac, double* fval, double* dfval, double* thetap, double* z, double* adjrho, const double* ll,
+               const double* dll, const double* temps, const double* lo, const double* hi, const double* hc,
+               const double* cov0, double* scal, long long* kstep, double* save, int* row_valid, cudaStream_t stream);
 
 }  // namespace sb

@@ -17,8 +17,10 @@ constexpr int WT = 128;
 
 __global__ void __launch_bounds__(WT) woodbury_trigger_kernel(int B, int K, int m, const double* __restrict__ predvars,
                                                               const double* __restrict__ phiT,
-                                                              const double* __restrict__ extravar, int* fired) {
+                                                              const double* __restrict__ extravar,
+                                                              const int* __restrict__ row_valid, int* fired) {
     const int b = blockIdx.x;
+    if (row_valid && !row_valid[b]) return;          // rows the caller will discard (prior = -inf) take no part in the test
     extern __shared__ double sh[];
     double* v = sh;
     for (int a = threadIdx.x; a < K; a += WT) v[a] = predvars[(long)b * K + a];
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
 int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const double* predvars, const double* dpv,
                     const double* dpvar, const double* phiT, const double* resid0, const double* extravar,
                     const double* sinv, const double* G, int want_grad, int variant, double* ll, double* dll,
-                    int* fired, cudaStream_t stream) {
+                    int* fired, const int* row_valid, cudaStream_t stream) {
     SB_CHECK_ARG(B > 0 && m > 0, "woodbury: empty batch");
     SB_CHECK_ARG(K >= 1 && K <= WOODBURY_MAXK, "woodbury: k=%d outside [1,%d]", K, WOODBURY_MAXK);
     SB_CHECK_ARG(!want_grad || (dpv && dpvar && dll), "woodbury: gradient buffers are NULL");
@@ -185,7 +187,7 @@ int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const do
     }));
     if (variant < 0) {
         SB_CUDA(cudaMemsetAsync(fired, 0, sizeof(int), stream));
-        woodbury_trigger_kernel<<<B, WT, K * sizeof(double), stream>>>(B, K, m, predvars, phiT, extravar, fired);
+        woodbury_trigger_kernel<<<B, WT, K * sizeof(double), stream>>>(B, K, m, predvars, phiT, extravar, row_valid, fired);
         SB_LAUNCH_CHECK();
     }
     woodbury_loglik_kernel<<<B, WT, smem, stream>>>(B, K, m, d, predvecs, predvars, dpv, dpvar, phiT, resid0, sinv, G,
@@ -195,10 +197,10 @@ int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const do
 }
 
 int woodbury_trigger(int B, int K, int m, const double* predvars, const double* phiT, const double* extravar,
-                     int* fired, cudaStream_t stream) {
+                     int* fired, const int* row_valid, cudaStream_t stream) {
     SB_CHECK_ARG(B > 0 && m > 0 && K >= 1, "woodbury_trigger: empty batch");
     SB_CUDA(cudaMemsetAsync(fired, 0, sizeof(int), stream));
-    woodbury_trigger_kernel<<<B, WT, K * sizeof(double), stream>>>(B, K, m, predvars, phiT, extravar, fired);
+    woodbury_trigger_kernel<<<B, WT, K * sizeof(double), stream>>>(B, K, m, predvars, phiT, extravar, row_valid, fired);
     SB_LAUNCH_CHECK();
     return 0;
 }

@@ -279,7 +279,7 @@ def gp_weights(Linv, fidx, g, sig2ofconst=0.01):
     return pw, sig2
 
 
-def gp_predict(state, thetanew, want_grad=False, out=None, population=None):
+def gp_predict(state, thetanew, want_grad=False, out=None, population=None, out_ld=0):
     """PC-space prediction (PCGPwM.py:219-270) from a device state dict (see emulation module).
 
     Returns device tensors predvecs, predvars (B,k) and, if want_grad, gradients (B,k,d).
@@ -287,6 +287,8 @@ def gp_predict(state, thetanew, want_grad=False, out=None, population=None):
     population: size of the caller's WHOLE theta population when thetanew is a chunk or a rank's slice of it (default:
     thetanew itself).  Only a population of one theta with d == 1 takes the reference's single-(1-nug) gradient
     (PCGPwM.py:236, 262-268), so results do not depend on chunking or on the number of ranks.
+    out_ld: with `out`, the row length (in components) of the output buffers when they are wider than this state's k
+    (PC-sharded prediction writes each rank's components into a padded (B, kmax[, d]) block).
     """
     torch = _torch()
     tn = _f64(torch, thetanew)
@@ -308,7 +310,7 @@ def gp_predict(state, thetanew, want_grad=False, out=None, population=None):
     grad_mode = (2 if (total == 1 and d == 1) else 1) if want_grad else 0
     check(lib.sb200_gp_predict(K, nf, nu, n, d, B, _ptr(state['theta']), _ptr(tn), _ptr(state['hypcov']),
                                _ptr(state['fu']), _ptr(state['fidx']), _ptr(state['nug']), _ptr(state['sig2']),
-                               _ptr(state['Linv']), ldl, n * ldl, _ptr(state['pw']), grad_mode, _ptr(pv),
+                               _ptr(state['Linv']), ldl, n * ldl, _ptr(state['pw']), grad_mode, int(out_ld), _ptr(pv),
                                _ptr(pvar), _ptr(dpv), _ptr(dpvar), _ptr(ws), ws.numel(), _stream(torch)),
           'sb200_gp_predict')
     return pv, pvar, dpv, dpvar
@@ -333,18 +335,18 @@ def pc_backproject(phi, offset, extravar, pv, pvar, dpv=None, dpvar=None, want_c
     return mean, var, cxh, mg, cg
 
 
-def woodbury_trigger(consts, pvar):
+def woodbury_trigger(consts, pvar, row_valid=None):
     """Device int32 flag: does the unmodelled-variance test (dbw.py:277-279) fire for this batch?"""
     torch = _torch()
     _need_cuda(pvar, consts['phiT'])
     B, K = pvar.shape
     fired = torch.empty(1, dtype=torch.int32, device=pvar.device)
     check(lib.sb200_woodbury_trigger(B, K, consts['phiT'].shape[1], _ptr(pvar), _ptr(consts['phiT']),
-                                     _ptr(consts['extravar']), _ptr(fired), _stream(torch)), 'sb200_woodbury_trigger')
+                                     _ptr(consts['extravar']), _ptr(fired), _ptr(row_valid), _stream(torch)), 'sb200_woodbury_trigger')
     return fired
 
 
-def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1, out=None):
+def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1, out=None, row_valid=None):
     """Batched directbayeswoodbury log-likelihood (+ gradient) (dbw.py:261-383).
 
     consts: dict of device tensors phiT (k,m), resid0 (m), extravar (m), sinv (2,m), G (2,k,k).
@@ -366,7 +368,7 @@ def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1, out=None
     check(lib.sb200_woodbury_loglik(B, K, m, d, _ptr(pv), _ptr(pvar), _ptr(dpv), _ptr(dpvar), _ptr(consts['phiT']),
                                     _ptr(consts['resid0']), _ptr(consts['extravar']), _ptr(consts['sinv']),
                                     _ptr(consts['G']), int(want_grad), int(variant), _ptr(ll), _ptr(dll), _ptr(fired),
-                                    _stream(torch)), 'sb200_woodbury_loglik')
+                                    _ptr(row_valid), _stream(torch)), 'sb200_woodbury_loglik')
     return ll, dll, fired
 
 

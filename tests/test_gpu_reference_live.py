@@ -96,7 +96,7 @@ def test_c5_shape_predict_on_adopted_reference_emulator(ref, adopted):
                 cxh=rel(got['covxhalf'], want['covxhalf']))
     report('live_c5shape_predict', cond=cond, **errs)
     assert errs['mean'] < 1e-6 and errs['var'] < 1e-6            # north_star bar
-    assert max(errs.values()) < 1e-8                              # what this conditioning allows
+    assert max(errs.values()) < 1e-10                             # measured on a B200: <= 7e-12 at cond 1.3e6
 
 
 def test_c5_shape_loglik_on_adopted_reference_emulator(ref, adopted):
@@ -117,7 +117,7 @@ def test_c5_shape_loglik_on_adopted_reference_emulator(ref, adopted):
     report('live_c5shape_loglik', B=264, ll=e_l, ll_gradcall=e_l2, dll=e_d)
     assert ll.shape == want_ll.shape and dll.shape == want_dll.shape
     assert e_l < 1e-9 and e_l2 < 1e-9, (e_l, e_l2)               # north_star bar, per theta
-    assert e_d < 1e-8
+    assert e_d < 1e-10                                           # measured 1.1e-11 / 9.2e-12
 
 
 def test_c3_shape_missing_outputs_through_standardize(ref):
@@ -140,7 +140,8 @@ def test_c3_shape_missing_outputs_through_standardize(ref):
                 pcstdvar=float(np.max(np.abs(got['unscaled_pcstdvar'] - fi['unscaled_pcstdvar']))))
     report('live_c3shape_standardize', k=got['pc'].shape[1], **errs)
     assert errs['offset'] < 1e-13 and errs['scale'] < 1e-13
-    # 40 fixed-point sweeps amplify rounding differences between SVD (reference) and Gram-eigh (here); the imputed
-    # entries agree to ~1e-5 of the data scale on the committed golden (profiles/parity_report_r1.txt); bound = 5 x that
-    assert errs['fs'] < 5e-5 and errs['pc'] < 5e-5 and errs['pcw'] < 5e-6
-    assert errs['extravar'] < 2e-4 and errs['pcstdvar'] < 1e-3
+    # 40 fixed-point sweeps amplify rounding differences between SVD (reference) and Gram-eigh (here).  Bounds = 5 x the
+    # discrepancies measured on a B200 (fs 7.3e-7, pc 1.4e-6, pcw 2.0e-9, pcstdvar 1.2e-6; extravar -- a residual
+    # variance of order 1e-10 of the data scale, hence the most sensitive -- 2.2e-3 of its largest entry)
+    assert errs['fs'] < 4e-6 and errs['pc'] < 7e-6 and errs['pcw'] < 1e-8
+    assert errs['extravar'] < 1.1e-2 and errs['pcstdvar'] < 6e-6
