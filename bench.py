@@ -778,9 +778,9 @@ def secondary_single(w, dev, torch, ops, peak):
             out['c2_adopted_parity'] = par
     except Exception as exc:
         out['c2_adopted_parity'] = {'error': repr(exc)}
-    # (iii) C5 through the calibrator plugin (bounded: 1000 kept draws per chain = 1500 MCMC steps of 264 chains)
+    # (iii) C5 through the calibrator plugin (bounded: 2000 kept draws per chain = 3000 MCMC steps of 264 chains)
     try:
-        out['c5_ptlmc'] = c5_run(C, fi, w, y, yvar, torch, 1000)
+        out['c5_ptlmc'] = c5_run(C, fi, w, y, yvar, torch, 2000)
     except Exception as exc:
         out['c5_ptlmc'] = {'error': repr(exc)}
     del fi, fp
@@ -923,7 +923,7 @@ def secondary_multi(w, dev, torch, dist, ops, world, rank, peak):
                                                'B_per_rank': B, 'distinct_factors': int(f2['_b200']['Linv'].shape[0])}
     out['theta_loglik_evals_per_s_all_ranks'] = rates
     try:
-        out['c5_ptlmc'] = c5_run(C, f2, w2, y, yvar, torch, 1000, shard_theta=True)
+        out['c5_ptlmc'] = c5_run(C, f2, w2, y, yvar, torch, 2000, shard_factors=True)
         out['c5_ptlmc']['ranks'] = world
     except Exception as exc:
         import traceback

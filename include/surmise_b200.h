@@ -126,14 +126,18 @@ int sb200_pc_backproject(int m, int k, int B, int d, const double* phi, const do
  *   several GPUs evaluates sb200_woodbury_trigger per shard, OR-reduces the flags and passes the result).
  *   row_valid (B ints, may be NULL): rows with 0 take no part in the batch-wide test -- the reference only ever
  *   evaluates the proposals with finite prior (dbw.py:100-129), so a caller that keeps the whole population on the
- *   device masks the others here; their ll / dll are still written and are the caller's to discard. */
+ *   device masks the others here; their ll / dll are still written and are the caller's to discard.
+ *   seg_k, seg_stride: 0, 0 for dense (B,k) / (B,k,d) inputs.  Otherwise the k components arrive in k / seg_k groups,
+ *   each a dense (B, seg_k[, d]) block, consecutive groups seg_stride doubles apart -- exactly what an all-gather of the
+ *   per-rank blocks of a PC-sharded prediction (sb200_gp_predict with out_ld = seg_k) leaves in memory; phiT / G are
+ *   then given in that component order, with zero rows for padded components. */
 int sb200_woodbury_loglik(int B, int k, int m, int d, const double* predvecs, const double* predvars,
                           const double* predvecs_grad, const double* predvars_grad, const double* phiT,
                           const double* resid0, const double* extravar, const double* sinv, const double* G,
                           int want_grad, int variant, double* ll, double* dll, int* fired, const int* row_valid,
-                          void* stream);
+                          int seg_k, long seg_stride, void* stream);
 int sb200_woodbury_trigger(int B, int k, int m, const double* predvars, const double* phiT, const double* extravar,
-                           int* fired, const int* row_valid, void* stream);
+                           int* fired, const int* row_valid, int seg_k, long seg_stride, void* stream);
 
 /* One step of the device-resident PT-LMC sampler: what surmise's PTLMC (utilitiesmethods/PTLMC.py:203-273) does between
  * two evaluations of the log-posterior, for a population of B = numtemps + numchain chains kept on the device.

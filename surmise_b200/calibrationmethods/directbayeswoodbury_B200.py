@@ -189,6 +189,105 @@ def _evaluate_sharded(fitinfo, emu, theta, y, x, return_grad, comm):
     return comm.allgather_rows(local, sizes)
 
 
+class DeviceLogpost:
+    """What a device-resident sampler (utilitiesmethods/PTLMC_B200) needs from the log-posterior closure: the prior's
+    box, if the prior is uniform on one, and a fixed-shape, allocation-free, synchronisation-free evaluation of the
+    log-likelihood and its gradient that can be enqueued thousands of times (and captured in a CUDA graph).
+
+    A prior object declares its box with an attribute `box = (lo, hi)` (arrays of length d): lpdf is constant inside
+    and -inf outside.  Without it the sampler keeps calling the host closure (any Python prior works there)."""
+
+    def __init__(self, fitinfo, emu, x, y, thetaprior, extra_logp=None):
+        self.fitinfo, self.emu, self.x, self.y, self.prior = fitinfo, emu, x, y, thetaprior
+        box = getattr(thetaprior, 'box', None)
+        self.box = None
+        if box is not None and extra_logp is None:
+            lo, hi = (np.asarray(b, dtype=np.float64).reshape(-1) for b in box)
+            if lo.shape == hi.shape and np.all(hi > lo):
+                self.box = (lo, hi)
+
+    def evaluator(self, B, d):
+        return _DeviceEvaluator(self.fitinfo, self.emu, self.x, self.y, B, d)
+
+    def record(self, **stats):
+        self.fitinfo['_b200sampler'] = stats
+
+
+class _DeviceEvaluator:
+    """ll (B), dll (B,d) of the proposals in `thetap` (B,d), rows masked by `valid` (int32) -- all device buffers of
+    fixed address.  launch() enqueues predict + Woodbury on the current stream.  With factors sharded over ranks
+    (PCGPwM_B200 fit option factors='owner') every rank evaluates the components whose factor it owns straight into
+    its block of one buffer, the blocks are all-gathered in place (NCCL), and the Woodbury kernel reads the gathered
+    blocks as they lie (segmented layout): one collective, no repacking."""
+
+    def __init__(self, fitinfo, emu, x, y, B, d):
+        ops = _ops()
+        torch = ops._torch()
+        self.ops, self.torch = ops, torch
+        consts = woodbury_constants(fitinfo, emu, x, y)
+        st = _device_state(emu)['_b200']
+        dev = consts['phiT'].device
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.B, self.d, self.st = B, d, st
+        self.thetap = torch.zeros((B, d), **f64)
+        self.valid = torch.ones(B, dtype=torch.int32, device=dev)
+        self.ll, self.dll = torch.zeros(B, **f64), torch.zeros((B, d), **f64)
+        self.fired = torch.zeros(1, dtype=torch.int32, device=dev)
+        sh = st.get('shard')
+        if sh is None:
+            K = st['pw'].shape[0]
+            self.consts, self.segments, self.comm = consts, None, None
+            self.pred = (torch.empty((B, K), **f64), torch.empty((B, K), **f64), torch.empty((B, K, d), **f64),
+                         torch.empty((B, K, d), **f64))
+            return
+        from .. import _dist
+        self.comm = _dist.Comm()
+        if self.comm.world != sh['world'] or self.comm.rank != sh['rank']:
+            raise RuntimeError('the emulator\'s factors are sharded over %d ranks; calibrate in the same process group'
+                               % sh['world'])
+        world, rank = sh['world'], sh['rank']
+        kmax = max(max(sh['counts']), 1)
+        chunk = B * kmax * (2 + 2 * d)
+        self.gathered = torch.zeros(world * chunk, **f64)
+        blocks = self.gathered.view(world, chunk)
+        blocks[:, B * kmax:2 * B * kmax] = 1.0                 # padded components: predvar 1, everything else 0
+        self.local = blocks[rank]
+
+        def views(block):
+            o = B * kmax
+            return (block[:o].view(B, kmax), block[o:2 * o].view(B, kmax), block[2 * o:2 * o + o * d].view(B, kmax, d),
+                    block[2 * o + o * d:].view(B, kmax, d))
+        self.pred_local, self.pred = views(self.local), views(blocks[0])
+        self.kl, self.kmax = int(st['local']['pw'].shape[0]), kmax
+        self.segments = (kmax, chunk)
+        # constants in gathered component order, zero rows / columns for the padded components
+        K, Kp = st['pw'].shape[0], world * kmax
+        pos = np.zeros(K, dtype=np.int64)                      # padded position of component j
+        offs = np.concatenate([[0], np.cumsum(sh['counts'])])
+        order = np.argsort(sh['owner'], kind='stable')
+        for r in range(world):
+            for c, j in enumerate(order[offs[r]:offs[r + 1]]):
+                pos[j] = r * kmax + c
+        pos_t = torch.from_numpy(pos).to(dev)
+        phiT = torch.zeros((Kp, consts['phiT'].shape[1]), **f64)
+        phiT[pos_t] = consts['phiT']
+        G = torch.zeros((2, Kp, Kp), **f64)
+        G[:, pos_t[:, None], pos_t[None, :]] = consts['G']
+        self.consts = dict(consts, phiT=phiT, G=G)
+
+    def launch(self):
+        ops = self.ops
+        if self.segments is None:
+            ops.gp_predict(self.st, self.thetap, True, out=self.pred, population=self.B)
+        else:
+            if self.kl:
+                ops.gp_predict(self.st['local'], self.thetap, True, out=self.pred_local, population=self.B,
+                               out_ld=self.kmax)
+            self.comm.dist.all_gather_into_tensor(self.gathered, self.local)
+        ops.woodbury_loglik(self.consts, *self.pred, out=(self.ll, self.dll, self.fired), row_valid=self.valid,
+                            segments=self.segments)
+
+
 def loglik(fitinfo, emu, theta, y, x):
     """(B,1) log-likelihoods; same contract as directbayeswoodbury.loglik (dbw.py:261-306)."""
     return _evaluate(fitinfo, emu, theta, y, x, False)
@@ -252,6 +351,8 @@ def make_logpost(fitinfo, emu, x, y, fd_step=10 ** (-6), extra_logp=None, with_g
             theta0 = theta0[np.random.randint(theta0.shape[0], size=n), :]
         return theta0
 
+    # lets a device-resident sampler plugin (PTLMC_B200) keep the whole chain on the GPU when the prior allows it
+    logpostfull_wgrad.b200 = DeviceLogpost(fitinfo, emu, x, y, thetaprior, extra_logp) if with_grad else None
     return logpostfull_wgrad, draw_func
 
 
@@ -261,8 +362,12 @@ def fit(fitinfo, emu, x, y, **bayeswoodbury_args):
         from surmise.utilities import sampler        # the reference's dispatcher, used unmodified
     except ImportError:
         from ..utilities import sampler              # same contract, for installations without surmise
-    if 'shard_theta' in bayeswoodbury_args:          # our option, not a sampler option
+    if 'shard_theta' in bayeswoodbury_args:          # our options, not sampler options
         fitinfo['shard_theta'] = bool(bayeswoodbury_args.pop('shard_theta'))
+    if bayeswoodbury_args.pop('shard_factors', False):
+        # every rank holds the same emulator: keep only this rank's block of the full-data factors and evaluate
+        # PC-sharded from here on (collective; all ranks run the same sampler with the same seed)
+        _emu_method.shard_state(_device_state(emu))
     woodbury_constants(fitinfo, emu, x, y)
     logpost, draw_func = make_logpost(fitinfo, emu, x, y)
     sampler_obj = sampler(logpost_func=logpost, draw_func=draw_func, **bayeswoodbury_args)

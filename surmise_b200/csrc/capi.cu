@@ -186,17 +186,17 @@ int sb200_woodbury_loglik(int B, int k, int m, int d, const double* predvecs, co
                           const double* predvecs_grad, const double* predvars_grad, const double* phiT,
                           const double* resid0, const double* extravar, const double* sinv, const double* G,
                           int want_grad, int variant, double* ll, double* dll, int* fired, const int* row_valid,
-                          void* stream) {
+                          int seg_k, long seg_stride, void* stream) {
     SB_CHECK_ARG(predvecs && predvars && phiT && resid0 && extravar && sinv && G && ll && fired,
                  "woodbury_loglik: NULL pointer");
     return woodbury_loglik(B, k, m, d, predvecs, predvars, predvecs_grad, predvars_grad, phiT, resid0, extravar, sinv,
-                           G, want_grad, variant, ll, dll, fired, row_valid, ST(stream));
+                           G, want_grad, variant, ll, dll, fired, row_valid, seg_k, seg_stride, ST(stream));
 }
 
 int sb200_woodbury_trigger(int B, int k, int m, const double* predvars, const double* phiT, const double* extravar,
-                           int* fired, const int* row_valid, void* stream) {
+                           int* fired, const int* row_valid, int seg_k, long seg_stride, void* stream) {
     SB_CHECK_ARG(predvars && phiT && extravar && fired, "woodbury_trigger: NULL pointer");
-    return woodbury_trigger(B, k, m, predvars, phiT, extravar, fired, row_valid, ST(stream));
+    return woodbury_trigger(B, k, m, predvars, phiT, extravar, fired, row_valid, seg_k, seg_stride, ST(stream));
 }
 
 int sb200_ptlmc_step(int B, int d, int numtemps, int tune, int nsave, int mode, unsigned long long seed, double taracc,

@@ -48,9 +48,9 @@ constexpr int WOODBURY_MAXK = 112;
 int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const double* predvars, const double* dpv,
                     const double* dpvar, const double* phiT, const double* resid0, const double* extravar,
                     const double* sinv, const double* G, int want_grad, int variant, double* ll, double* dll,
-                    int* fired, const int* row_valid, cudaStream_t stream);
+                    int* fired, const int* row_valid, int segk, long segstride, cudaStream_t stream);
 int woodbury_trigger(int B, int K, int m, const double* predvars, const double* phiT, const double* extravar,
-                     int* fired, const int* row_valid, cudaStream_t stream);
+                     int* fired, const int* row_valid, int segk, long segstride, cudaStream_t stream);
 
 
 // sampler.cu: one step of the device-resident PT-LMC sampler (surmise utilitiesmethods/PTLMC.py:203-273)

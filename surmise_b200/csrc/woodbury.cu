@@ -15,15 +15,23 @@ namespace {
 
 constexpr int WT = 128;
 
+// Component a of proposal b in a (possibly) segmented (B, K) table: components arrive in groups of `segk` (one group
+// per rank of a PC-sharded prediction, each a dense (B, segk) block, `segstride` doubles apart -- the layout an
+// all-gather of the ranks' blocks produces).  segk == K, segstride == 0 is the plain dense table.
+__device__ __forceinline__ long seg_at(int b, int a, int segk, long segstride) {
+    return (long)(a / segk) * segstride + (long)b * segk + (a % segk);
+}
+
 __global__ void __launch_bounds__(WT) woodbury_trigger_kernel(int B, int K, int m, const double* __restrict__ predvars,
                                                               const double* __restrict__ phiT,
                                                               const double* __restrict__ extravar,
-                                                              const int* __restrict__ row_valid, int* fired) {
+                                                              const int* __restrict__ row_valid, int segk,
+                                                              long segstride, int* fired) {
     const int b = blockIdx.x;
     if (row_valid && !row_valid[b]) return;          // rows the caller will discard (prior = -inf) take no part in the test
     extern __shared__ double sh[];
     double* v = sh;
-    for (int a = threadIdx.x; a < K; a += WT) v[a] = predvars[(long)b * K + a];
+    for (int a = threadIdx.x; a < K; a += WT) v[a] = predvars[seg_at(b, a, segk, segstride)];
     __syncthreads();
     bool hit = false;
     for (int x = threadIdx.x; x < m; x += WT) {
@@ -47,8 +55,8 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
                                                              const double* __restrict__ resid0,
                                                              const double* __restrict__ sinvb,
                                                              const double* __restrict__ Gb, int* fired,
-                                                             int forced_variant, int want_grad, double* __restrict__ ll,
-                                                             double* __restrict__ dll) {
+                                                             int forced_variant, int want_grad, int segk, long segstride,
+                                                             double* __restrict__ ll, double* __restrict__ dll) {
     extern __shared__ double sh[];
     double* Lm = sh;                    // K*K : A, then L, then Ainv
     double* Xm = Lm + K * K;            // K*K : L^-1
@@ -68,8 +76,8 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
     const double* G = Gb + (long)variant * K * K;
 
     for (int a = tid; a < K; a += WT) {
-        D[a] = sqrt(predvars[(long)b * K + a]);
-        pvv[a] = predvecs[(long)b * K + a];
+        D[a] = sqrt(predvars[seg_at(b, a, segk, segstride)]);
+        pvv[a] = predvecs[seg_at(b, a, segk, segstride)];
     }
     __syncthreads();
     double t1 = 0.0;
@@ -156,10 +164,10 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
     for (int i = 0; i < d; i++) {
         double val = 0.0;
         for (int a = tid; a < K; a += WT) {
-            double dpa = dpv[((long)b * K + a) * d + i];
-            double dD = 0.5 * dpvar[((long)b * K + a) * d + i] / D[a];
+            double dpa = dpv[seg_at(b, a, segk, segstride) * d + i];
+            double dD = 0.5 * dpvar[seg_at(b, a, segk, segstride) * d + i] / D[a];
             double gd = 0.0;
-            for (int c = 0; c < K; c++) gd += G[a * K + c] * dpv[((long)b * K + c) * d + i];
+            for (int c = 0; c < K; c++) gd += G[a * K + c] * dpv[seg_at(b, c, segk, segstride) * d + i];
             double dJ2 = -D[a] * gd + dD * q[a];
             // -1/2 dterm3 - 1/2 (dterm1 - dterm2), term by term (dbw.py:344-381 in k-space)
             val += -dD * Nv[a] + q[a] * dpa + dJ2 * J3[a] - dD * J3[a] * MJ3[a];
@@ -174,8 +182,13 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
 int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const double* predvars, const double* dpv,
                     const double* dpvar, const double* phiT, const double* resid0, const double* extravar,
                     const double* sinv, const double* G, int want_grad, int variant, double* ll, double* dll,
-                    int* fired, const int* row_valid, cudaStream_t stream) {
+                    int* fired, const int* row_valid, int segk, long segstride, cudaStream_t stream) {
     SB_CHECK_ARG(B > 0 && m > 0, "woodbury: empty batch");
+    if (segk <= 0 || segk >= K) {
+        segk = K;
+        segstride = 0;
+    }
+    SB_CHECK_ARG(K % segk == 0, "woodbury: k=%d is not a multiple of the segment width %d", K, segk);
     SB_CHECK_ARG(K >= 1 && K <= WOODBURY_MAXK, "woodbury: k=%d outside [1,%d]", K, WOODBURY_MAXK);
     SB_CHECK_ARG(!want_grad || (dpv && dpvar && dll), "woodbury: gradient buffers are NULL");
     size_t smem = (size_t)(2 * K * K + m + 7 * K + 32) * sizeof(double);
@@ -187,20 +200,28 @@ int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const do
     }));
     if (variant < 0) {
         SB_CUDA(cudaMemsetAsync(fired, 0, sizeof(int), stream));
-        woodbury_trigger_kernel<<<B, WT, K * sizeof(double), stream>>>(B, K, m, predvars, phiT, extravar, row_valid, fired);
+        woodbury_trigger_kernel<<<B, WT, K * sizeof(double), stream>>>(B, K, m, predvars, phiT, extravar, row_valid, segk,
+                                                                       segstride, fired);
         SB_LAUNCH_CHECK();
     }
     woodbury_loglik_kernel<<<B, WT, smem, stream>>>(B, K, m, d, predvecs, predvars, dpv, dpvar, phiT, resid0, sinv, G,
-                                                    fired, variant > 0 ? 1 : variant, want_grad, ll, dll);
+                                                    fired, variant > 0 ? 1 : variant, want_grad, segk, segstride, ll,
+                                                    dll);
     SB_LAUNCH_CHECK();
     return 0;
 }
 
 int woodbury_trigger(int B, int K, int m, const double* predvars, const double* phiT, const double* extravar,
-                     int* fired, const int* row_valid, cudaStream_t stream) {
+                     int* fired, const int* row_valid, int segk, long segstride, cudaStream_t stream) {
     SB_CHECK_ARG(B > 0 && m > 0 && K >= 1, "woodbury_trigger: empty batch");
+    if (segk <= 0 || segk >= K) {
+        segk = K;
+        segstride = 0;
+    }
+    SB_CHECK_ARG(K % segk == 0, "woodbury_trigger: k=%d is not a multiple of the segment width %d", K, segk);
     SB_CUDA(cudaMemsetAsync(fired, 0, sizeof(int), stream));
-    woodbury_trigger_kernel<<<B, WT, K * sizeof(double), stream>>>(B, K, m, predvars, phiT, extravar, row_valid, fired);
+    woodbury_trigger_kernel<<<B, WT, K * sizeof(double), stream>>>(B, K, m, predvars, phiT, extravar, row_valid, segk,
+                                                                   segstride, fired);
     SB_LAUNCH_CHECK();
     return 0;
 }

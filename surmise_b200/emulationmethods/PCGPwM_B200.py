@@ -808,6 +808,49 @@ def import_state(theta, pc, gvar_damped, hyps, hypinds, pcti, spc):
     return emulist, fitter.device_state(emulist, spc, pcti)
 
 
+def shard_state(fitinfo):
+    """Turn a REPLICATED device state (every rank fitted or adopted the same emulator) into the owner layout of a
+    fit with factors='owner': each rank of the initialised torch.distributed group keeps a contiguous block of the
+    distinct factors and drops the rest; predict / calibration then run PC-sharded and collectively (SURVEY 8e,
+    "by PC").  No-op on one rank or when the state is sharded already.  Returns fitinfo."""
+    from .. import _dist
+    ops = _ops()
+    torch = ops._torch()
+    st = fitinfo['_b200']
+    comm = _dist.Comm()
+    if comm.world == 1 or st.get('shard') is not None:
+        return fitinfo
+    nf = int(st['Linv'].shape[0])
+    fidx = st['fidx'].cpu().numpy().astype(np.int64)
+    fu = st['fu'].cpu().numpy().astype(np.int64)
+    sizes, starts = _dist.block_partition(nf, comm.world)
+    lo, hi = int(starts[comm.rank]), int(starts[comm.rank + 1])
+    plan = _dist.owner_plan(fidx, starts, comm.rank)
+    pcs = plan['pcs_local']
+    dev = st['Linv'].device
+    sets, fu_local = np.unique(fu[lo:hi], return_inverse=True) if hi > lo else (np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64))
+    sel = torch.from_numpy(pcs).to(dev)
+    local_L = st['Linv'][lo:hi].clone()
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
+    new = dict(st)
+    new['generation'] = next(_GENERATION)
+    new['nf_total'] = nf
+    new['Linv'] = local_L
+    new['local'] = {'theta': st['theta'], 'Linv': local_L, 'pw': st['pw'][sel].contiguous(),
+                    'sig2': st['sig2'][sel].contiguous(), 'nug': st['nug'][sel].contiguous(),
+                    'hypcov': st['hypcov'][torch.from_numpy(sets).to(dev)].contiguous(),
+                    'fu': t(fu_local, torch.int32), 'fidx': t(fidx[pcs] - lo, torch.int32)}
+    new['shard'] = {'world': comm.world, 'rank': comm.rank, 'counts': list(plan['counts']),
+                    'inverse': torch.from_numpy(plan['inverse'].astype(np.int64)).to(dev),
+                    'pcs_local': pcs, 'owner': plan['owner']}
+    for key in ('hypcov', 'fu', 'fidx'):
+        new.pop(key, None)
+    fitinfo['_b200'] = new
+    del st
+    torch.cuda.empty_cache()
+    return fitinfo
+
+
 def adopt(fitinfo):
     """Attach the device state to a `fitinfo` produced by the reference's own PCGPwM.fit (no optimisation).
 

@@ -342,19 +342,27 @@ def woodbury_trigger(consts, pvar, row_valid=None):
     B, K = pvar.shape
     fired = torch.empty(1, dtype=torch.int32, device=pvar.device)
     check(lib.sb200_woodbury_trigger(B, K, consts['phiT'].shape[1], _ptr(pvar), _ptr(consts['phiT']),
-                                     _ptr(consts['extravar']), _ptr(fired), _ptr(row_valid), _stream(torch)), 'sb200_woodbury_trigger')
+                                     _ptr(consts['extravar']), _ptr(fired), _ptr(row_valid), 0, 0, _stream(torch)),
+          'sb200_woodbury_trigger')
     return fired
 
 
-def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1, out=None, row_valid=None):
+def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1, out=None, row_valid=None, segments=None):
     """Batched directbayeswoodbury log-likelihood (+ gradient) (dbw.py:261-383).
 
     consts: dict of device tensors phiT (k,m), resid0 (m), extravar (m), sinv (2,m), G (2,k,k).
+    row_valid: optional int32 (B,) mask of the rows that take part in the batch-wide variance test.
+    segments: None for dense (B,k) inputs, or (seg_k, seg_stride) when pv / pvar / dpv / dpvar are the FIRST blocks
+    (B, seg_k[, d]) of an all-gathered PC-sharded prediction whose blocks lie seg_stride doubles apart; k is then
+    consts['phiT'].shape[0] (see include/surmise_b200.h).
     Returns device tensors ll (B,), dll (B,d) or None, fired (int32 scalar tensor).
     """
     torch = _torch()
     _need_cuda(pv, pvar, consts['phiT'])
     B, K = pv.shape
+    seg_k, seg_stride = (0, 0) if segments is None else segments
+    if segments is not None:
+        K = consts['phiT'].shape[0]
     m = consts['phiT'].shape[1]
     want_grad = dpv is not None
     d = dpv.shape[2] if want_grad else 1
@@ -368,8 +376,22 @@ def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1, out=None
     check(lib.sb200_woodbury_loglik(B, K, m, d, _ptr(pv), _ptr(pvar), _ptr(dpv), _ptr(dpvar), _ptr(consts['phiT']),
                                     _ptr(consts['resid0']), _ptr(consts['extravar']), _ptr(consts['sinv']),
                                     _ptr(consts['G']), int(want_grad), int(variant), _ptr(ll), _ptr(dll), _ptr(fired),
-                                    _ptr(row_valid), _stream(torch)), 'sb200_woodbury_loglik')
+                                    _ptr(row_valid), int(seg_k), int(seg_stride), _stream(torch)), 'sb200_woodbury_loglik')
     return ll, dll, fired
+
+
+def ptlmc_step(state, mode, ll=None, dll=None):
+    """One launch of the device-resident PT-LMC step (PTLMC.py:203-273; see include/surmise_b200.h).
+
+    state: dict built by utilitiesmethods.PTLMC_B200 -- device tensors thetac, fval, dfval, thetap, z, adjrho, temps, lo,
+    hi, hc, cov0, scal, kstep, save, valid and the ints B, d, numtemps, tune, nsave, seed, plus taracc."""
+    torch = _torch()
+    s = state
+    check(lib.sb200_ptlmc_step(s['B'], s['d'], s['numtemps'], s['tune'], s['nsave'], int(mode), int(s['seed']),
+                               float(s['taracc']), _ptr(s['thetac']), _ptr(s['fval']), _ptr(s['dfval']), _ptr(s['thetap']),
+                               _ptr(s['z']), _ptr(s['adjrho']), _ptr(ll), _ptr(dll), _ptr(s['temps']), _ptr(s['lo']),
+                               _ptr(s['hi']), _ptr(s['hc']), _ptr(s['cov0']), _ptr(s['scal']), _ptr(s['kstep']),
+                               _ptr(s['save']), _ptr(s['valid']), _stream(torch)), 'sb200_ptlmc_step')
 
 
 # ----------------------------------------------------------------------------------------------

@@ -191,9 +191,80 @@ def _preoptimise_steps(theta0, value_and_grad, cen, sca, lo, hi, kicks, out, Cor
     return out
 
 
+def _device_chain(dl, thetac, fval, dfval, temps, cov0, hc, numtemps, numchain, tune, sampperchain, taracc,
+                  steps_per_graph=25):
+    """The main loop of the sampler (PTLMC.py:203-257) without leaving the GPU.
+
+    dl: the closure's DeviceLogpost (prior box + fixed-buffer likelihood evaluation).  Per MCMC step the stream sees
+    predict -> Woodbury -> ONE single-CTA kernel (accept, 5 B exchange proposals, adaptation or save, next Langevin
+    proposal); `steps_per_graph` consecutive steps are captured once as a CUDA graph and replayed, so the host issues
+    one launch per 25 steps and synchronises once at the end.  Returns the kept draws (numchain, sampperchain, d) and
+    a dict of statistics, or None when the device loop cannot run (population too large for one CTA's shared memory)."""
+    from .. import ops, _lib
+    torch = ops._torch()
+    B, d = thetac.shape
+    lo, hi = dl.box
+    ev = dl.evaluator(B, d)
+    dev = ev.thetap.device
+    t64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2 ** 31 + int(np.random.randint(0, 2 ** 31 - 1))
+    tau0 = -1.0
+    rho0 = 2 * (1 + np.tanh(tau0))
+    st = {'B': B, 'd': d, 'numtemps': numtemps, 'tune': tune, 'nsave': sampperchain, 'seed': seed, 'taracc': taracc,
+          'thetac': t64(thetac), 'fval': t64(np.squeeze(fval)), 'dfval': t64(dfval), 'thetap': ev.thetap,
+          'z': torch.zeros((B, d), dtype=torch.float64, device=dev), 'adjrho': t64(np.squeeze(rho0 * temps ** (1 / 3))),
+          'temps': t64(np.squeeze(temps)), 'lo': t64(lo), 'hi': t64(hi), 'hc': t64(hc), 'cov0': t64(cov0),
+          'scal': t64(np.array([tau0, 0.0, 0.0, 0.0, rho0, 0.0, 0.0, 0.0])),
+          'kstep': torch.zeros(1, dtype=torch.int64, device=dev),
+          'save': torch.zeros((numchain, sampperchain, d), dtype=torch.float64, device=dev), 'valid': ev.valid}
+    total = tune + sampperchain
+
+    def one_step():
+        ev.launch()
+        ops.ptlmc_step(st, 3, ev.ll, ev.dll)
+    try:
+        ops.ptlmc_step(st, 2)                                 # proposal of step 0
+    except _lib.SurmiseB200Error:
+        return None
+    done, graph, used_graph = 0, None, False
+    if total - 1 >= 3 * steps_per_graph:
+        one_step()                                            # warm-up outside capture: workspaces, attributes, NCCL
+        done = 1
+        try:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for _ in range(steps_per_graph):
+                    one_step()                                # recorded, not executed: the replays below run them
+        except Exception:                                     # capture unavailable (e.g. a collective that cannot be
+            graph = None                                      # captured): same launches, issued eagerly
+            torch.cuda.synchronize()
+    while total - 1 - done > 0:
+        if graph is not None and total - 1 - done >= steps_per_graph:
+            graph.replay()
+            done += steps_per_graph
+            used_graph = True
+        else:
+            one_step()
+            done += 1
+    ev.launch()                                               # likelihood of the last proposal
+    ops.ptlmc_step(st, 1, ev.ll, ev.dll)
+    save, scal = ops.to_host([st['save'], st['scal']])
+    stats = {'theta_evaluated_on_device': total * B, 'mcmc_steps': total, 'cuda_graph': used_graph,
+             'steps_per_graph': steps_per_graph if used_graph else 0, 'accept_rate': float(scal[2] / (total * B)),
+             'swap_rate': float(scal[3] / (5 * B * total)), 'final_rho': float(scal[4]),
+             'outside_box_rate': float(scal[5] / (total * B)), 'seed': seed}
+    return save, stats
+
+
 def sampler(logpostfunc, draw_func, theta0=None, numsamp=2000, numtemps=32, numchain=16, sampperchain=400,
-            maxtemp=30, **ptlmc_options):
-    """Parallel-tempering ensemble MCMC with Langevin proposals; returns {'theta': (numsamp, d), 'logpost': ...}."""
+            maxtemp=30, device_resident='auto', **ptlmc_options):
+    """Parallel-tempering ensemble MCMC with Langevin proposals; returns {'theta': (numsamp, d), 'logpost': ...}.
+
+    device_resident: 'auto' (default) -- when the closure comes from directbayeswoodbury_B200 and its prior declares a
+    box (`thetaprior.box = (lo, hi)`: uniform inside, -inf outside), the main loop runs entirely on the GPU
+    (_device_chain); otherwise, or with False, the host loop below calls the closure once per step (any Python prior).
+    The two loops are the same algorithm with different random-number streams."""
     if theta0 is None or theta0.shape[0] < 10 * theta0.shape[1]:
         theta0 = draw_func(1000)
     theta0 = np.array(theta0, dtype=np.float64)
@@ -247,6 +318,21 @@ def sampler(logpostfunc, draw_func, theta0=None, numsamp=2000, numtemps=32, numc
         hc = V @ np.diag(np.sqrt(W)) @ V.T
     else:
         hc = np.sqrt(cov0)
+    dl = getattr(logpostfunc, 'b200', None)
+    if (device_resident and has_grad and dl is not None and dl.box is not None and dl.box[0].shape[0] == d
+            and np.all(np.isfinite(fval)) and np.all(np.isfinite(dfval))):
+        # the box prior is constant inside: it cancels in every acceptance ratio, so the device chain carries the
+        # log-likelihood alone (the constant is removed from the starting values)
+        prior0 = np.asarray(dl.prior.lpdf(thetac), dtype=np.float64).reshape(-1, 1)
+        if np.all(np.isfinite(prior0)):
+            res = _device_chain(dl, thetac, fval - prior0 / temps, dfval, temps, cov0, hc, numtemps, numchain, tune,
+                                sampperchain, taracc)
+            if res is not None:
+                save, stats = res
+                dl.record(**stats)
+                flat = save.reshape(-1, d)
+                theta = flat[np.random.choice(flat.shape[0], size=numsamp)]
+                return {'theta': theta, 'logpost': value_only(theta)}
     tau = -1.0
     rho = 2 * (1 + np.tanh(tau))
     adjrho = rho * temps ** (1 / 3)
