@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(ST) ptlmc_step_kernel(
     double* s_logu = s_rho + B;              // 5B
     double* s_th = s_logu + 5 * B;           // B*d staging for the permutation
     double* s_df = s_th + (size_t)B * d;     // B*d
-    double* s_red = s_df + (size_t)B * d;    // 32
-    int* s_ord = (int*)(s_red + 32);         // B
+    double* s_red = s_df + (size_t)B * d;    // 32 for block_sum + 2 scalars
+    int* s_ord = (int*)(s_red + 34);         // B
     int* s_rt = s_ord + B;                   // 5B
     const int tid = threadIdx.x;
     const Philox rng(seed);
@@ -159,16 +159,15 @@ __global__ void __launch_bounds__(ST) ptlmc_step_kernel(
         __syncthreads();
         // ---- adaptation while tuning / save afterwards (PTLMC.py:247-257) ----
         if (k < tune && k % 10 == 0) {
-            __shared__ double s_rho_new;
             if (tid == 0) {
                 const double tau = scal[0] + (scal[1] / 10.0 - taracc) / sqrt(1.0 + (double)k / 10.0);
                 scal[0] = tau;
                 scal[1] = 0.0;
-                s_rho_new = 2.0 * (1.0 + tanh(tau));
-                scal[4] = s_rho_new;
+                s_red[32] = 2.0 * (1.0 + tanh(tau));
+                scal[4] = s_red[32];
             }
             __syncthreads();
-            for (int b = tid; b < B; b += ST) adjrho[b] = s_rho_new * cbrt(temps[b]);
+            for (int b = tid; b < B; b += ST) adjrho[b] = s_red[32] * cbrt(temps[b]);
         } else if (k >= tune && k - tune < nsave) {
             const int nc = B - numtemps;
             for (int idx = tid; idx < nc * d; idx += ST) {
@@ -219,7 +218,7 @@ __global__ void __launch_bounds__(ST) ptlmc_step_kernel(
 }  // namespace
 
 size_t ptlmc_step_smem(int B, int d) {
-    return (size_t)(2 * d * d + B + B + 5 * B + 2 * (size_t)B * d + 32) * sizeof(double) + (size_t)(B + 5 * B) * sizeof(int);
+    return (size_t)(2 * d * d + B + B + 5 * B + 2 * (size_t)B * d + 34) * sizeof(double) + (size_t)(B + 5 * B) * sizeof(int);
 }
 
 int ptlmc_step(int B, int d, int numtemps, int tune, int nsave, int mode, unsigned long long seed, double taracc,
@@ -229,10 +228,10 @@ int ptlmc_step(int B, int d, int numtemps, int tune, int nsave, int mode, unsign
     SB_CHECK_ARG(B >= 2 && d >= 1 && d <= MAXD, "ptlmc_step: B=%d d=%d outside the supported range", B, d);
     SB_CHECK_ARG(numtemps >= 0 && numtemps < B && tune >= 0 && nsave >= 0, "ptlmc_step: bad ladder / schedule");
     const size_t smem = ptlmc_step_smem(B, d);
-    SB_CHECK_ARG(smem <= 227 * 1024, "ptlmc_step: a population of %d chains (d=%d) needs %zu B of shared memory", B, d, smem);
+    SB_CHECK_ARG(smem <= 200 * 1024, "ptlmc_step: a population of %d chains (d=%d) needs %zu B of shared memory", B, d, smem);
     static DeviceOnce once;
     SB_TRY(once.run([&]() -> int {
-        SB_CUDA(cudaFuncSetAttribute(ptlmc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SB_CUDA(cudaFuncSetAttribute(ptlmc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         return 0;
     }));
     ptlmc_step_kernel<<<1, ST, smem, stream>>>(B, d, numtemps, tune, nsave, mode, seed, taracc, thetac, fval, dfval, thetap,
