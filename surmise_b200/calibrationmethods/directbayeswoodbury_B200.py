@@ -360,6 +360,11 @@ def fit(fitinfo, emu, x, y, **bayeswoodbury_args):
     """Posterior sampling with surmise's own sampler plugins (dbw.py:7-163)."""
     try:
         from surmise.utilities import sampler        # the reference's dispatcher, used unmodified
+        import sys
+        from .. import UTILITIES_METHODS, register
+        name = bayeswoodbury_args.get('sampler')
+        if name in UTILITIES_METHODS and 'surmise.utilitiesmethods.' + name not in sys.modules:
+            register()                               # our sampler plugins, asked for before register() was called
     except ImportError:
         from ..utilities import sampler              # same contract, for installations without surmise
     if 'shard_theta' in bayeswoodbury_args:          # our options, not sampler options

@@ -22,6 +22,12 @@ __device__ __forceinline__ long seg_at(int b, int a, int segk, long segstride) {
     return (long)(a / segk) * segstride + (long)b * segk + (a % segk);
 }
 
+// Entry i of the d-vector of component a of proposal b in a segmented (B, K, d) table: the segment offset counts
+// doubles (it is the same block stride as for the scalar tables), only the position inside a block scales with d.
+__device__ __forceinline__ long seg_at_d(int b, int a, int i, int d, int segk, long segstride) {
+    return (long)(a / segk) * segstride + ((long)b * segk + (a % segk)) * d + i;
+}
+
 __global__ void __launch_bounds__(WT) woodbury_trigger_kernel(int B, int K, int m, const double* __restrict__ predvars,
                                                               const double* __restrict__ phiT,
                                                               const double* __restrict__ extravar,
@@ -164,10 +170,10 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
     for (int i = 0; i < d; i++) {
         double val = 0.0;
         for (int a = tid; a < K; a += WT) {
-            double dpa = dpv[seg_at(b, a, segk, segstride) * d + i];
-            double dD = 0.5 * dpvar[seg_at(b, a, segk, segstride) * d + i] / D[a];
+            double dpa = dpv[seg_at_d(b, a, i, d, segk, segstride)];
+            double dD = 0.5 * dpvar[seg_at_d(b, a, i, d, segk, segstride)] / D[a];
             double gd = 0.0;
-            for (int c = 0; c < K; c++) gd += G[a * K + c] * dpv[seg_at(b, c, segk, segstride) * d + i];
+            for (int c = 0; c < K; c++) gd += G[a * K + c] * dpv[seg_at_d(b, c, i, d, segk, segstride)];
             double dJ2 = -D[a] * gd + dD * q[a];
             // -1/2 dterm3 - 1/2 (dterm1 - dterm2), term by term (dbw.py:344-381 in k-space)
             val += -dD * Nv[a] + q[a] * dpa + dJ2 * J3[a] - dD * J3[a] * MJ3[a];

@@ -302,6 +302,52 @@ def test_woodbury_kernel_isolated(ops, golden):
         assert e_l < 1e-9 and e_d < 1e-8
 
 
+@pytest.mark.parametrize('world', [2, 3])
+def test_woodbury_segmented_layout_equals_dense(ops, golden, world):
+    """The layout an all-gather of PC-sharded predictions produces (one (B, kmax[, d]) block per rank, padded
+    components with predvar 1 and zero loadings) gives the dense result bit for bit in ll and to rounding in dll."""
+    import torch
+    g = golden('emu_c1')
+    phi = g['st_pcti'] * g['st_scale'][:, None]
+    yv, ev = g['yvar'], g['st_extravar']
+    sinv = np.stack([1 / yv, 1 / (yv + np.abs(ev))])
+    G = np.stack([phi.T @ (phi * s[:, None]) for s in sinv])
+    consts = {'phiT': dev(phi.T.copy()), 'resid0': dev(g['y'] - g['st_offset']), 'extravar': dev(ev),
+              'sinv': dev(sinv), 'G': dev(G)}
+    pv, pvar, dpv, dpvar = (np.asarray(g[k]) for k in ('predvecs', 'predvars', 'predvecs_grad', 'predvars_grad'))
+    B, K = pv.shape
+    d = dpv.shape[2]
+    ll0, dll0, _ = ops.woodbury_loglik(consts, dev(pv), dev(pvar), dev(dpv), dev(dpvar), variant=0)
+    counts = [len(c) for c in np.array_split(np.arange(K), world)]
+    kmax = max(counts)
+    chunk = B * kmax * (2 + 2 * d)
+    gathered = np.zeros((world, chunk))
+    pos, o, j = [], B * kmax, 0
+    for r, cnt in enumerate(counts):
+        blk = gathered[r]
+        a, b_, c, e = (blk[:o].reshape(B, kmax), blk[o:2 * o].reshape(B, kmax), blk[2 * o:2 * o + o * d].reshape(B, kmax, d),
+                       blk[2 * o + o * d:].reshape(B, kmax, d))
+        b_[...] = 1.0
+        a[:, :cnt], b_[:, :cnt], c[:, :cnt], e[:, :cnt] = pv[:, j:j + cnt], pvar[:, j:j + cnt], dpv[:, j:j + cnt], dpvar[:, j:j + cnt]
+        pos += [r * kmax + i for i in range(cnt)]
+        j += cnt
+    Kp = world * kmax
+    phiT = np.zeros((Kp, phi.shape[0]))
+    phiT[pos] = phi.T
+    Gp = np.zeros((2, Kp, Kp))
+    Gp[:, np.array(pos)[:, None], np.array(pos)[None, :]] = G
+    gt = dev(gathered.reshape(-1))
+    blk0 = gt[:chunk]
+    views = (blk0[:o].view(B, kmax), blk0[o:2 * o].view(B, kmax), blk0[2 * o:2 * o + o * d].view(B, kmax, d),
+             blk0[2 * o + o * d:].view(B, kmax, d))
+    ll1, dll1, _ = ops.woodbury_loglik(dict(consts, phiT=dev(phiT), G=dev(Gp)), *views, variant=0, segments=(kmax, chunk))
+    torch.cuda.synchronize()
+    e_l = float(np.max(np.abs((ll1 - ll0).cpu().numpy()) / np.abs(ll0.cpu().numpy())))
+    e_d = rel(dll1.cpu().numpy(), dll0.cpu().numpy())
+    report('woodbury_segmented_w%d' % world, ll=e_l, dll=e_d)
+    assert e_l < 1e-12 and e_d < 1e-10
+
+
 def test_logpost_closure_contract(ops, golden):
     """Shapes / -inf handling of the closure handed to samplers (dbw.py:100-129)."""
     from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
