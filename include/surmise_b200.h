@@ -186,6 +186,27 @@ int sb200_trtri_batched(int batch, int n, const double* L, long lda, long stride
 int sb200_lauum_batched(int batch, int n, const double* Linv, long ldl, long stride_linv, double* C, long ldc,
                         long stride_c, void* stream);
 
+/* Standardisation and PCA stage of PCGPwM (emulationmethods/PCGPwM.py:533-605 __standardizef, 608-654 __PCs).
+ * sb200_pca_col_stats: per column of f (n x m, leading dimension ldf; non-finite cells are missing) offset = nanmean,
+ *   scale = nanstd / sqrt(1 - missing fraction) (PCGPwM.py:553-557) and nmiss = number of missing cells.
+ * sb200_pca_standardize: fs = (f - offset) / scale; with miss != NULL (n x m bytes) the missing mask is written and
+ *   the missing cells get the reference's alternating +2 / -2 seed minus its mean, in row order (PCGPwM.py:565-571).
+ * sb200_pca_sumsq: out[0] = sum of squares of `count` doubles (deterministic); scratch holds 1024 doubles.
+ * sb200_syevj_batched: eigen-decomposition of `batch` symmetric p x p matrices, p <= sb200_syevj_max_p() (112), by
+ *   cyclic Jacobi with one CTA per matrix (matrix and vectors in shared memory): W (p) descending, the columns of
+ *   Z (p x p, ldz) the eigenvectors; sweeps (batch, may be NULL) = sweeps used.  With sb200_dgemm it forms the block
+ *   subspace iteration (orthonormalisation + Rayleigh-Ritz) that replaces the reference's full SVD of fs', of which
+ *   only the components with S^2 > epsilonPC are ever used (PCGPwM.py:575-577, 589-591, 620-622). */
+size_t sb200_pca_col_stats_workspace(int n, int m);
+int sb200_pca_col_stats(int n, int m, const double* f, long ldf, double* offset, double* scale, int* nmiss,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int sb200_pca_standardize(int n, int m, const double* f, long ldf, const double* offset, const double* scale,
+                          double* fs, long ldfs, unsigned char* miss, const int* nmiss, void* stream);
+int sb200_pca_sumsq(long count, const double* x, double* out, double* scratch, void* stream);
+int sb200_syevj_max_p(void);
+int sb200_syevj_batched(int batch, int p, const double* H, long ldh, long stride_h, double* W, long stride_w,
+                        double* Z, long ldz, long stride_z, int max_sweeps, int* sweeps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,12 @@ SIGNATURES = {
     'sb200_debug_panel_stamps': (None, [_p]),
     'sb200_trtri_batched': (_i, [_i, _i, _p, _l, _l, _p, _l, _l, _p, _z, _p]),
     'sb200_lauum_batched': (_i, [_i, _i, _p, _l, _l, _p, _l, _l, _p]),
+    'sb200_pca_col_stats_workspace': (_z, [_i, _i]),
+    'sb200_pca_col_stats': (_i, [_i, _i, _p, _l, _p, _p, _p, _p, _z, _p]),
+    'sb200_pca_standardize': (_i, [_i, _i, _p, _l, _p, _p, _p, _l, _p, _p, _p]),
+    'sb200_pca_sumsq': (_i, [_l, _p, _p, _p, _p]),
+    'sb200_syevj_max_p': (_i, []),
+    'sb200_syevj_batched': (_i, [_i, _i, _p, _l, _l, _p, _l, _p, _l, _l, _i, _p, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -1,15 +1,22 @@
-"""Device (torch CUDA) version of the standardisation / imputation / PCA stage of PCGPwM.
+"""Device version of the standardisation / imputation / PCA stage of PCGPwM.
 
 Same mathematics as surmise's PCGPwM.__standardizef / __PCs (emulationmethods/PCGPwM.py:533-654) and as the
-host implementation in _pca.py; SURVEY.md section 8(f) row 2.  This stage is not one of the hand-written
-kernels of the hot path: it is expressed with torch.linalg on the device (library eigensolver / batched solve),
-because with missing data it otherwise dominates the whole fit (config C3: 287 s on the host, 41 SVDs of a
-1000 x 4000 matrix plus 160 k ridge systems).
+host implementation in _pca.py; SURVEY.md section 8(f) row 2.  Everything numerical runs in this package's own kernels
+through the C ABI (include/surmise_b200.h): the column statistics and the scaling (sb200_pca_col_stats /
+sb200_pca_standardize), every dense product (sb200_dgemm, FP64 DMMA), the eigen-decomposition (block subspace
+iteration on sb200_dgemm with the Jacobi kernel sb200_syevj_batched for orthonormalisation and Rayleigh-Ritz) and the
+per-row ridge / Schur systems of the imputation (sb200_spd_solve_small, or the blocked sb200_potrf_batched /
+sb200_trtri_batched beyond its size); torch supplies memory, indexing and elementwise glue.
 
-The reference takes the SVD of fs' (m x n) and only ever uses U and S.  Here U and S^2 come from the symmetric
-eigendecomposition of the m x m Gram matrix fs' fs, which is much cheaper and accurate for every component the
-method keeps (S^2 > epsilonPC; relative eigenvalue error ~ eps * S_max^2 / S_k^2 <= 1e-9).  Singular-vector signs
-are arbitrary in both; nothing downstream depends on them.
+The reference takes the SVD of fs' (m x n) and only ever uses the left singular vectors whose S^2 exceeds epsilonPC
+(PCGPwM.py:575-577, 589-591, 620-622).  Here those come from the m x m Gram matrix G = fs' fs as a CERTIFIED leading
+block: Ritz pairs (X, w) of a p-dimensional subspace with ||G - X diag(w) X'||_F < epsilonPC, which bounds every
+eigenvalue outside the block (Weyl), so the set of components above the threshold is the reference's.  U and S in
+standardpcinfo are that block (m x p, p), not the full m x m basis -- nothing downstream reads more.  If no block of
+at most sb200_syevj_max_p() columns can be certified (a spectrum that does not drop below epsilonPC within 112
+components, e.g. the first imputation sweeps) the full symmetric eigensolver of the CUDA library (torch.linalg.eigh)
+is used for that decomposition and the fact is recorded in standardpcinfo['_eig_path'].
+Singular-vector signs are arbitrary in both implementations; nothing downstream depends on them.
 """
 import numpy as np
 
@@ -19,72 +26,147 @@ def _torch():
     return _lib.require_cuda()
 
 
-def _left_singular(fs, torch):
-    """U (m, m) and S (m,) of fs' (descending), from eigh of the Gram matrix."""
-    lam, U = torch.linalg.eigh(fs.T @ fs)
-    lam = torch.flip(lam, [0])
-    U = torch.flip(U, [1])
-    return U, torch.sqrt(torch.clamp(lam, min=0.0)), lam
+def _ops():
+    from . import ops
+    return ops
 
 
-def _leading_eig(G, V0, eps_pc, torch, steps=2, tol=1e-11):
-    """Eigenpairs of the PSD Gram matrix G above eps_pc from a warm start, or None if that cannot be certified.
-
-    Once the imputation sweeps have settled, only k << m components exceed eps_pc and the basis barely moves from
-    one sweep to the next, so a block power iteration from the previous basis V0 (m, k + pad) plus Rayleigh-Ritz
-    replaces the full m x m eigendecomposition (C3: 13 ms -> 2 ms per sweep).  Two checks make it safe:
-      * trace(G) - sum(Ritz values) bounds the sum of ALL remaining eigenvalues (Ritz values never exceed the true
-        ones); if that is below eps_pc, no component outside the block can pass the threshold;
-      * the residual |G X - X diag(w)| of the kept pairs must be at rounding level.
-    Returns (X_keep (m, k) in descending order, w_keep (k,), X_all for the next warm start) or None."""
-    V = V0
-    for _ in range(steps):
-        V, _r = torch.linalg.qr(G @ V)
-    GV = G @ V
-    w, Q = torch.linalg.eigh(V.T @ GV)
-    w, Q = torch.flip(w, [0]), torch.flip(Q, [1])
-    X = V @ Q
-    if float(torch.trace(G) - w.sum()) >= eps_pc:
-        return None
-    keep = (w - eps_pc) > 0
-    if bool(keep.all()):                                # no Ritz value below the threshold inside the block: widen it
-        return None
-    Xk, wk = X[:, keep], w[keep]
-    resid = torch.linalg.matrix_norm(G @ Xk - Xk * wk) / torch.linalg.matrix_norm(G)
-    if float(resid) > tol:
-        return None
-    return Xk, wk, X
+# ------------------------------------------------------------------------------------------------------------------
+# eigen-decomposition of the Gram matrix
+def _full_eig(G, torch):
+    """All eigenpairs, descending (library fallback, see the module docstring)."""
+    lam, U = torch.linalg.eigh(G)
+    return torch.flip(U, [1]).contiguous(), torch.flip(lam, [0]).contiguous()
 
 
+def _orthonormalise(Y, ops, torch):
+    """Columns of Y -> an orthonormal basis of their span (SVQB: Y Z Lam^-1/2 from the Jacobi eigen-decomposition of
+    the column-scaled Gram matrix; a second pass when the first met a badly conditioned block)."""
+    for _ in range(2):
+        Y = Y / torch.sqrt((Y * Y).sum(0)).clamp_min(1e-300)
+        lam, Z, _s = ops.syevj(ops.mm(Y, Y, ta=True))
+        top = lam[0]
+        Y = ops.mm(Y, Z / torch.sqrt(lam.clamp_min(top * 1e-28)))
+        if float(lam[-1]) > 1e-3 * float(top):
+            break
+    return Y
+
+
+def _leading_block(G, p, warm, eps_pc, ops, torch, max_iter=60):
+    """Ritz pairs of a p-dimensional invariant subspace of the PSD matrix G by block subspace iteration (two products
+    with G per step) with Rayleigh-Ritz.  Returns (X (m,p), w (p) descending, certified) where certified means
+    ||G - X diag(w) X'||_F < eps_pc and the pairs above eps_pc have residuals at rounding level."""
+    m = G.shape[0]
+    gen = torch.Generator(device=G.device)
+    gen.manual_seed(1234567 + p)
+    X = torch.randn((m, p), dtype=torch.float64, device=G.device, generator=gen)
+    if warm is not None:
+        c = min(p, warm.shape[1])
+        X[:, :c] = warm[:, :c]
+    best = None
+    prev = np.inf
+    for it in range(max_iter):
+        Q = _orthonormalise(ops.mm(G, ops.mm(G, X)) if it else ops.mm(G, X), ops, torch)
+        GQ = ops.mm(G, Q)
+        w, Z, _s = ops.syevj(ops.mm(Q, GQ, ta=True))
+        X = ops.mm(Q, Z)
+        R = ops.mm(GQ, Z) - X * w
+        rn = torch.sqrt((R * R).sum(0))
+        keep = w > eps_pc
+        if p < m and bool(keep[-1]):                   # Ritz values never exceed the eigenvalues they approximate: the
+            return X, w, False                         # p-th eigenvalue is above the threshold, the block is too small
+        top = float(w[0])
+        worst = float((rn * keep).max())
+        best = (X, w)
+        if worst <= 1e-13 * top:
+            break
+        if worst <= 1e-10 * top and worst > 0.5 * prev:       # stagnated at rounding level
+            break
+        prev = worst
+    else:
+        return X, w, False
+    E = ops.mm(X * w, X, tb=True, alpha=-1.0, beta=1.0, out=G.clone())
+    return best[0], best[1], bool(float(ops.sumsq(E)) < eps_pc * eps_pc)
+
+
+def _eig_above(G, eps_pc, warm, ops, torch, note):
+    """(U, lam) descending such that every eigenvalue of G above eps_pc is among them (see module docstring)."""
+    m = G.shape[0]
+    cap = min(ops.syevj_max_p(), m)
+    p = min(cap, max(16, warm.shape[1] if warm is not None else 32))
+    while cap >= 2:
+        X, w, ok = _leading_block(G, p, warm, eps_pc, ops, torch)
+        if ok:
+            note['subspace'] = note.get('subspace', 0) + 1
+            return X, w
+        if p >= cap:
+            break
+        warm, p = X, min(cap, (p + max(16, p // 2) + 7) // 8 * 8)
+    note['library_eigh'] = note.get('library_eigh', 0) + 1
+    return _full_eig(G, torch)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# batched small SPD systems of the imputation
 _CHUNK_BYTES = 8 << 30      # bound on the temporaries of one row chunk (early imputation sweeps keep k ~ m PCs)
 
 
-def _row_chunks(nrows, m, k):
-    per_row = 8 * k * max(m, 3 * k)
-    step = max(1, min(nrows, _CHUNK_BYTES // max(per_row, 1)))
+def _spd_inverse(A, ops, torch):
+    """Inverses of a batch (c, q, q) of symmetric positive definite matrices (full symmetric), on our own kernels."""
+    c, q, _ = A.shape
+    if q <= ops.small_max_n():                       # register-resident sweep kernel
+        lda = (q + 7) // 8 * 8
+        W = torch.zeros((c, q + 1, lda), dtype=A.dtype, device=A.device)
+        W[:, :q, :q] = A
+        info = ops.spd_solve_small(W, q)
+        low = W[:, :q, :q]
+    else:                                            # blocked Cholesky / triangular inverse / L^-T L^-1 on the DMMA GEMM
+        lda = (q + 7) // 8 * 8
+        W = torch.zeros((c, q, lda), dtype=A.dtype, device=A.device)
+        W[:, :, :q] = A
+        Linv, info = ops.potrf_batched(W, q, q)
+        ops.trtri_batched(W, Linv, q)
+        low = ops.lauum_batched(Linv, q)[:, :, :q]
+    if bool((info != 0).any()):
+        raise ValueError('imputation: a ridge system of the missing entries is not positive definite')
+    low = torch.tril(low)
+    return low + torch.tril(low, -1).transpose(1, 2)
+
+
+def _batch_cap(q, ops):
+    """Largest batch one call of the batched solvers takes (grid limits of the blocked path beyond the sweep kernel)."""
+    return 60000 if q <= ops.small_max_n() else 8000
+
+
+def _row_chunks(nrows, m, k, ops):
+    per_row = 8 * k * max(m, 4 * k)
+    step = max(1, min(nrows, _batch_cap(k, ops), _CHUNK_BYTES // max(per_row, 1)))
     return [(s, min(s + step, nrows)) for s in range(0, nrows, step)]
 
 
-def _ridge_rows(basis, obs, cur, diag_add, torch, want_qih=False):
+def _ridge_rows(basis, obs, cur, diag_add, ops, torch, want_qih=False):
     """Per row r: H = basis' diag(obs_r) basis, J = basis' (obs_r * cur_r), sol = (H + diag_add)^-1 J.
 
     Returns vec = J - H sol  (nr, k) and, if want_qih, term3 = diag(H) - sum_a H_ab [(H + diag_add)^-1 H]_ab.
-    Rows are processed in chunks so the (chunk, k, k) temporaries stay below _CHUNK_BYTES."""
+    The masked Gram matrices of all rows of a chunk are ONE product obs (c, m) x [basis_a basis_b] (m, k^2)."""
     nr, m = obs.shape
     k = basis.shape[1]
     vec = torch.empty((nr, k), dtype=torch.float64, device=basis.device)
     term3 = torch.empty((nr, k), dtype=torch.float64, device=basis.device) if want_qih else None
     D = torch.diag(diag_add)
-    for lo, hi in _row_chunks(nr, m, k):
-        o = obs[lo:hi]
-        H = torch.matmul((basis.unsqueeze(0) * o.unsqueeze(2)).transpose(1, 2), basis)    # (c, k, k)
-        J = (o * cur[lo:hi]) @ basis
-        A = H + D
-        sol = torch.linalg.solve(A, J.unsqueeze(2)).squeeze(2)
-        vec[lo:hi] = J - torch.einsum('rab,rb->ra', H, sol)
+    outer = (basis[:, :, None] * basis[:, None, :]).reshape(m, k * k).contiguous()
+    for lo, hi in _row_chunks(nr, m, k, ops):
+        o = obs[lo:hi].contiguous()
+        c = hi - lo
+        H = ops.mm(o, outer).view(c, k, k)
+        J = ops.mm((o * cur[lo:hi]).contiguous(), basis)
+        Ainv = _spd_inverse(H + D, ops, torch)
+        sol = (Ainv * J[:, None, :]).sum(2)
+        vec[lo:hi] = J - (H * sol[:, None, :]).sum(2)
         if want_qih:
-            QiH = torch.linalg.solve(A, H)
-            term3[lo:hi] = torch.diagonal(H, dim1=1, dim2=2) - torch.einsum('rab,rab->rb', H, QiH)
+            QiH = torch.empty_like(H)
+            ops.dgemm(Ainv, H, QiH, True, False, k, k, k, batch=c, strides=(k * k, k * k, k * k), lds=(k, k, k))
+            term3[lo:hi] = torch.diagonal(H, dim1=1, dim2=2) - (H * QiH).sum(1)
     return vec, term3
 
 
@@ -98,7 +180,7 @@ def _missing_index(miss, torch):
     return idx, valid
 
 
-def _impute_schur(Up, sp2, eps_impute, cur, obs, idx, valid, torch):
+def _impute_schur(Up, sp2, eps_impute, cur, obs, idx, valid, ops, torch):
     """The ridge update of the missing entries (PCGPwM.py:576-586) through the |missing| x |missing| system.
 
     The reference solves, per row, the k x k system (H + D) sol = J with H = Up' diag(obs) Up, D = diag(eps / sp2),
@@ -108,15 +190,14 @@ def _impute_schur(Up, sp2, eps_impute, cur, obs, idx, valid, torch):
     all rows plus a batched Cholesky of size |missing| instead of size k.  Early sweeps keep k ~ m components
     (k^3 per row); |missing| is the missing fraction of m.  Returns the filled values, (nr, qmax), 0 where padded."""
     lam_inv = sp2 / (sp2 + eps_impute)
-    P = (Up * lam_inv) @ Up.T
-    Z = (obs * cur) @ P                                            # (nr, m): P_{.,o} cur_o for every column
+    P = ops.mm((Up * lam_inv).contiguous(), Up.contiguous(), tb=True)
+    Z = ops.mm((obs * cur).contiguous(), P)                        # (nr, m): P_{.,o} cur_o for every column
     z = torch.gather(Z, 1, idx) * valid
     nr, qmax = idx.shape
     w = torch.zeros_like(z)
     eye = torch.eye(qmax, dtype=Up.dtype, device=Up.device)
-    per_row = 8 * qmax * qmax * 3
-    step = max(1, min(nr, _CHUNK_BYTES // max(per_row, 1)))
-    from . import ops
+    per_row = 8 * qmax * qmax * 4
+    step = max(1, min(nr, _batch_cap(qmax, ops), _CHUNK_BYTES // max(per_row, 1)))
     small = qmax <= ops.small_max_n()                 # the register-resident sweep kernel solves these directly
     for lo in range(0, nr, step):
         hi = min(lo + step, nr)
@@ -134,73 +215,77 @@ def _impute_schur(Up, sp2, eps_impute, cur, obs, idx, valid, torch):
                 raise ValueError('imputation: a Schur system of the missing entries is not positive definite')
             w[lo:hi] = A[:, qmax, :qmax]
         else:
-            L = torch.linalg.cholesky(S)
-            w[lo:hi] = torch.cholesky_solve(z[lo:hi, :, None], L).squeeze(2)
+            w[lo:hi] = (_spd_inverse(S, ops, torch) * z[lo:hi, None, :]).sum(2)
     return w * valid
 
 
+# ------------------------------------------------------------------------------------------------------------------
+def _upload(f_np, torch, dev):
+    """(n, m) host matrix -> contiguous device tensor; a transposed view of a C-contiguous (m, n) array (what
+    PCGPwM_B200.fit holds) is copied as it lies in memory and transposed on the device."""
+    if f_np.flags.c_contiguous:
+        return torch.from_numpy(f_np).to(dev)
+    if f_np.T.flags.c_contiguous:
+        return torch.from_numpy(f_np.T).to(dev).T.contiguous()
+    return torch.from_numpy(np.ascontiguousarray(f_np)).to(dev)
+
+
 def standardize(f, eps_pc, eps_impute, n_iter=40):
-    """f: (n, m) numpy with NaN/inf for missing.  Returns (standardpcinfo of numpy arrays, mof, mofrows)."""
+    """f: (n, m) numpy with NaN/inf for missing.  Returns (standardpcinfo, mof, mofrows); fs / U / S / _lam are device
+    tensors until principal_components() converts them."""
     torch = _torch()
+    ops = _ops()
     dev = torch.device('cuda', torch.cuda.current_device())
     f_np = np.asarray(f, dtype=np.float64)
-    mof_np = ~np.isfinite(f_np)
-    any_missing = bool(mof_np.any())
-    # offset / scale exactly as the reference computes them (PCGPwM.py:553-557), on the host: O(n m)
-    if any_missing:
-        offset_np = np.nanmean(f_np, axis=0)
-        scale_np = np.nanstd(f_np, axis=0) / np.sqrt(1 - np.isnan(f_np).mean(axis=0))
-    else:                           # same bits as the nan-versions on complete data, three times faster (C4: 0.2 s)
-        offset_np = np.mean(f_np, axis=0)
-        scale_np = np.std(f_np, axis=0)
-    if np.any(scale_np == 0):
+    fd = _upload(f_np, torch, dev)
+    offset, scale, nmiss = ops.col_stats(fd)                       # PCGPwM.py:553-557
+    any_missing = bool(nmiss.sum().item() > 0)
+    if bool((scale == 0).any()):
         raise ValueError("You have a row that is non-varying.")
-    fs_np = (f_np - offset_np) / scale_np
-    mofrows_np = None
+    fs, miss_all = ops.standardize(fd, offset, scale, nmiss, want_mask=any_missing)    # + seed, PCGPwM.py:565-571
+    del fd
+    note = {}
+    mof_np = mofrows_np = None
     if any_missing:
-        mofrows_np = np.where(mof_np.any(axis=1))[0]
-        # initial fill +2, -2, +2, ... minus its mean, in row order within each column (PCGPwM.py:565-571)
-        rank = np.cumsum(mof_np, axis=0) - 1
-        alt = np.where(rank % 2 == 0, 2.0, -2.0)
-        cnt = mof_np.sum(axis=0)
-        col_mean = np.where(cnt > 0, (alt * mof_np).sum(axis=0) / np.maximum(cnt, 1), 0.0)
-        fs_np = np.where(mof_np, alt - col_mean, fs_np)
-    fs = torch.from_numpy(np.ascontiguousarray(fs_np)).to(dev)
-    if any_missing:
-        rows = torch.from_numpy(mofrows_np).to(dev)
-        miss = torch.from_numpy(mof_np[mofrows_np]).to(dev)
+        rows = torch.nonzero(miss_all.any(dim=1)).squeeze(1)
+        miss = miss_all[rows].bool()
         obs = (~miss).to(torch.float64)
         idx, valid = _missing_index(miss, torch)
         warm, pad = None, 8
-        for _ in range(n_iter):                                   # PCGPwM.py:573-587
-            lead = None
-            if warm is not None and warm.shape[1] <= fs.shape[1] // 4:
-                lead = _leading_eig(fs.T @ fs, warm, eps_pc, torch)
-            if lead is not None:
-                Up, lam_keep, warm = lead
-                sp2 = lam_keep - eps_pc
-            else:
-                U, _S, lam = _left_singular(fs, torch)
-                keep = (lam - eps_pc) > 0
-                Up = U[:, keep]
-                sp2 = lam[keep] - eps_pc
-                nk = int(keep.sum().item())
-                warm = U[:, :min(nk + pad, U.shape[1])]
+        cap = ops.syevj_max_p()
+        for sweep in range(n_iter):                               # PCGPwM.py:573-587
+            G = ops.mm(fs, fs, ta=True)
+            if warm is not None or sweep == 0:
+                U, lam = _eig_above(G, eps_pc, warm, ops, torch, note)
+            else:                                                 # the last sweep kept more components than a block holds
+                U, lam = _full_eig(G, torch)
+                note['library_eigh'] = note.get('library_eigh', 0) + 1
+            keep = (lam - eps_pc) > 0
+            Up = U[:, keep].contiguous()
+            sp2 = lam[keep] - eps_pc
+            nk = int(Up.shape[1])
+            warm = U[:, :min(nk + pad, U.shape[1])] if nk + pad <= cap else None
             cur = fs[rows]
-            if Up.shape[1] > idx.shape[1]:                        # more components than missing entries per row
-                w = _impute_schur(Up, sp2, eps_impute, cur, obs, idx, valid, torch)
+            if nk > idx.shape[1]:                                 # more components than missing entries per row
+                w = _impute_schur(Up, sp2, eps_impute, cur, obs, idx, valid, ops, torch)
                 filled = cur.scatter(1, idx, torch.where(valid, w, torch.gather(cur, 1, idx)))
                 fs[rows] = filled
             else:
-                vec, _ = _ridge_rows(Up, obs, cur, eps_impute / sp2, torch)
-                filled = vec @ (Up * (sp2 / eps_impute)).T
+                vec, _ = _ridge_rows(Up, obs, cur, eps_impute / sp2, ops, torch)
+                filled = ops.mm(vec, (Up * (sp2 / eps_impute)).contiguous(), tb=True)
                 fs[rows] = torch.where(miss, filled, cur)
-    U, S, lam = _left_singular(fs, torch)
-    Up = U[:, (lam - eps_pc) > 0]
-    resid = fs - (fs @ Up) @ Up.T
+        mof_np = miss_all.cpu().numpy().astype(bool)
+        mofrows_np = rows.cpu().numpy()
+        U, lam = _eig_above(ops.mm(fs, fs, ta=True), eps_pc, warm, ops, torch, note)
+    else:
+        U, lam = _eig_above(ops.mm(fs, fs, ta=True), eps_pc, None, ops, torch, note)
+    Up = U[:, (lam - eps_pc) > 0].contiguous()
+    resid = fs - ops.mm(ops.mm(fs, Up), Up, tb=True)
+    offset_np, scale_np = offset.cpu().numpy(), scale.cpu().numpy()
     extravar = (resid ** 2).mean(0).cpu().numpy() * scale_np ** 2   # PCGPwM.py:594
-    info = {'offset': offset_np, 'scale': scale_np, 'fs': fs, 'U': U, 'S': S, 'extravar': extravar, '_lam': lam}
-    return info, (mof_np if any_missing else None), mofrows_np
+    info = {'offset': offset_np, 'scale': scale_np, 'fs': fs, 'U': U, 'S': torch.sqrt(torch.clamp(lam, min=0.0)),
+            'extravar': extravar, '_lam': lam, '_eig_path': note}
+    return info, mof_np, mofrows_np
 
 
 def principal_components(spc, mof, mofrows, eps_pc, eps_impute):
@@ -208,23 +293,23 @@ def principal_components(spc, mof, mofrows, eps_pc, eps_impute):
 
     Returns a dict of numpy arrays and converts spc's device tensors to numpy in place."""
     torch = _torch()
+    ops = _ops()
     fs, U, lam = spc['fs'], spc['U'], spc.pop('_lam')
     keep = (lam - eps_pc) > 0
-    basis = U[:, keep]
+    basis = U[:, keep].contiguous()
     pcw = torch.sqrt(lam[keep] - eps_pc)
     pcstdvar = torch.zeros((fs.shape[0], basis.shape[1]), dtype=torch.float64, device=fs.device)
     if mof is not None:
         rows = torch.from_numpy(mofrows).to(fs.device)
         obs = torch.from_numpy(~mof[mofrows]).to(fs.device).to(torch.float64)
         gain = pcw ** 2 / eps_impute + 1
-        vec, term3 = _ridge_rows(basis, obs, fs[rows], eps_impute / pcw ** 2, torch, want_qih=True)
-        fs[rows] = (gain * vec) @ basis.T
+        vec, term3 = _ridge_rows(basis, obs, fs[rows], eps_impute / pcw ** 2, ops, torch, want_qih=True)
+        fs[rows] = ops.mm((gain * vec).contiguous(), basis, tb=True)
         pcstdvar[rows] = 1 - gain * term3
     effn = torch.sum(torch.clamp(1 - pcstdvar, 0, 1))
-    pct = basis * pcw / torch.sqrt(effn)
+    pct = (basis * pcw / torch.sqrt(effn)).contiguous()
     out = {'pcw': pcw, 'pcto': basis.clone(), 'pct': pct, 'pcti': basis * (torch.sqrt(effn) / pcw),
-           'pc': fs @ pct, 'unscaled_pcstdvar': pcstdvar}
-    from . import ops
+           'pc': ops.mm(fs, pct), 'unscaled_pcstdvar': pcstdvar}
     keys = list(out)
     host = ops.to_host([out[k] for k in keys] + [spc[k] for k in ('fs', 'U', 'S')])   # pinned copies, one sync
     out = dict(zip(keys, host[:len(keys)]))

