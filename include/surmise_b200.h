@@ -171,7 +171,9 @@ void sb200_host_tempexchange(const double* lpost, const double* temps, int B, co
  *   4 B lower, 8 B upper (triangular operands must hold zeros in the empty triangle), 16 lower-C only.
  * sb200_potrf_batched: in-place lower Cholesky of `batch` matrices (rows n..mrows-1 are solved as
  *   right-hand sides X <- X L^-T); Linv receives the inverted diagonal blocks and is zeroed elsewhere;
- *   `info` must hold 2*batch ints (first half = result, second half = scratch).
+ *   `info` must hold sb200_potrf_info_ints(batch, mrows) ints (the first `batch` = result, the rest = scratch: arrival
+ *   counters, and the row-progress counters / ticket of the task-graph kernel that factors the whole batch in ONE
+ *   persistent launch -- left-looking 64 x 64 tile tasks, dependencies tracked per tile row).
  * sb200_trtri_batched: completes Linv = L^-1 from the output of sb200_potrf_batched.
  * sb200_lauum_batched: lower triangle of C = Linv' Linv. */
 int sb200_dgemm(int a_kc, int b_kc, int M, int N, int K, double alpha, const double* A, long lda, long stride_a,
@@ -179,8 +181,12 @@ int sb200_dgemm(int a_kc, int b_kc, int M, int N, int K, double alpha, const dou
                 int batch, int flags, int tile, void* stream);
 int sb200_potrf_batched(int batch, int n, int mrows, double* A, long lda, long stride_a, double* Linv, long ldl,
                         long stride_linv, int* info, void* stream);
+size_t sb200_potrf_info_ints(int batch, int mrows);
 size_t sb200_trtri_tmp_elems(int n);
 void sb200_debug_panel_stamps(long long* device_ptr);   /* instrumentation: clock64 stamps of the panel kernel's phases */
+void sb200_debug_dag_stats(long long* device_ptr);      /* instrumentation: per CTA of the task-graph Cholesky, 5 slots
+                                                           [cycles total, waiting on dependencies, in diagonal tasks'
+                                                           factorisation, in off-diagonal tasks' solve, tasks]; NULL = off */
 int sb200_trtri_batched(int batch, int n, const double* L, long lda, long stride_a, double* Linv, long ldl,
                         long stride_linv, double* tmp, size_t tmp_elems_per_matrix, void* stream);
 int sb200_lauum_batched(int batch, int n, const double* Linv, long ldl, long stride_linv, double* C, long ldc,

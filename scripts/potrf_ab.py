@@ -22,5 +22,5 @@ for n, nb in [(2000, 1), (2000, 4), (2000, 20), (4000, 8), (8000, 1), (8000, 8)]
         torch.cuda.synchronize()
         if it:
             best = min(best, e0.elapsed_time(e1))
-    print('fuse=%s n=%d batch=%d  %.3f ms  %.2f TFLOP/s' % (os.environ.get('SB200_PANEL_FUSE', '1'), n, nb, best, nb * n ** 3 / 3 / best / 1e9))
+    print('dag=%s fuse=%s n=%d batch=%d  %.3f ms  %.2f TFLOP/s' % (os.environ.get('SB200_POTRF_DAG', '1'), os.environ.get('SB200_PANEL_FUSE', '1'), n, nb, best, nb * n ** 3 / 3 / best / 1e9))
     del buf, A0

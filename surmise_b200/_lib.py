@@ -49,8 +49,10 @@ SIGNATURES = {
     'sb200_host_tempexchange': (None, [_p, _p, _i, _p, _p, _i, _p]),
     'sb200_dgemm': (_i, [_i, _i, _i, _i, _i, _d, _p, _l, _l, _p, _l, _l, _d, _p, _l, _l, _i, _i, _i, _p]),
     'sb200_potrf_batched': (_i, [_i, _i, _i, _p, _l, _l, _p, _l, _l, _p, _p]),
+    'sb200_potrf_info_ints': (_z, [_i, _i]),
     'sb200_trtri_tmp_elems': (_z, [_i]),
     'sb200_debug_panel_stamps': (None, [_p]),
+    'sb200_debug_dag_stats': (None, [_p]),
     'sb200_trtri_batched': (_i, [_i, _i, _p, _l, _l, _p, _l, _l, _p, _z, _p]),
     'sb200_lauum_batched': (_i, [_i, _i, _p, _l, _l, _p, _l, _l, _p]),
     'sb200_pca_col_stats_workspace': (_z, [_i, _i]),

@@ -231,17 +231,20 @@ int sb200_potrf_batched(int batch, int n, int mrows, double* A, long lda, long s
                         long stride_linv, int* info, void* stream) {
     SB_CHECK_ARG(A && Linv && info, "potrf: NULL pointer");
     SB_CHECK_ARG(ldl >= n && stride_linv >= (long)n * ldl, "potrf: bad Linv layout");
-    SB_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * 2 * batch, ST(stream)));      // [info | scratch counters]
+    SB_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * 2 * batch, ST(stream)));      // [info | panel counters | task graph]
     SB_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * ((size_t)(batch - 1) * stride_linv + (size_t)n * ldl), ST(stream)));
     CholBatch c{};
     c.batch = batch; c.n = n; c.mrows = mrows; c.A = A; c.lda = lda; c.strideA = stride_a; c.info = info;
     c.counters = info + batch;
+    c.dag_scratch = info + 2 * batch;
     c.Dinv = Linv; c.ldd = ldl; c.strideD = stride_linv; c.blockD = (long)CHOL_NB * ldl + CHOL_NB;
     return potrf_batched(c, ST(stream));
 }
 
+size_t sb200_potrf_info_ints(int batch, int mrows) { return 2 * (size_t)batch + potrf_dag_scratch_ints(batch, mrows); }
 size_t sb200_trtri_tmp_elems(int n) { return trtri_tmp_elems(n); }
 void sb200_debug_panel_stamps(long long* device_ptr) { debug_panel_stamps(device_ptr); }
+void sb200_debug_dag_stats(long long* device_ptr) { debug_dag_stats(device_ptr); }
 
 int sb200_trtri_batched(int batch, int n, const double* L, long lda, long stride_a, double* Linv, long ldl,
                         long stride_linv, double* tmp, size_t tmp_elems_per_matrix, void* stream) {

@@ -18,7 +18,15 @@ struct CholBatch {
     long strideD, blockD;
     int* info;        // (batch) 0 = ok, j>0 = leading minor j not positive (LAPACK convention)
     int* counters;    // (batch) zero-initialised scratch: arrival counters of the panel kernel (left at zero)
+    int* dag_scratch; // potrf_dag_scratch_ints(batch, mrows) ints, or NULL: row-progress counters and the ticket of the
+                      //   task-graph kernel (chol_dag.cu); with NULL the recursive multi-launch path is used
 };
+
+// task-graph variant (one persistent launch; chol_dag.cu): same contract as potrf_batched
+size_t potrf_dag_scratch_ints(int batch, int mrows);
+bool potrf_dag_usable(const CholBatch& c);
+int potrf_dag(const CholBatch& c, cudaStream_t stream);
+void debug_dag_stats(long long* device_ptr);     // instrumentation: 5 clock64 counters per CTA (296 CTAs at most)
 
 // A <- L (in place), Dinv filled, extra rows <- rows * L^-T.   ~ n^3/3 + (mrows-n) n^2 flop per matrix
 int potrf_batched(const CholBatch& c, cudaStream_t stream);

@@ -256,6 +256,7 @@ size_t gp_nll_grad_workspace(int batch, int n, int d, int want_grad) {
     w.take<double>((size_t)batch * (n + 1) * lda);
     w.take<double>((size_t)batch);                                  // sig2hat
     w.take<int>((size_t)batch);                                     // panel arrival counters
+    w.take<int>(potrf_dag_scratch_ints(batch, n + 1));
     if (want_grad) {
         w.take<double>((size_t)batch * n * lda);                    // Linv
         w.take<double>((size_t)batch * trtri_tmp_elems(n));
@@ -284,13 +285,14 @@ int gp_nll_grad(int batch, int n, int d, const double* theta, long strideTheta, 
     double* A = w.take<double>((size_t)batch * strideA);
     double* sig2hat = w.take<double>((size_t)batch);
     int* counters = w.take<int>((size_t)batch);
+    int* dag_scratch = w.take<int>(potrf_dag_scratch_ints(batch, n + 1));
     SB_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * batch, stream));
     SB_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, stream));
     SB_TRY(gp_assemble(batch, n, d, theta, strideTheta, g, strideG, gvar, strideGvar, hyp, A, lda, strideA, stream));
 
     CholBatch c{};
     c.batch = batch; c.n = n; c.mrows = n + 1; c.A = A; c.lda = lda; c.strideA = strideA; c.info = info;
-    c.counters = counters;
+    c.counters = counters; c.dag_scratch = dag_scratch;
     double *Linv = nullptr, *tmp = nullptr, *alpha = nullptr, *partial = nullptr;
     const long strideL = (long)n * lda;
     if (want_grad) {
@@ -323,6 +325,7 @@ size_t gp_factorize_workspace(int batch, int n) {
     w.take<double>((size_t)batch * (n + 1) * lda);
     w.take<double>((size_t)batch * trtri_tmp_elems(n));
     w.take<int>((size_t)batch);
+    w.take<int>(potrf_dag_scratch_ints(batch, n + 1));
     return w.off;
 }
 
@@ -340,13 +343,14 @@ int gp_factorize(int batch, int n, int d, const double* theta, long strideTheta,
     double* A = w.take<double>((size_t)batch * strideA);
     double* tmp = w.take<double>((size_t)batch * trtri_tmp_elems(n));
     int* counters = w.take<int>((size_t)batch);
+    int* dag_scratch = w.take<int>(potrf_dag_scratch_ints(batch, n + 1));
     SB_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * batch, stream));
     SB_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, stream));
     SB_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * ((size_t)(batch - 1) * strideL + (size_t)n * ldl), stream));
     SB_TRY(gp_assemble(batch, n, d, theta, strideTheta, g, strideG, gvar, strideGvar, hyp, A, lda, strideA, stream));
     CholBatch c{};
     c.batch = batch; c.n = n; c.mrows = n + 1; c.A = A; c.lda = lda; c.strideA = strideA; c.info = info;
-    c.counters = counters;
+    c.counters = counters; c.dag_scratch = dag_scratch;
     c.Dinv = Linv; c.ldd = ldl; c.strideD = strideL; c.blockD = (long)NB * ldl + NB;
     SB_TRY(potrf_batched(c, stream));
     nll_finalize_kernel<<<batch, 256, 0, stream>>>(n, d, A, lda, strideA, hyp, nullptr, nullptr, s0, nullptr, sig2,

@@ -412,7 +412,7 @@ def potrf_batched(A, n, mrows):
     _need_cuda(A)
     batch, _, lda = A.shape
     Linv = torch.empty((batch, n, lda), dtype=torch.float64, device=A.device)
-    info = torch.empty(2 * batch, dtype=torch.int32, device=A.device)      # [info | scratch]
+    info = torch.empty(lib.sb200_potrf_info_ints(batch, mrows), dtype=torch.int32, device=A.device)   # [info | scratch]
     check(lib.sb200_potrf_batched(batch, n, mrows, _ptr(A), lda, A.stride(0), _ptr(Linv), lda, n * lda, _ptr(info),
                                   _stream(torch)), 'sb200_potrf_batched')
     return Linv, info[:batch]
