@@ -444,6 +444,8 @@ def main():
     _lib.lib.sb200_gemm_profile_enable(0)
     g_ms, g_fl = ctypes.c_double(0), ctypes.c_double(0)
     g_n = _lib.lib.sb200_gemm_profile_collect(ctypes.byref(g_ms), ctypes.byref(g_fl))
+    c_ms, c_fl = ctypes.c_double(0), ctypes.c_double(0)
+    c_n = _lib.lib.sb200_kernel_profile_collect(1, ctypes.byref(c_ms), ctypes.byref(c_fl))   # task-graph Cholesky launches
     clk.__exit__(None, None, None)
 
     # strong scaling reference point: the SAME k-component step on one GPU (rank 0 alone, the others wait)
@@ -540,6 +542,7 @@ def main():
                          'measured_on': 'rank 0' if strong else 'the GPU',
                          'peak_source': 'cuBLAS DGEMM 8192^3 via torch.matmul, best of 5, measured in this run '
                                         '(MEASURED_PEAKS.json has no FP64 entry)'},
+            'roofline_kernels': roofline_kernels(g_n, g_ms.value, g_fl.value, c_n, c_ms.value, c_fl.value, K, ms_dev, peak),
             'cpu_baseline': cpu,
             'secondary': secondary,
         }
@@ -554,6 +557,31 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def roofline_kernels(g_n, g_ms, g_fl, c_n, c_ms, c_fl, K, ms_step, peak):
+    """Per-kernel roofline entries of the timed step.  The two FP64 tensor-core kernels are timed live with CUDA events
+    around every launch (algorithmic flop / event time); the FP64-ALU / HBM kernels carry the figures of the committed
+    ncu --set full captures (profiles/ncu_kernels_r2.json, same command line), marked as such."""
+    out = []
+    for name, n, ms, fl, what in (
+            ('dgemm_dmma_kernel', g_n, g_ms, g_fl, 'triangular inverse, L^-T L^-1, predict products (and the recursion\'s '
+                                                   'trailing updates where the task-graph kernel is not used)'),
+            ('potrf_dag_kernel', c_n, c_ms, c_fl, 'batched Cholesky as one persistent task-graph launch (n^3/3 + rhs flop)')):
+        if n and ms > 0:
+            ach = fl / (ms * 1e-3) / 1e12
+            out.append({'kernel': name, 'bound': 'tensor', 'what': what, 'launches_per_step': n / K, 'ms_per_step': ms / K,
+                        'share_of_step': ms / K / ms_step, 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
+                        'frac': ach / peak if peak else None, 'timed': 'CUDA events around every launch, this run'})
+    try:
+        extra = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_kernels_r2.json')))['kernels']
+        for e in extra:
+            e = dict(e)
+            e['timed'] = 'ncu --set full capture committed under profiles/ (not this run)'
+            out.append(e)
+    except Exception:
+        pass
+    return out
 
 
 def single_gpu_same_work(w, theta_d, mean_d, std_d, dev, torch, ops, chunk=32):
@@ -689,7 +717,10 @@ def c5_run(C, fi, w, y, yvar, torch, sampperchain, sampler='PTLMC_B200', **extra
     return {'sampler': sampler, 'mcmc_steps': steps, 'population': 264, 'wall_s': dt, 'theta_evaluated': rows,
             'theta_per_s_end_to_end': rows / dt, 'ms_per_mcmc_step_end_to_end': dt / steps * 1e3,
             'posterior_mean_abs_err': float(np.mean(np.abs(post.mean(0) - w['theta_true'][0]))),
-            'distinct_factors': int(fi['_b200'].get('nf_total', fi['_b200']['Linv'].shape[0]))}
+            'distinct_factors': int(fi['_b200'].get('nf_total', fi['_b200']['Linv'].shape[0])),
+            'device_chain': {k: v for k, v in cal.get('_b200sampler', {}).items()
+                             if k in ('cuda_graph', 'steps_per_graph', 'accept_rate', 'swap_rate', 'preoptimise_s',
+                                      'setup_and_capture_s', 'loop_s', 'ms_per_step_in_loop')}}
 
 
 def adopted_parity(M, C, w):

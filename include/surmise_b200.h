@@ -38,6 +38,8 @@ const char* sb200_last_error(void);
 long sb200_launch_count(void);
 void sb200_gemm_profile_enable(int on);
 int sb200_gemm_profile_collect(double* total_ms, double* total_flops);
+int sb200_kernel_profile_collect(int kind, double* total_ms, double* total_flops);   /* kind 0 = DMMA GEMM launches,
+                                                   1 = task-graph Cholesky launches (algorithmic flop n^3/3 + rhs n^2) */
 int sb200_gemm_profile_dump(double* ms, double* flops, int cap);   /* per launch, host arrays */
 
 /* Replaces surmise.emulationsupport.matern_covmat.covmat (emulationsupport/matern_covmat.pyx:27-64,

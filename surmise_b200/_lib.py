@@ -28,6 +28,7 @@ SIGNATURES = {
     'sb200_launch_count': (_l, []),
     'sb200_gemm_profile_enable': (None, [_i]),
     'sb200_gemm_profile_collect': (_i, [_p, _p]),
+    'sb200_kernel_profile_collect': (_i, [_i, _p, _p]),
     'sb200_gemm_profile_dump': (_i, [_p, _p, _i]),
     'sb200_matern_covmat': (_i, [_p, _i, _p, _i, _i, _p, _p, _l, _p, _i, _p]),
     'sb200_gp_nll_small_max_n': (_i, []),

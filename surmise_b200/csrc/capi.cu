@@ -22,14 +22,15 @@ void set_last_error(const char* fmt, ...) {
 static std::atomic<long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-struct GemmSample { cudaEvent_t a, b; double flops; };
+struct GemmSample { cudaEvent_t a, b; double flops; int kind; };
 static std::mutex g_prof_mu;
 static std::vector<GemmSample> g_prof;
 static std::atomic<bool> g_prof_on{false};
 bool gemm_profile_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
-void gemm_profile_add(cudaEvent_t a, cudaEvent_t b, double flops) {
+void gemm_profile_add(cudaEvent_t a, cudaEvent_t b, double flops) { kernel_profile_add(0, a, b, flops); }
+void kernel_profile_add(int kind, cudaEvent_t a, cudaEvent_t b, double flops) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    g_prof.push_back(GemmSample{a, b, flops});
+    g_prof.push_back(GemmSample{a, b, flops, kind});
 }
 }  // namespace sb
 
@@ -72,7 +73,8 @@ int sb200_gemm_profile_dump(double* ms, double* flops, int cap) {
     int n = 0;
     for (auto& smp : sb::g_prof) {
         float t = 0.f;
-        bool ok = cudaEventSynchronize(smp.b) == cudaSuccess && cudaEventElapsedTime(&t, smp.a, smp.b) == cudaSuccess;
+        bool ok = smp.kind == 0 && cudaEventSynchronize(smp.b) == cudaSuccess &&
+                  cudaEventElapsedTime(&t, smp.a, smp.b) == cudaSuccess;
         if (ok && n < cap) {
             ms[n] = t;
             flops[n] = smp.flops;
@@ -85,13 +87,18 @@ int sb200_gemm_profile_dump(double* ms, double* flops, int cap) {
     return n;
 }
 
-// Synchronises the recorded events, returns the number of DMMA GEMM launches booked since the last call and
-// their summed device time (ms) and algorithmic flop; clears the record.
-int sb200_gemm_profile_collect(double* total_ms, double* total_flops) {
+// Synchronises the recorded events of one kind (0 = DMMA GEMM launches, 1 = task-graph Cholesky launches), returns how
+// many were booked since the last call and their summed device time (ms) and algorithmic flop; clears those records.
+int sb200_kernel_profile_collect(int kind, double* total_ms, double* total_flops) {
     std::lock_guard<std::mutex> lk(sb::g_prof_mu);
     double ms = 0.0, fl = 0.0;
     int n = 0;
+    std::vector<sb::GemmSample> keep;
     for (auto& smp : sb::g_prof) {
+        if (smp.kind != kind) {
+            keep.push_back(smp);
+            continue;
+        }
         float t = 0.f;
         if (cudaEventSynchronize(smp.b) == cudaSuccess && cudaEventElapsedTime(&t, smp.a, smp.b) == cudaSuccess) {
             ms += t;
@@ -101,10 +108,13 @@ int sb200_gemm_profile_collect(double* total_ms, double* total_flops) {
         cudaEventDestroy(smp.a);
         cudaEventDestroy(smp.b);
     }
-    sb::g_prof.clear();
+    sb::g_prof.swap(keep);
     if (total_ms) *total_ms = ms;
     if (total_flops) *total_flops = fl;
     return n;
+}
+int sb200_gemm_profile_collect(double* total_ms, double* total_flops) {
+    return sb200_kernel_profile_collect(0, total_ms, total_flops);
 }
 const char* sb200_last_error(void) { return sb::g_err; }
 

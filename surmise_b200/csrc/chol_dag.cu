@@ -593,6 +593,18 @@ int potrf_dag(const CholBatch& c, cudaStream_t stream) {
     }
     SB_CUDA(cudaMemsetAsync(c.dag_scratch, 0, sizeof(int) * potrf_dag_scratch_ints(c.batch, c.mrows), stream));
     const int grid = (int)std::min<long>(total, 2L * sms);
+    if (gemm_profile_enabled()) {                  // bench.py's roofline leg: CUDA events around this launch
+        cudaEvent_t e0, e1;
+        SB_CUDA(cudaEventCreate(&e0));
+        SB_CUDA(cudaEventCreate(&e1));
+        SB_CUDA(cudaEventRecord(e0, stream));
+        potrf_dag_kernel<<<grid, DT, smem, stream>>>(a);
+        SB_CUDA(cudaEventRecord(e1, stream));
+        const double nn = (double)c.n;             // n^3/3 for the factor + n^2 per right-hand-side row
+        kernel_profile_add(1, e0, e1, (double)c.batch * (nn * nn * nn / 3.0 + (double)(c.mrows - c.n) * nn * nn));
+        SB_LAUNCH_CHECK();
+        return 0;
+    }
     potrf_dag_kernel<<<grid, DT, smem, stream>>>(a);
     SB_LAUNCH_CHECK();
     return 0;

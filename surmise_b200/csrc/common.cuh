@@ -21,6 +21,7 @@ void count_launch();
 // each launch with CUDA events on its stream and books the launch's algorithmic flop count
 bool gemm_profile_enabled();
 void gemm_profile_add(cudaEvent_t start, cudaEvent_t stop, double flops);
+void kernel_profile_add(int kind, cudaEvent_t start, cudaEvent_t stop, double flops);   // 0 = DMMA GEMM, 1 = task-graph Cholesky
 
 #define SB_CHECK_ARG(cond, ...)                         \
     do {                                                \

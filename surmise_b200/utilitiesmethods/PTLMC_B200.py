@@ -218,6 +218,8 @@ def _device_chain(dl, thetac, fval, dfval, temps, cov0, hc, numtemps, numchain, 
           'kstep': torch.zeros(1, dtype=torch.int64, device=dev),
           'save': torch.zeros((numchain, sampperchain, d), dtype=torch.float64, device=dev), 'valid': ev.valid}
     total = tune + sampperchain
+    import time
+    t_begin = time.perf_counter()
 
     def one_step():
         ev.launch()
@@ -239,6 +241,9 @@ def _device_chain(dl, thetac, fval, dfval, temps, cov0, hc, numtemps, numchain, 
         except Exception:                                     # capture unavailable (e.g. a collective that cannot be
             graph = None                                      # captured): same launches, issued eagerly
             torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    t_loop = time.perf_counter()
+    done_before = done
     while total - 1 - done > 0:
         if graph is not None and total - 1 - done >= steps_per_graph:
             graph.replay()
@@ -250,7 +255,10 @@ def _device_chain(dl, thetac, fval, dfval, temps, cov0, hc, numtemps, numchain, 
     ev.launch()                                               # likelihood of the last proposal
     ops.ptlmc_step(st, 1, ev.ll, ev.dll)
     save, scal = ops.to_host([st['save'], st['scal']])
+    t_end = time.perf_counter()
     stats = {'theta_evaluated_on_device': total * B, 'mcmc_steps': total, 'cuda_graph': used_graph,
+             'setup_and_capture_s': t_loop - t_begin, 'loop_s': t_end - t_loop,
+             'ms_per_step_in_loop': 1e3 * (t_end - t_loop) / max(total - 1 - done_before, 1),
              'steps_per_graph': steps_per_graph if used_graph else 0, 'accept_rate': float(scal[2] / (total * B)),
              'swap_rate': float(scal[3] / (5 * B * total)), 'final_rho': float(scal[4]),
              'outside_box_rate': float(scal[5] / (total * B)), 'seed': seed}
@@ -302,8 +310,11 @@ def sampler(logpostfunc, draw_func, theta0=None, numsamp=2000, numtemps=32, numc
     taracc = 0.60 if has_grad else 0.25
 
     # starting points: best-ranked draws (with a random tie-breaker), each improved by a bounded optimiser
+    import time
+    t_start = time.perf_counter()
     rank = np.argsort(-np.squeeze(value_only(theta0)) + d * np.random.standard_normal(size=theta0.shape[0]) ** 2)
     thetac = _preoptimise(theta0[rank[:B]], value_and_grad, has_grad)
+    t_preopt = time.perf_counter() - t_start
 
     if has_grad:
         fval, dfval = value_and_grad(thetac)
@@ -329,6 +340,7 @@ def sampler(logpostfunc, draw_func, theta0=None, numsamp=2000, numtemps=32, numc
                                 sampperchain, taracc)
             if res is not None:
                 save, stats = res
+                stats['preoptimise_s'] = t_preopt
                 dl.record(**stats)
                 flat = save.reshape(-1, d)
                 theta = flat[np.random.choice(flat.shape[0], size=numsamp)]
