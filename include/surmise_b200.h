@@ -186,9 +186,10 @@ int sb200_potrf_batched(int batch, int n, int mrows, double* A, long lda, long s
 size_t sb200_potrf_info_ints(int batch, int mrows);
 size_t sb200_trtri_tmp_elems(int n);
 void sb200_debug_panel_stamps(long long* device_ptr);   /* instrumentation: clock64 stamps of the panel kernel's phases */
-void sb200_debug_dag_stats(long long* device_ptr);      /* instrumentation: per CTA of the task-graph Cholesky, 5 slots
+void sb200_debug_dag_stats(long long* device_ptr);      /* instrumentation: per CTA of the task-graph Cholesky, 8 slots
                                                            [cycles total, waiting on dependencies, in diagonal tasks'
-                                                           factorisation, in off-diagonal tasks' solve, tasks]; NULL = off */
+                                                           factorisation, in off-diagonal tasks' solve, tasks, 64x64 factor +
+                                                           inverse, solve of the rows under the block, diagonal tasks]; NULL = off */
 int sb200_trtri_batched(int batch, int n, const double* L, long lda, long stride_a, double* Linv, long ldl,
                         long stride_linv, double* tmp, size_t tmp_elems_per_matrix, void* stream);
 int sb200_lauum_batched(int batch, int n, const double* Linv, long ldl, long stride_linv, double* C, long ldc,

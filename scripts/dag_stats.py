@@ -14,7 +14,7 @@ for n, nb in shapes:
     A0 = torch.tril(X @ X.T / n + 1e-3 * torch.eye(n, dtype=torch.float64, device='cuda'))
     del X
     buf = torch.empty((nb, n, n), dtype=torch.float64, device='cuda')
-    stats = torch.zeros((296, 5), dtype=torch.int64, device='cuda')
+    stats = torch.zeros((296, 8), dtype=torch.int64, device='cuda')
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for it in range(3):
         buf[:] = A0
@@ -27,7 +27,13 @@ for n, nb in shapes:
     lib.sb200_debug_dag_stats(None)
     s = stats.cpu().double()
     s = s[s[:, 0] > 0]
+    if s.shape[0] == 0:
+        print('n=%d batch=%d  %.3f ms  (recursive path, no task-graph statistics)' % (n, nb, e0.elapsed_time(e1)))
+        continue
     tot = s[:, 0].sum()
+    nd = max(float(s[:, 7].sum()), 1.0)
+    print('   per diagonal task: finish %.0f cycles, of which factor+inverse %.0f, rows below %.0f'
+          % (s[:, 2].sum() / nd, s[:, 5].sum() / nd, s[:, 6].sum() / nd))
     print('n=%d batch=%d  %.3f ms  %.2f TFLOP/s  ctas=%d  cycles/cta mean %.0f max %.0f | wait %.1f%%  diag %.1f%%  solve %.1f%%  '
           'tasks/cta %.1f' % (n, nb, e0.elapsed_time(e1), nb * n ** 3 / 3 / e0.elapsed_time(e1) / 1e9, s.shape[0],
                               s[:, 0].mean(), s[:, 0].max(), 100 * s[:, 1].sum() / tot, 100 * s[:, 2].sum() / tot,

@@ -26,7 +26,7 @@ struct CholBatch {
 size_t potrf_dag_scratch_ints(int batch, int mrows);
 bool potrf_dag_usable(const CholBatch& c);
 int potrf_dag(const CholBatch& c, cudaStream_t stream);
-void debug_dag_stats(long long* device_ptr);     // instrumentation: 5 clock64 counters per CTA (296 CTAs at most)
+void debug_dag_stats(long long* device_ptr);     // instrumentation: 8 clock64 counters per CTA (2 CTAs per SM)
 
 // A <- L (in place), Dinv filled, extra rows <- rows * L^-T.   ~ n^3/3 + (mrows-n) n^2 flop per matrix
 int potrf_batched(const CholBatch& c, cudaStream_t stream);

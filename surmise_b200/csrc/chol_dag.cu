@@ -18,6 +18,8 @@
 #include "dgemm_tile.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
+#include <cuda.h>           // CUtensorMap (type and enums only; the encoder is fetched through the runtime)
 
 namespace sb {
 namespace {
@@ -42,7 +44,7 @@ struct DagArgs {
     int n, mrows, batch, nt, mtp, total;        // nt column tiles (64), mtp row pairs (128 rows)
     int* info; int* prog; int* ticket;      // prog: batch * mtp counters; ticket[0] = next task, ticket[1] = abort flag
     int nowait;                             // experiments only (SB200_DAG_NOWAIT=1): ignore dependencies, results are wrong
-    long long* stats;                       // instrumentation (may be NULL): per CTA [total, waiting, diagonal, solve, tasks]
+    long long* stats;                       // instrumentation (may be NULL): per CTA [total, waiting, diagonal, solve, tasks, factor, chunk, ndiag]
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -59,6 +61,52 @@ __device__ __forceinline__ double rsqrt_normal(double x) {
 }
 __device__ __forceinline__ bool normal_positive(double x) {
     return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fe00000u;
+}
+
+
+// ---- TMA / mbarrier plumbing of the task-graph kernel's operand pipeline ------------------------------------------
+// Operand tiles (64 rows x 16 k-contiguous doubles = 64 x 128 B) are fetched by cp.async.bulk.tensor (SASS UTMALDG) with
+// the 128-byte swizzle: row r of a tile lies at r * 128 B and its 16-byte chunk c at position c ^ (r & 7).  A warp's
+// DMMA fragment loads stay bank-conflict free under that swizzle when lane t of k-step s takes
+// k = 8 (t >> 1) + 2 s + (t & 1) instead of 4 s + t -- any assignment of the 16 k's of a tile to (step, lane) is valid
+// as long as both operands use the same one.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// a transfer that never completes would otherwise hang the GPU: trap after ~2 s
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > SPIN_LIMIT) __trap();
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
 }
 
 // all threads: returns min(prog_a, prog_b) once it is >= need (uniform); s_avail is a shared scratch word
@@ -302,18 +350,33 @@ __device__ __forceinline__ void solve_chunk64(const double* T, const double* X, 
     }
 }
 
-__global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p) {
-    extern __shared__ __align__(16) double sm[];
+template <bool TMA>
+__global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(16) double sm_raw[];
+    // the swizzled TMA tiles need 1024-byte alignment (the launch reserves the slack)
+    double* sm = TMA ? reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~(uintptr_t)1023) : sm_raw;
     __shared__ int s_task, s_avail;
+    __shared__ __align__(8) unsigned long long full_bar[DSTAGES], empty_bar[DSTAGES];
+    unsigned git = 0;                                     // k-tiles this CTA has consumed so far (all tasks): stage = git % S
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     constexpr int WM = 32, WN = 32, MI = WM / 8, NI = WN / 8, WARPS_N = NB / WN;      // 4 x 2 warps on a 128 x 64 tile
     const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
     int* abort_flag = p.ticket + 1;
     const int avail0 = p.nowait ? (1 << 30) : 0;
+    if (TMA) {
+        if (tid == 0) {
+            for (int i = 0; i < DSTAGES; i++) {
+                mbar_init(&full_bar[i], 1);               // one arrival (the producer's expect_tx) + the bytes
+                mbar_init(&empty_bar[i], DT / 32);        // one arrival per warp
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncthreads();
+    }
 
     // ticket -> task decoding state (tickets of one CTA increase, so the column segment only moves forward)
     int seg = -1, seg_start = 0, seg_size = p.batch;
-    long long c_wait = 0, c_diag = 0, c_solve = 0, c_tasks = 0;
+    long long c_wait = 0, c_diag = 0, c_solve = 0, c_tasks = 0, c_factor = 0, c_chunk = 0, c_ndiag = 0;
     const long long c_begin = clock64();
 
     for (;;) {
@@ -391,6 +454,79 @@ __global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p) {
             }
         }
 
+        if constexpr (TMA) {
+            // One elected thread (lane 0 of warp 0) produces: it waits until all warps have released the slot and, at
+            // every 64-wide k-slab, until the operand rows' progress counters cover it, then posts the byte count and
+            // issues the bulk-tensor loads.  Everyone consumes: wait for the slot's bytes, multiply, release the slot.
+            // No CTA-wide barrier inside the loop -- warps drift up to DSTAGES - 1 tiles apart.
+            const unsigned tx_bytes = (unsigned)((diag ? 2 : 3) * NB * BK * sizeof(double));
+            auto produce = [&](int ktl) {
+                const unsigned it = git + (unsigned)ktl, slot = it % DSTAGES, ph = (it / DSTAGES) & 1;
+                mbar_wait(&empty_bar[slot], ph ^ 1);
+                const int slab = ktl / KT_PER_SLAB;
+                if (slab >= avail) {
+                    const long long t0 = clock64();
+                    for (;;) {
+                        int v = ld_acquire(prog_i);
+                        if (!diag) v = min(v, ld_acquire(prog_j));
+                        if (v > slab) {
+                            avail = v;
+                            break;
+                        }
+                        if (clock64() - t0 > SPIN_LIMIT || ld_acquire(abort_flag)) {
+                            atomicExch(abort_flag, 1);
+                            avail = 1 << 30;
+                            break;
+                        }
+                        __nanosleep(40);
+                    }
+                    c_wait += clock64() - t0;
+                    asm volatile("fence.proxy.async;\n" ::: "memory");      // the loads below go through the async proxy
+                }
+                double* dst = sm + (size_t)slot * STAGE_ELEMS;
+                mbar_expect_tx(&full_bar[slot], tx_bytes);
+                tma_load_3d(dst, &tmap, ktl * BK, r0, z, &full_bar[slot]);
+                tma_load_3d(dst + NB * BK, &tmap, ktl * BK, r0 + NB, z, &full_bar[slot]);
+                if (!diag) tma_load_3d(dst + 2 * NB * BK, &tmap, ktl * BK, c0, z, &full_bar[slot]);
+            };
+            const bool producer = tid == 0;
+            if (producer) {
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the buffers were last touched by ld/st.shared
+                for (int s = 0; s < DSTAGES - 1 && s < ktiles; s++) produce(s);
+            }
+            // swizzled fragment columns of this lane for the four k-steps of a tile (see the helper comment)
+            int colk[BK / 4];
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 4; k4++) colk[k4] = ((((t >> 1) * 4 + k4) ^ g) << 1) | (t & 1);
+#pragma unroll 1
+            for (int kt = 0; kt < ktiles; kt++) {
+                if (producer && kt + DSTAGES - 1 < ktiles) produce(kt + DSTAGES - 1);
+                __syncwarp();
+                const unsigned it = git + (unsigned)kt, slot = it % DSTAGES, ph = (it / DSTAGES) & 1;
+                mbar_wait(&full_bar[slot], ph);
+                if (!idle_warp) {
+                    const double* as = sm + (size_t)slot * STAGE_ELEMS;
+                    const double* bs = diag ? as + diag_off * BK : as + 2 * NB * BK;
+#pragma unroll
+                    for (int k4 = 0; k4 < BK / 4; k4++) {
+                        double a[MI], b[NI];
+#pragma unroll
+                        for (int i = 0; i < MI; i++) a[i] = as[(wm0 + i * 8 + g) * BK + colk[k4]];
+#pragma unroll
+                        for (int j = 0; j < NI; j++) b[j] = bs[(wn0 + j * 8 + g) * BK + colk[k4]];
+#pragma unroll
+                        for (int i = 0; i < MI; i++)
+#pragma unroll
+                            for (int j = 0; j < NI; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[slot]);
+            }
+            git += (unsigned)ktiles;
+            __syncthreads();                              // every warp is done with the stage buffers: reuse them below
+            avail = avail0;                               // (the producer's knowledge is not shared: the solve re-checks)
+        } else {
         auto stage_load = [&](int kt) {
             const int slot = kt % DSTAGES;
             load_tile<2 * NB, true, DT>(As + slot * BK * 2 * NB, A, p.lda, r0, p.mrows, kt * BK, c0, true, tid);
@@ -438,6 +574,7 @@ __global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p) {
         }
         cp_async_wait<0>();
         __syncthreads();                                  // the pipeline buffers are free: reuse them below
+        }
 
         const long long c_fin = clock64();
         double* X = sm;                                   // [64][SLD]   L_jj^-1
@@ -463,7 +600,10 @@ __global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p) {
                         if (row >= lo && row < rows_here && col < nbj) A[(long)(r0 + row) * p.lda + c0 + col] = v;
                     }
             __syncthreads();
+            const long long c_f0 = clock64();
             const int bad_at = factor_invert_64(S, X, W, invd, c0, tid);
+            c_factor += clock64() - c_f0;
+            c_ndiag++;
             double* D = p.Dinv + (long)z * p.strideD + (long)tj * p.blockD;
             for (int idx = tid; idx < nbj * nbj; idx += DT) {
                 const int i = idx / nbj, c = idx % nbj;
@@ -471,6 +611,7 @@ __global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p) {
                 D[(long)i * p.ldd + c] = X[i * SLD + c];
             }
             if (tid == 0 && bad_at != 0 && p.info[z] == 0) p.info[z] = bad_at;
+            const long long c_c0 = clock64();
             for (int ch = lo; ch < rows_here; ch += NB) {             // rows below the block, 64 at a time: P <- P X'
                 __syncthreads();                                      // S (or the previous chunk) is no longer read
                 const int rows = min(NB, rows_here - ch);
@@ -482,6 +623,7 @@ __global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p) {
                 __syncthreads();
                 solve_chunk64(S, X, P, p.lda, 0, rows, nbj, warp, g, t);
             }
+            c_chunk += clock64() - c_c0;
             c_diag += clock64() - c_fin;
         } else {
 #pragma unroll
@@ -537,12 +679,15 @@ __global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p) {
         if (tid == 0) atomicAdd(p.prog + (long)z * p.mtp + tI, 1);
     }
     if (p.stats && tid == 0) {
-        long long* st = p.stats + 5 * (long)blockIdx.x;
+        long long* st = p.stats + 8 * (long)blockIdx.x;
         st[0] = clock64() - c_begin;
         st[1] = c_wait;
         st[2] = c_diag;
         st[3] = c_solve;
         st[4] = c_tasks;
+        st[5] = c_factor;
+        st[6] = c_chunk;
+        st[7] = c_ndiag;
     }
 }
 
@@ -559,14 +704,43 @@ bool potrf_dag_usable(const CholBatch& c) {
            (long)c.batch * cdiv(c.mrows, NB) * (cdiv(c.mrows, NB) + 1) / 2 < (1L << 30);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static std::atomic<void*> fn{nullptr};
+    void* f = fn.load();
+    if (!f) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        fn.store(f);
+    }
+    return (EncodeTiledFn)f;
+}
+
+// 0 = cp.async staging, 1 = TMA + mbarrier pipeline (default); SB200_DAG_TMA=0 selects the former (A/B experiments)
+static int dag_use_tma() {
+    static int on = -1;
+    if (on < 0) {
+        const char* env = getenv("SB200_DAG_TMA");
+        on = (env && env[0] == '0') ? 0 : 1;
+    }
+    return on;
+}
+
 int potrf_dag(const CholBatch& c, cudaStream_t stream) {
     constexpr size_t smem = (size_t)SM_DOUBLES * sizeof(double);
+    constexpr size_t smem_tma = smem + 1024;
     static DeviceOnce once;
     static int sm_count[64];
     int dev = 0;
     SB_CUDA(cudaGetDevice(&dev));
     SB_TRY(once.run([&]() -> int {
-        SB_CUDA(cudaFuncSetAttribute(potrf_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(potrf_dag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(cudaFuncSetAttribute(potrf_dag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
         int n = 0;
         SB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
         if (dev >= 0 && dev < 64) sm_count[dev] = n;
@@ -593,19 +767,38 @@ int potrf_dag(const CholBatch& c, cudaStream_t stream) {
     }
     SB_CUDA(cudaMemsetAsync(c.dag_scratch, 0, sizeof(int) * potrf_dag_scratch_ints(c.batch, c.mrows), stream));
     const int grid = (int)std::min<long>(total, 2L * sms);
+
+    // operand tiles as a 3-d tensor (k, row, matrix): 64 rows x 16 doubles per box, 128-byte swizzle, zero fill out of bounds
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    bool tma = dag_use_tma() != 0 && encode_tiled() != nullptr && c.batch >= 1;
+    if (tma) {
+        const cuuint64_t dims[3] = {(cuuint64_t)c.lda, (cuuint64_t)c.mrows, (cuuint64_t)c.batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)c.lda * sizeof(double), (cuuint64_t)c.strideA * sizeof(double)};
+        const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)NB, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)c.A, dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) tma = false;                // e.g. a stride the encoder refuses: cp.async staging instead
+    }
+    auto launch = [&]() {
+        if (tma) potrf_dag_kernel<true><<<grid, DT, smem_tma, stream>>>(a, tmap);
+        else potrf_dag_kernel<false><<<grid, DT, smem, stream>>>(a, tmap);
+    };
     if (gemm_profile_enabled()) {                  // bench.py's roofline leg: CUDA events around this launch
         cudaEvent_t e0, e1;
         SB_CUDA(cudaEventCreate(&e0));
         SB_CUDA(cudaEventCreate(&e1));
         SB_CUDA(cudaEventRecord(e0, stream));
-        potrf_dag_kernel<<<grid, DT, smem, stream>>>(a);
+        launch();
         SB_CUDA(cudaEventRecord(e1, stream));
         const double nn = (double)c.n;             // n^3/3 for the factor + n^2 per right-hand-side row
         kernel_profile_add(1, e0, e1, (double)c.batch * (nn * nn * nn / 3.0 + (double)(c.mrows - c.n) * nn * nn));
         SB_LAUNCH_CHECK();
         return 0;
     }
-    potrf_dag_kernel<<<grid, DT, smem, stream>>>(a);
+    launch();
     SB_LAUNCH_CHECK();
     return 0;
 }
