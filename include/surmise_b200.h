@@ -36,6 +36,7 @@ const char* sb200_last_error(void);
  * optional per-launch CUDA-event timing of the DMMA GEMM (enable, run, collect -> launches, summed ms, summed
  * algorithmic flop = 2 M N K with exact triangular ranges). */
 long sb200_launch_count(void);
+long sb200_tma_gemm_count(void);    /* DMMA GEMM launches that staged their operands by TMA (cp.async.bulk.tensor) */
 void sb200_gemm_profile_enable(int on);
 int sb200_gemm_profile_collect(double* total_ms, double* total_flops);
 int sb200_kernel_profile_collect(int kind, double* total_ms, double* total_flops);   /* kind 0 = DMMA GEMM launches,

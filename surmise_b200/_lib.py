@@ -26,6 +26,7 @@ SIGNATURES = {
     'sb200_version': (_i, []),
     'sb200_last_error': (C.c_char_p, []),
     'sb200_launch_count': (_l, []),
+    'sb200_tma_gemm_count': (_l, []),
     'sb200_gemm_profile_enable': (None, [_i]),
     'sb200_gemm_profile_collect': (_i, [_p, _p]),
     'sb200_kernel_profile_collect': (_i, [_i, _p, _p]),

@@ -63,6 +63,7 @@ void sb200_host_tempexchange(const double* lpost, const double* temps, int B, co
 }
 
 long sb200_launch_count(void) { return sb::g_launches.load(); }
+long sb200_tma_gemm_count(void) { return sb::dgemm_tma_launch_count(); }
 
 void sb200_gemm_profile_enable(int on) { sb::g_prof_on.store(on != 0); }
 

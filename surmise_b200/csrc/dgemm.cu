@@ -262,6 +262,11 @@ int launch_layout(const GemmArgs& g, int batch, cudaStream_t stream) {
 
 }  // namespace
 
+double dgemm_algorithmic_flops(const GemmArgs& g) { return algorithmic_flops(g, 0, 0); }
+
+static std::atomic<long> g_tma_launches{0};
+long dgemm_tma_launch_count() { return g_tma_launches.load(); }
+
 int launch_dgemm(const GemmArgs& g, int batch, int tile, cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return 0;
     SB_CHECK_ARG(batch <= 65535, "dgemm: batch %d exceeds grid.z limit", batch);
@@ -275,6 +280,19 @@ int launch_dgemm(const GemmArgs& g, int batch, int tile, cudaStream_t stream) {
     if (tile < 0) {
         const char* env = getenv("SB200_GEMM_TILE");              // experiments only
         tile = env ? atoi(env) : 7;
+        // default: TMA-staged 64x64 tiles (scripts/gemm_tma_ab.py on B200: 33.7 vs 32.8 TFLOP/s at 4096^3, 1-3 % faster on
+        // the batched mid-size products of the trtri / lauum / predict steps); the smallest products (K < 128, a few
+        // k-tiles per CTA) do not amortise the barrier set-up and keep the cp.async kernel
+        if (!env && g.K >= 128) tile = 8;
+    }
+    if (tile == 8 || tile == 9) {                      // TMA + mbarrier pipeline (dgemm_tma.cu), 64x64 / 128x64 tiles
+        SB_CHECK_ARG(batch <= 65535, "dgemm: batch %d exceeds grid.z limit", batch);
+        const int rc = launch_dgemm_tma(g, batch, tile == 8 ? 64 : 128, stream);
+        if (rc != -2) {
+            if (rc == 0) g_tma_launches.fetch_add(1, std::memory_order_relaxed);
+            return rc;
+        }
+        tile = 7;                                      // operands a tensor map cannot describe: cp.async staging
     }
     if (tile == 7) return launch_layout<64, 64, 32, 32>(g, batch, stream);
     if (tile == 1) return launch_layout<128, 64, 32, 32>(g, batch, stream);

@@ -34,8 +34,14 @@ struct GemmArgs {
     int last_M;     // > 0: the last z2 group has this many rows instead of M (0 = all groups alike)
 };
 
-// tile: 7 = 64x64 CTA tile, 4 warps, 4 CTAs/SM (default, -1); 1 = 128x64 (2 CTAs/SM); 0 = 128x128 (1 CTA/SM);
-// 2-4 experimental variants
+// tile: 7 = 64x64 CTA tile, 4 warps, 4 CTAs/SM, cp.async staging; 1 = 128x64 (2 CTAs/SM); 0 = 128x128 (1 CTA/SM);
+// 2-4 experimental variants; 8 / 9 = TMA-staged 64x64 / 128x64 (below); -1 = default
 int launch_dgemm(const GemmArgs& g, int batch, int tile, cudaStream_t stream);
+
+// tile 8 / 9: the same product with TMA operand staging and an mbarrier pipeline (dgemm_tma.cu; 64x64 / 128x64 tiles);
+// returns -2 without launching when the operands cannot be described by tensor maps (launch_dgemm then falls back)
+int launch_dgemm_tma(const GemmArgs& g, int batch, int bm, cudaStream_t stream);
+double dgemm_algorithmic_flops(const GemmArgs& g);     // 2 M N K with the exact triangular k-ranges
+long dgemm_tma_launch_count();
 
 }  // namespace sb

@@ -388,7 +388,9 @@ int gp_weights(int K, int n, const double* Linv, long ldl, long strideL, const i
 }
 
 // ------------------------------------------------------------------------------------------------
-static long ldb_for(int B) { return round_up(B, 8); }
+// multiple of 16: the row-contiguous (n x B) operands are then describable by a TMA tensor map for EVERY population size,
+// so the summation order (and with it every bit of the result) does not depend on how a population is chunked
+static long ldb_for(int B) { return round_up(B, 16); }
 
 size_t gp_predict_workspace(int K, int nf, int nu, int n, int d, int B, int want_grad) {
     Workspace w(nullptr, 0);

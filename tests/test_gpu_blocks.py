@@ -292,3 +292,131 @@ def test_mm_wrapper(ops):
     C = rng.normal(size=(70, 90))
     out = ops.mm(dev(A), dev(B), alpha=-1.0, beta=1.0, out=dev(C.copy()))
     assert rel(out.cpu().numpy(), C - A @ B) < 1e-14
+
+
+# ---------------------------------------------------------------------------------- TMA-staged DMMA GEMM (tile 8 / 9)
+def _tma_count():
+    from surmise_b200._lib import lib
+    return int(lib.sb200_tma_gemm_count())
+
+
+@pytest.mark.parametrize('a_kc', [True, False])
+@pytest.mark.parametrize('b_kc', [True, False])
+@pytest.mark.parametrize('shape', [(128, 128, 64), (208, 80, 136), (48, 272, 96), (256, 64, 16), (16, 16, 2), (1008, 992, 1024)])
+@pytest.mark.parametrize('tile', [8, 9])
+def test_dgemm_tma_layouts(ops, a_kc, b_kc, shape, tile):
+    """Same products as test_dgemm_layouts through the TMA / mbarrier kernel; every launch must really take that path
+    (shapes are tensor-map friendly: even leading dimensions, row-contiguous extents that are multiples of 16)."""
+    import torch
+    rng = np.random.default_rng(11)
+    M, N, K = shape
+    for pad in (0, 2):
+        A, Abuf, lda = _operand(rng, M, K, a_kc, pad)
+        B, Bbuf, ldb = _operand(rng, N, K, b_kc, pad)
+        C0 = rng.normal(size=(M, N + pad))
+        Cd = dev(C0.copy())
+        before = _tma_count()
+        ops.dgemm(dev(Abuf), dev(Bbuf), Cd, a_kc, b_kc, M, N, K, alpha=-0.7, beta=1.3, tile=tile, lds=(lda, ldb, N + pad))
+        torch.cuda.synchronize()
+        assert _tma_count() == before + 1
+        want = C0.copy()
+        want[:, :N] = -0.7 * A @ B.T + 1.3 * C0[:, :N]
+        err = rel(Cd.cpu().numpy(), want)
+        report('dgemm_tma', akc=a_kc, bkc=b_kc, M=M, N=N, K=K, tile=tile, pad=pad, err=err)
+        assert err < 1e-13
+
+
+@pytest.mark.parametrize('tile', [8, 9])
+def test_dgemm_tma_falls_back_on_odd_strides(ops, tile):
+    import torch
+    rng = np.random.default_rng(12)
+    M, N, K = 70, 50, 33
+    A, B = rng.normal(size=(M, K)), rng.normal(size=(N, K))
+    Cd = dev(np.zeros((M, N)))
+    before = _tma_count()
+    ops.dgemm(dev(A), dev(B), Cd, True, True, M, N, K, tile=tile, lds=(K, K, N))      # lda = 33: not a legal TMA stride
+    torch.cuda.synchronize()
+    assert _tma_count() == before and rel(Cd.cpu().numpy(), A @ B.T) < 1e-13
+
+
+@pytest.mark.parametrize('tile', [8, 9])
+@pytest.mark.parametrize('flag,which', [(1, 'A_LOWER'), (2, 'A_UPPER'), (4, 'B_LOWER'), (8, 'B_UPPER'), (16, 'C_LOWER')])
+def test_dgemm_tma_triangular_flags(ops, flag, which, tile):
+    import torch
+    rng = np.random.default_rng(2)
+    n = 304
+    A = rng.normal(size=(n, n))
+    B = rng.normal(size=(n, n))
+    A = np.tril(A) if which == 'A_LOWER' else (np.triu(A) if which == 'A_UPPER' else A)
+    B = np.tril(B) if which == 'B_LOWER' else (np.triu(B) if which == 'B_UPPER' else B)
+    for a_kc in (True, False):
+        for b_kc in (True, False):
+            Cd = dev(np.zeros((n, n)))
+            before = _tma_count()
+            ops.dgemm(dev(A if a_kc else A.T.copy()), dev(B if b_kc else B.T.copy()), Cd, a_kc, b_kc, n, n, n,
+                      flags=flag, tile=tile, lds=(n, n, n))
+            torch.cuda.synchronize()
+            assert _tma_count() == before + 1
+            got, want = Cd.cpu().numpy(), A @ B.T
+            if which == 'C_LOWER':
+                got, want = np.tril(got), np.tril(want)
+            assert rel(got, want) < 1e-13
+
+
+@pytest.mark.parametrize('tile', [8, 9])
+def test_dgemm_tma_batched_strided(ops, tile):
+    import torch
+    rng = np.random.default_rng(3)
+    nb, M, N, K = 5, 150, 144, 90
+    A = rng.normal(size=(nb, M, K))
+    B = rng.normal(size=(N, K))                       # shared operand: stride 0
+    Cd = dev(np.zeros((nb, M, N)))
+    before = _tma_count()
+    ops.dgemm(dev(A), dev(B), Cd, True, True, M, N, K, batch=nb, strides=(M * K, 0, M * N), lds=(K, K, N), tile=tile)
+    torch.cuda.synchronize()
+    assert _tma_count() == before + 1
+    assert rel(Cd.cpu().numpy(), A @ B.T) < 1e-13
+    Bt = rng.normal(size=(nb, K, N))                  # row-contiguous batched operand
+    Cd = dev(np.zeros((nb, M, N)))
+    ops.dgemm(dev(A), dev(Bt), Cd, True, False, M, N, K, batch=nb, strides=(M * K, K * N, M * N), lds=(K, N, N), tile=tile)
+    torch.cuda.synchronize()
+    assert rel(Cd.cpu().numpy(), A @ Bt) < 1e-13
+
+
+@pytest.mark.parametrize('tile', [7, 8, 9])
+def test_dgemm_triangular_range_ending_inside_a_tile(ops, tile):
+    """A_LOWER with M not a multiple of 16 inside a wider buffer full of junk: the k-range of the last row tile ends
+    inside a 16-wide k-tile, and what lies beyond it in memory (here NaN) must not reach the product."""
+    import torch
+    rng = np.random.default_rng(5)
+    M, N, ld = 116, 64, 136
+    A = np.full((M, ld), np.nan)
+    A[:, :M] = np.tril(rng.normal(size=(M, M)))
+    Bm = np.full((ld, N), np.nan)
+    Bm[:M] = rng.normal(size=(M, N))
+    Cd = dev(np.zeros((M, N)))
+    ops.dgemm(dev(A), dev(Bm), Cd, True, False, M, N, M, flags=1, tile=tile, lds=(ld, N, N))
+    torch.cuda.synchronize()
+    assert rel(Cd.cpu().numpy(), A[:, :M] @ Bm[:M]) < 1e-13
+
+
+@pytest.mark.parametrize('n', [500, 116, 1000])
+def test_trtri_ragged_levels_in_a_batch(ops, n):
+    """Orders whose block pairs are ragged at several levels (the last group of a two-level batched launch is shorter):
+    L^-1 of every matrix of a batch, the last one included (its ragged blocks end at the end of the allocation)."""
+    import torch
+    rng = np.random.default_rng(n)
+    nb = 4
+    lda = (n + 7) // 8 * 8
+    mats = [_spd(rng, n) for _ in range(nb)]
+    buf = np.zeros((nb, n, lda))
+    for z in range(nb):
+        buf[z, :, :n] = np.tril(mats[z])
+    Ad = dev(buf)
+    Linv, info = ops.potrf_batched(Ad, n, n)
+    ops.trtri_batched(Ad, Linv, n)
+    torch.cuda.synchronize()
+    assert np.all(info.cpu().numpy() == 0)
+    Li = Linv.cpu().numpy()
+    for z in range(nb):
+        assert rel(Li[z, :, :n], np.linalg.inv(np.linalg.cholesky(mats[z]))) < 1e-9
