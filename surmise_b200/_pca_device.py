@@ -26,6 +26,74 @@ def _torch():
     return _lib.require_cuda()
 
 
+class LazyHostDict(dict):
+    """standardpcinfo whose large entries (the standardised n x m matrix fs) stay on the device until someone reads
+    them: the reference only reads fs inside the fit itself (PCGPwM.py:616), and copying 128 MB to fresh host memory was
+    a quarter of a C4 fit.  Reading through [], get, items, values, copying or pickling materialises numpy arrays;
+    the mapping then behaves like the plain dict the reference stores."""
+    __slots__ = ('_pending',)
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._pending = {}
+
+    def defer(self, key, tensor):
+        self._pending[key] = tensor
+        dict.__setitem__(self, key, None)
+
+    def _materialise(self, key=None):
+        keys = [key] if key is not None else list(self._pending)
+        keys = [k for k in keys if k in self._pending]
+        if keys:
+            from . import ops
+            for k, v in zip(keys, ops.to_host([self._pending[k] for k in keys])):
+                dict.__setitem__(self, k, v)
+                del self._pending[k]
+
+    def __getitem__(self, key):
+        if key in self._pending:
+            self._materialise(key)
+        return dict.__getitem__(self, key)
+
+    def __setitem__(self, key, value):
+        self._pending.pop(key, None)
+        dict.__setitem__(self, key, value)
+
+    def __delitem__(self, key):
+        self._pending.pop(key, None)
+        dict.__delitem__(self, key)
+
+    def __iter__(self):                      # (overridden so that dict(d) / {**d} go through keys() and [])
+        return dict.__iter__(self)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def pop(self, key, *default):
+        self._materialise(key)
+        return dict.pop(self, key, *default)
+
+    def items(self):
+        self._materialise()
+        return dict.items(self)
+
+    def values(self):
+        self._materialise()
+        return dict.values(self)
+
+    def copy(self):
+        self._materialise()
+        return dict(dict.items(self))
+
+    def device(self, key):
+        """The device tensor of a deferred entry (None once it has been materialised)."""
+        return self._pending.get(key)
+
+    def __reduce__(self):
+        self._materialise()
+        return (dict, (dict(dict.items(self)),))
+
+
 def _ops():
     from . import ops
     return ops
@@ -283,15 +351,15 @@ def standardize(f, eps_pc, eps_impute, n_iter=40):
     resid = fs - ops.mm(ops.mm(fs, Up), Up, tb=True)
     offset_np, scale_np = offset.cpu().numpy(), scale.cpu().numpy()
     extravar = (resid ** 2).mean(0).cpu().numpy() * scale_np ** 2   # PCGPwM.py:594
-    info = {'offset': offset_np, 'scale': scale_np, 'fs': fs, 'U': U, 'S': torch.sqrt(torch.clamp(lam, min=0.0)),
-            'extravar': extravar, '_lam': lam, '_eig_path': note}
+    info = LazyHostDict({'offset': offset_np, 'scale': scale_np, 'fs': fs, 'U': U,
+                         'S': torch.sqrt(torch.clamp(lam, min=0.0)), 'extravar': extravar, '_lam': lam, '_eig_path': note})
     return info, mof_np, mofrows_np
 
 
 def principal_components(spc, mof, mofrows, eps_pc, eps_impute):
     """PC loadings / scores / per-row imputation variance (PCGPwM.py:608-654) from a device standardpcinfo.
 
-    Returns a dict of numpy arrays and converts spc's device tensors to numpy in place."""
+    Returns a dict of numpy arrays and converts spc's small device tensors to numpy in place; fs is deferred."""
     torch = _torch()
     ops = _ops()
     fs, U, lam = spc['fs'], spc['U'], spc.pop('_lam')
@@ -311,8 +379,9 @@ def principal_components(spc, mof, mofrows, eps_pc, eps_impute):
     out = {'pcw': pcw, 'pcto': basis.clone(), 'pct': pct, 'pcti': basis * (torch.sqrt(effn) / pcw),
            'pc': ops.mm(fs, pct), 'unscaled_pcstdvar': pcstdvar}
     keys = list(out)
-    host = ops.to_host([out[k] for k in keys] + [spc[k] for k in ('fs', 'U', 'S')])   # pinned copies, one sync
+    host = ops.to_host([out[k] for k in keys] + [spc[k] for k in ('U', 'S')])        # pinned copies, one sync
     out = dict(zip(keys, host[:len(keys)]))
-    for k, v in zip(('fs', 'U', 'S'), host[len(keys):]):
+    for k, v in zip(('U', 'S'), host[len(keys):]):
         spc[k] = v
+    spc.defer('fs', fs)                                   # n x m: copied to the host only if somebody reads it
     return out

@@ -43,6 +43,7 @@ struct DagArgs {
     double* Dinv; long ldd, strideD, blockD;
     int n, mrows, batch, nt, mtp, total;        // nt column tiles (64), mtp row pairs (128 rows)
     int* info; int* prog; int* ticket;      // prog: batch * mtp counters; ticket[0] = next task, ticket[1] = abort flag
+    int* xflag;                             // batch * nt: 1 once L_jj and its inverse are in global memory
     int nowait;                             // experiments only (SB200_DAG_NOWAIT=1): ignore dependencies, results are wrong
     long long* stats;                       // instrumentation (may be NULL): per CTA [total, waiting, diagonal, solve, tasks, factor, chunk, ndiag]
 };
@@ -611,9 +612,12 @@ __global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p, const __gri
                 D[(long)i * p.ldd + c] = X[i * SLD + c];
             }
             if (tid == 0 && bad_at != 0 && p.info[z] == 0) p.info[z] = bad_at;
+            // L_jj^-1 is what every other task of this column waits for: announce it before solving the rows below
+            __threadfence();
+            __syncthreads();                                          // (also: S is no longer read)
+            if (tid == 0) atomicExch(p.xflag + (long)z * p.nt + tj, 1);
             const long long c_c0 = clock64();
             for (int ch = lo; ch < rows_here; ch += NB) {             // rows below the block, 64 at a time: P <- P X'
-                __syncthreads();                                      // S (or the previous chunk) is no longer read
                 const int rows = min(NB, rows_here - ch);
                 double* P = A + (long)(r0 + ch) * p.lda + c0;
                 for (int idx = tid; idx < NB * NB; idx += DT) {
@@ -622,6 +626,7 @@ __global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p, const __gri
                 }
                 __syncthreads();
                 solve_chunk64(S, X, P, p.lda, 0, rows, nbj, warp, g, t);
+                __syncthreads();                                      // the chunk buffer is free again
             }
             c_chunk += clock64() - c_c0;
             c_diag += clock64() - c_fin;
@@ -634,7 +639,7 @@ __global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p, const __gri
                     T[row * SLD + col] = (col < nbj) ? -acc[i][j][0] : 0.0;
                     T[row * SLD + col + 1] = (col + 1 < nbj) ? -acc[i][j][1] : 0.0;
                 }
-            if (avail < tj + 1) avail = wait_progress(prog_j, nullptr, tj + 1, &s_avail, abort_flag, tid, c_wait);
+            if (!p.nowait) wait_progress(p.xflag + (long)z * p.nt + tj, nullptr, 1, &s_avail, abort_flag, tid, c_wait);
             const double* D = p.Dinv + (long)z * p.strideD + (long)tj * p.blockD;
             for (int idx = tid; idx < NB * NB; idx += DT) {
                 const int i = idx >> 6, c = idx & 63;
@@ -697,7 +702,9 @@ std::atomic<long long*> g_dag_stats{nullptr};
 
 void debug_dag_stats(long long* p) { g_dag_stats.store(p); }
 
-size_t potrf_dag_scratch_ints(int batch, int mrows) { return (size_t)batch * cdiv(mrows, 2 * NB) + 2; }
+size_t potrf_dag_scratch_ints(int batch, int mrows) {      // row-pair counters, ticket + abort flag, diagonal flags
+    return (size_t)batch * cdiv(mrows, 2 * NB) + 2 + (size_t)batch * cdiv(mrows, NB);
+}
 
 bool potrf_dag_usable(const CholBatch& c) {
     return (c.lda % 2 == 0) && (c.strideA % 2 == 0) && (((uintptr_t)c.A & 15) == 0) && c.dag_scratch != nullptr &&
@@ -760,6 +767,7 @@ int potrf_dag(const CholBatch& c, cudaStream_t stream) {
     a.info = c.info;
     a.prog = c.dag_scratch;
     a.ticket = c.dag_scratch + (size_t)c.batch * a.mtp;
+    a.xflag = a.ticket + 2;
     a.stats = g_dag_stats.load();
     {
         const char* env = getenv("SB200_DAG_NOWAIT");

@@ -1,6 +1,7 @@
 """CPU: host-side logic, the C-ABI surface, and the no-fallback guarantees (no compute calls)."""
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -256,3 +257,34 @@ def test_reverse_communication_lbfgsb_equals_scipy_minimize():
                              bounds=spo.Bounds(lo, hi), options={'gtol': gtol})
             assert np.array_equal(r.x, X[i]) and r.fun == F[i] and r.nfev == nfev[i]
     assert max(calls) == 7 and min(calls) >= 1
+
+
+def test_lazy_standardpcinfo_dict(monkeypatch):
+    """LazyHostDict (the standardpcinfo of the device PCA): deferred entries are copied to the host on first read, by
+    every way of reading a mapping, and the pickled form is a plain dict of numpy arrays."""
+    import copy
+    import pickle
+    import types
+    import surmise_b200
+    from surmise_b200 import _pca_device as P
+    calls = []
+    fake = types.SimpleNamespace(to_host=lambda ts: [calls.append(len(ts)) or np.asarray(t) for t in ts])
+    monkeypatch.setitem(sys.modules, 'surmise_b200.ops', fake)
+    monkeypatch.setattr(surmise_b200, 'ops', fake, raising=False)
+
+    def fresh():
+        d = P.LazyHostDict({'offset': np.zeros(2)})
+        d.defer('fs', [[1.0, 2.0]])
+        return d
+    d = fresh()
+    assert 'fs' in d and len(d) == 2 and not calls and d.device('fs') is not None
+    assert isinstance(d['fs'], np.ndarray) and calls == [1] and d.device('fs') is None
+    assert d['fs'] is d['fs'] and calls == [1]                       # copied once
+    for read in (lambda m: dict(m)['fs'], lambda m: {**m}['fs'], lambda m: m.get('fs'), lambda m: dict(m.items())['fs'],
+                 lambda m: list(m.values())[1], lambda m: m.copy()['fs'], lambda m: copy.deepcopy(m)['fs'],
+                 lambda m: pickle.loads(pickle.dumps(m))['fs'], lambda m: m.pop('fs')):
+        assert np.array_equal(read(fresh()), [[1.0, 2.0]])
+    assert type(pickle.loads(pickle.dumps(fresh()))) is dict
+    d = fresh()
+    d['fs'] = 3
+    assert d['fs'] == 3 and d.device('fs') is None
