@@ -629,12 +629,10 @@ int potrf_batched(const CholBatch& c, cudaStream_t stream) {
         const char* env = getenv("SB200_POTRF_DAG");
         dag = (env && env[0] == '0') ? 0 : ((env && env[0] == '2') ? 2 : 1);     // 2: always (experiments)
     }
-    // measured on B200 (scripts/potrf_ab.py): 1.20 vs 1.45 ms (n=2000, one matrix), 3.04 vs 3.41 ms (n=2000 x 20), 8.43 vs
-    // 8.45 ms (n=4000 x 8), 9.2 vs 10.8 ms (n=8000, one matrix) but 56.8 vs 48.6 ms at n=8000 x 8: a left-looking task
-    // re-reads its 128 operand rows from HBM once the batch no longer fits the 126 MB L2 several times over, where the
-    // recursion's large trailing updates reuse their panels out of L2
-    const bool dag_wins = c.n <= 3000 || (double)c.batch * c.n * c.n <= 1.5e8;
-    if (dag && (dag == 2 || dag_wins) && c.n > NB && potrf_dag_usable(c)) return potrf_dag(c, stream);
+    // measured on B200 (scripts/potrf_ab.py, task graph vs recursion): 1.20 vs 1.46 ms (n=2000, one matrix), 2.54 vs 3.37 ms
+    // (n=2000 x 20), 6.83 vs 8.32 ms (n=4000 x 8), 7.3 vs 10.6 ms (n=8000, one matrix), 44.9 vs 47.4 ms (n=8000 x 8,
+    // 30.4 TFLOP/s) -- the task graph wins at every shape once its operands come in by TMA
+    if (dag && c.n > NB && potrf_dag_usable(c)) return potrf_dag(c, stream);
     return potrf_rec(c, 0, c.n, stream);
 }
 

@@ -85,13 +85,28 @@ __global__ void __launch_bounds__(ST) ptlmc_step_kernel(
             const bool inside = row_valid[b] != 0;
             const double fp = inside ? ll[b] / T : -INFINITY;
             // qadj = -(2 sum(t1 t2) + sum(t2^2)),  t1 = z / sqrt 2,  t2 = (adjrho / 2) ((dfval + dfvalp) @ hc)
+            // the chain's vectors are read from global memory once (registers, d <= MAXD), hc comes from shared memory
+            double gs[MAXD], zz[MAXD], dn[MAXD];
+#pragma unroll
+            for (int i = 0; i < MAXD; i++)
+                if (i < d) {
+                    dn[i] = dll[(long)b * d + i] / T;
+                    gs[i] = dfval[(long)b * d + i] + dn[i];
+                    zz[i] = z[(long)b * d + i];
+                }
             double q1 = 0.0, q2 = 0.0;
             const double ar = adjrho[b];
             for (int j = 0; j < d; j++) {
                 double t2 = 0.0;
-                for (int i = 0; i < d; i++) t2 += (dfval[(long)b * d + i] + dll[(long)b * d + i] / T) * s_hc[i * d + j];
+#pragma unroll
+                for (int i = 0; i < MAXD; i++)
+                    if (i < d) t2 += gs[i] * s_hc[i * d + j];
                 t2 *= 0.5 * ar;
-                q1 += z[(long)b * d + j] * 0.70710678118654752440 * t2;
+                double zj = 0.0;
+#pragma unroll
+                for (int i = 0; i < MAXD; i++)
+                    if (i == j) zj = zz[i];
+                q1 += zj * 0.70710678118654752440 * t2;
                 q2 += t2 * t2;
             }
             const double qadj = -(2.0 * q1 + q2);
@@ -101,10 +116,12 @@ __global__ void __launch_bounds__(ST) ptlmc_step_kernel(
             if (inside && log(u0) < (fp - fval[b]) + qadj) {
                 nacc += 1.0;
                 fval[b] = fp;
-                for (int j = 0; j < d; j++) {
-                    thetac[(long)b * d + j] = thetap[(long)b * d + j];
-                    dfval[(long)b * d + j] = dll[(long)b * d + j] / T;
-                }
+#pragma unroll
+                for (int j = 0; j < MAXD; j++)
+                    if (j < d) {
+                        thetac[(long)b * d + j] = thetap[(long)b * d + j];
+                        dfval[(long)b * d + j] = dn[j];
+                    }
             }
         }
         nacc = block_sum(nacc, s_red);
@@ -130,10 +147,15 @@ __global__ void __launch_bounds__(ST) ptlmc_step_kernel(
         __syncthreads();
         if (tid == 0 && B > 1) {
             double nsw = 0.0;
+            // only the two log-posteriors depend on the previous proposal: its index, threshold and ladder gap are
+            // fetched one proposal ahead so that they are off the serial chain
+            int rt = s_rt[0];
+            double lu = s_logu[0], rh = s_rho[rt];
             for (int j = 0; j < 5 * B; j++) {
-                const int rt = s_rt[j];
+                const int rt_n = s_rt[min(j + 1, 5 * B - 1)];
+                const double lu_n = s_logu[min(j + 1, 5 * B - 1)], rh_n = s_rho[rt_n];
                 const double a = s_lp[rt], b = s_lp[rt - 1];
-                if ((a - b) * s_rho[rt] > s_logu[j]) {
+                if ((a - b) * rh > lu) {
                     s_lp[rt] = b;
                     s_lp[rt - 1] = a;
                     const int t = s_ord[rt - 1];
@@ -141,6 +163,9 @@ __global__ void __launch_bounds__(ST) ptlmc_step_kernel(
                     s_ord[rt] = t;
                     nsw += 1.0;
                 }
+                rt = rt_n;
+                lu = lu_n;
+                rh = rh_n;
             }
             scal[3] += nsw;
         }
@@ -197,12 +222,21 @@ __global__ void __launch_bounds__(ST) ptlmc_step_kernel(
         for (int b = tid; b < B; b += ST) {
             const double ar = adjrho[b];
             bool inside = true;
+            double zz[MAXD], df[MAXD];
+#pragma unroll
+            for (int i = 0; i < MAXD; i++)
+                if (i < d) {
+                    zz[i] = z[(long)b * d + i];
+                    df[i] = dfval[(long)b * d + i];
+                }
             for (int j = 0; j < d; j++) {
                 double zh = 0.0, dc = 0.0;
-                for (int i = 0; i < d; i++) {
-                    zh += z[(long)b * d + i] * s_hc[i * d + j];
-                    dc += dfval[(long)b * d + i] * s_cov[i * d + j];
-                }
+#pragma unroll
+                for (int i = 0; i < MAXD; i++)
+                    if (i < d) {
+                        zh += zz[i] * s_hc[i * d + j];
+                        dc += df[i] * s_cov[i * d + j];
+                    }
                 const double tp = thetac[(long)b * d + j] + 1.41421356237309504880 * ar * zh + ar * ar * dc;
                 thetap[(long)b * d + j] = tp;
                 inside = inside && (tp >= lo[j]) && (tp <= hi[j]);       // NaN -> outside
