@@ -492,11 +492,12 @@ def main():
         evals = k
         traffic, traffic_note = None, None
         try:                                            # DRAM bytes of the DMMA GEMM launches of one step, from the committed ncu run
-            tj = json.load(open(os.path.join(ROOT, 'profiles', 'dram_traffic_r1.json')))['kernels']['dgemm_dmma_kernel']
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'dram_traffic_r2.json')))['kernels']
+            tj = next(v for k, v in tj.items() if k.startswith('dgemm'))
             if not strong:
                 traffic = (tj['dram_read_bytes'] + tj['dram_write_bytes']) / tj['launches']
                 traffic_note = ('ncu dram__bytes_read+write summed over the %d DMMA GEMM launches of one C2 step / launches '
-                                '(profiles/dram_traffic_r1.json): %.2f GB per step'
+                                '(profiles/dram_traffic_r2.json): %.2f GB per step'
                                 % (tj['launches'], (tj['dram_read_bytes'] + tj['dram_write_bytes']) / 1e9))
         except Exception:
             pass
@@ -532,7 +533,7 @@ def main():
             'gpu_launches': int(launches) * world,
             'gpu_launches_per_rank': int(launches),
             'clocks': clk.summary(),
-            'roofline': {'bound': 'tensor', 'kernel': 'dgemm_dmma_kernel (FP64 DMMA.8x8x4)', 'achieved': ach,
+            'roofline': {'bound': 'tensor', 'kernel': 'dgemm_tma_kernel / dgemm_dmma_kernel (FP64 DMMA.8x8x4; TMA-staged where the operands allow)', 'achieved': ach,
                          'peak': peak, 'unit': 'TFLOP/s', 'frac': (ach / peak) if (ach and peak) else None,
                          'traffic': traffic, 'traffic_note': traffic_note, 'launches_timed': g_n, 'gemm_ms_per_step': g_ms.value / K,
                          'gemm_share_of_step': (g_ms.value / K) / ms_dev,
@@ -565,7 +566,7 @@ def roofline_kernels(g_n, g_ms, g_fl, c_n, c_ms, c_fl, K, ms_step, peak):
     ncu --set full captures (profiles/ncu_kernels_r2.json, same command line), marked as such."""
     out = []
     for name, n, ms, fl, what in (
-            ('dgemm_dmma_kernel', g_n, g_ms, g_fl, 'triangular inverse, L^-T L^-1, predict products (and the recursion\'s '
+            ('dgemm_tma_kernel + dgemm_dmma_kernel', g_n, g_ms, g_fl, 'triangular inverse, L^-T L^-1, predict products (and the recursion\'s '
                                                    'trailing updates where the task-graph kernel is not used)'),
             ('potrf_dag_kernel', c_n, c_ms, c_fl, 'batched Cholesky as one persistent task-graph launch (n^3/3 + rhs flop)')):
         if n and ms > 0:

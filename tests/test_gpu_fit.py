@@ -567,3 +567,47 @@ def test_merge_leaders_option_reduces_distinct_factors():
         res[merge] = (int(fi['_b200']['Linv'].shape[0]), float(np.sqrt(np.mean((p['mean'] - truth(tn)) ** 2)) / np.std(truth(tn))))
     report('merge_leaders', factors_off=res[False][0], factors_on=res[True][0], rmse_off=res[False][1], rmse_on=res[True][1])
     assert res[True][0] <= res[False][0] and res[True][1] < 2 * res[False][1] + 0.01
+
+
+def test_clamped_branch_against_the_references_abs_eigenvalues(golden):
+    """where R + e^{h_v} diag(gvar) is slightly indefinite (negative rounding noise in the imputation
+    variance), the reference keeps going with |eigenvalues| (PCGPwM.py:824-827, 840-844) and PCGPwM_B200 clamps the
+    negative variances at 0 and refactors.  This quantifies the difference in what comes out of predict, on the
+    reference-fitted missing-data golden with noise-level negative entries injected until the factorisation fails."""
+    import warnings
+    from surmise_b200.emulationmethods import PCGPwM_B200 as M
+    g = golden('emu_misspd')
+    theta, pc = g['st_theta'], g['st_pc']
+    gv = po.damp_gvar(g['st_unscaled_pcstdvar'], 10, 0.3)
+    hyp = g['st_hyp']
+    k = pc.shape[1]
+    # smallest eigenvalue of component 0's covariance, then three negative entries that push it just below zero
+    base = po.final_factorisation(theta, pc[:, 0], gv[:, 0], hyp[0])
+    lam_min = float(np.linalg.eigvalsh(base['R'])[0])
+    assert lam_min > 0
+    gv_bad = gv.copy()
+    rows = [5, 40, 77]
+    gv_bad[rows, 0] = -3.0 * lam_min / np.exp(hyp[0][-2])
+    ref_state = {'theta': theta, 'pcti': g['st_pcti'], 'standardpcinfo': {'offset': g['st_offset'], 'scale': g['st_scale'],
+                                                                          'extravar': g['st_extravar']}, 'emulist': []}
+    for j in range(k):
+        o = po.final_factorisation(theta, pc[:, j], gv_bad[:, j], hyp[int(g['st_hypind'][j])])
+        o['hypind'] = int(g['st_hypind'][j])
+        ref_state['emulist'].append(o)
+    assert np.linalg.eigvalsh(ref_state['emulist'][0]['R'])[0] < 0          # the reference's |W| branch is live
+    want = {}
+    po.predict(want, ref_state, g['in_x'], g['thetanew'])
+    spc = ref_state['standardpcinfo']
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter('always')
+        emulist, state = M.import_state(theta, pc, gv_bad, hyp, g['st_hypind'], g['st_pcti'], spc)
+    assert any('clamped' in str(w.message) for w in caught) and emulist[0]['gvar_clamped']
+    got = {}
+    M.predict(got, {'_b200': state, 'emulist': emulist, 'x': g['in_x'], 'theta': theta, 'pcti': g['st_pcti'],
+                    'standardpcinfo': spc}, g['in_x'], g['thetanew'])
+    e_mean = rel(got['mean'], want['mean'])
+    e_var = rel(got['var'], want['var'])
+    report('clamped_vs_abs_eigenvalues', lam_min=lam_min, mean=e_mean, var=e_var)
+    # both treatments replace a matrix that is not a covariance by a nearby one that is; the predictions must agree to
+    # the size of the perturbation (3 lam_min ~ the nugget), far inside the emulator's own predictive sd
+    assert e_mean < 1e-3 and e_var < 1e-1
