@@ -56,26 +56,30 @@ struct CovConsts {
 };
 
 constexpr int JC = 256;          // design points per CTA in the predict epilogue
-constexpr int XLD = MAXD + 1;
 
-// Per (PC, 32 new thetas, 256 design points): partial sums over j of
-//   T1^2, r pw, and (with gradients) T2 dr_i, dr_i pw, where dr_i = dR0/dtheta*_i rebuilt from r.
-// DT: compile-time bound on d for the register-resident per-dimension sums
-template <bool WANT_GRAD, int DT>
-__global__ void __launch_bounds__(256, 2) predict_partial_kernel(
-    int n, int d, int B, const double* __restrict__ theta, const double* __restrict__ thetanew,
+// Per (FACTOR, 32 new thetas, 256 design points): partial sums over j of T1^2, r pw and (with gradients) T2 dr_i,
+// dr_i pw, where dr_i = dR0/dtheta*_i is rebuilt from r -- with everything that depends only on the
+// factor computed once for all the components that share it -- T1^2, the derivative dr_i of the cross-covariance
+// (the expensive part: a reciprocal per dimension) and T2 dr_i -- and only the two products with the component's own
+// weights pw_k inside the loop over its members.  At C2 (20 components on 11-14 factors) this is 0.24 -> 0.14 ms of
+// the 1.5 ms a B = 264 evaluation takes.  Members are handled MP at a time (one pass for nearly every factor).
+template <bool WANT_GRAD, int DT, int MP>
+__global__ void __launch_bounds__(256, 2) predict_partial_factor_kernel(
+    int n, int d, int B, int K, const double* __restrict__ theta, const double* __restrict__ thetanew,
     const double* __restrict__ hypcovb, const int* __restrict__ fidx, const int* __restrict__ fu,
     const double* __restrict__ pwb, const double* __restrict__ rTb, long ldb, long strideU,
-    const double* __restrict__ T1b, const double* __restrict__ T2b, long strideT, int /*want_grad*/,
-    double* __restrict__ partial, int nchunks, int Q) {
+    const double* __restrict__ T1b, const double* __restrict__ T2b, long strideT, double* __restrict__ partial,
+    int nchunks, int Q) {
     constexpr bool want_grad = WANT_GRAD;
-    __shared__ double xj[JC * XLD];
-    __shared__ double xb[32 * XLD];
-    __shared__ double pwj[JC];
+    constexpr int XL = DT + 1;                                         // row stride of the staged points (d <= DT)
+    __shared__ double xj[JC * XL];
+    __shared__ double xb[32 * XL];
+    __shared__ double pwj[MP][JC];
     __shared__ double red[8][33];
     __shared__ CovConsts cc;
-    const int k = blockIdx.z, chunk = blockIdx.y, b0 = blockIdx.x * 32;
-    const int f = fidx[k], u = fu[f];
+    __shared__ int s_mem[WOODBURY_MAXK], s_cnt;
+    const int f = blockIdx.z, chunk = blockIdx.y, b0 = blockIdx.x * 32;
+    const int u = fu[f];
     const double* hc = hypcovb + (long)u * (d + 1);
     if (threadIdx.x < d) {
         cc.ell[threadIdx.x] = exp(hc[threadIdx.x]);
@@ -85,67 +89,35 @@ __global__ void __launch_bounds__(256, 2) predict_partial_kernel(
         double e = exp(hc[d]);
         cc.onemc = e / (1.0 + e);
     }
+    if (threadIdx.x == 64) {                                           // the components that use this factor, in order
+        int c = 0;
+        for (int k = 0; k < K; k++)
+            if (fidx[k] == f && c < WOODBURY_MAXK) s_mem[c++] = k;
+        s_cnt = c;
+    }
     __syncthreads();
+    const int cnt = s_cnt;
+    if (cnt == 0) return;
     const int j0 = chunk * JC;
-    for (int idx = threadIdx.x; idx < JC * d; idx += blockDim.x) {
-        int r = idx / d, c = idx % d;
-        xj[r * XLD + c] = (j0 + r < n) ? theta[(long)(j0 + r) * d + c] / cc.ell[c] : 0.0;
+    if (want_grad) {                                                   // the scaled points are only needed for dr_i
+        for (int idx = threadIdx.x; idx < JC * d; idx += blockDim.x) {
+            int r = idx / d, c = idx % d;
+            xj[r * XL + c] = (j0 + r < n) ? theta[(long)(j0 + r) * d + c] / cc.ell[c] : 0.0;
+        }
+        for (int idx = threadIdx.x; idx < 32 * d; idx += blockDim.x) {
+            int r = idx / d, c = idx % d;
+            xb[r * XL + c] = (b0 + r < B) ? thetanew[(long)(b0 + r) * d + c] / cc.ell[c] : 0.0;
+        }
     }
-    for (int idx = threadIdx.x; idx < 32 * d; idx += blockDim.x) {
-        int r = idx / d, c = idx % d;
-        xb[r * XLD + c] = (b0 + r < B) ? thetanew[(long)(b0 + r) * d + c] / cc.ell[c] : 0.0;
-    }
-    for (int idx = threadIdx.x; idx < JC; idx += blockDim.x) pwj[idx] = (j0 + idx < n) ? pwb[(long)k * n + j0 + idx] : 0.0;
-    __syncthreads();
-
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int b = b0 + tx;
-    double s1 = 0.0, s2 = 0.0, dv[DT], dp[DT];
-#pragma unroll
-    for (int i = 0; i < DT; i++) dv[i] = dp[i] = 0.0;
-    if (b < B) {
-        const double* rT = rTb + (long)u * strideU;
-        const double* T1 = T1b + (long)f * strideT;
-        const double* T2 = T2b ? T2b + (long)f * strideT : nullptr;
-        const int jmax = min(JC, n - j0);
-        // unrolled so that the three global loads of several design points are in flight together: the loop is
-        // bound by L2 latency, not by arithmetic
-#pragma unroll(WANT_GRAD ? 2 : 4)
-        for (int jl = ty; jl < jmax; jl += 8) {
-            const int j = j0 + jl;
-            double r = rT[(long)j * ldb + b];
-            double t1 = T1[(long)j * ldb + b];
-            double t2 = want_grad ? T2[(long)j * ldb + b] : 0.0;
-            double pwv = pwj[jl];
-            s1 += t1 * t1;
-            s2 += r * pwv;
-            if (want_grad) {
-                double rp = r - cc.onemc;                          // R_pre
-#pragma unroll
-                for (int i = 0; i < DT; i++)
-                    if (i < d) {
-                        double s = xb[tx * XLD + i] - xj[jl * XLD + i];
-                        double dr = rp * (-cc.ginv[i] * s * __drcp_rn(1.0 + fabs(s)));   // matern_covmat.pyx:13-24
-                        dv[i] += t2 * dr;
-                        dp[i] += dr * pwv;
-                    }
-            }
-        }
-    }
-    // fixed-order reduction over the 8 j-lanes, one quantity at a time
-    double* out = partial + (((long)k * nchunks + chunk) * Q) * ldb;
-    for (int q = 0; q < Q; q++) {
-        double v;
-        if (q == 0) v = s1;
-        else if (q == 1) v = s2;
-        else {
-            int i = (q - 2) >> 1;
-            double sel = 0.0;
-#pragma unroll
-            for (int ii = 0; ii < DT; ii++)
-                if (ii == i) sel = ((q - 2) & 1) ? dp[ii] : dv[ii];
-            v = sel;
-        }
+    const double* rT = rTb + (long)u * strideU;
+    const double* T1 = T1b + (long)f * strideT;
+    const double* T2 = T2b ? T2b + (long)f * strideT : nullptr;
+    const int jmax = min(JC, n - j0);
+
+    // fixed-order reduction over the 8 j-lanes of one quantity, written for component k as quantity q
+    auto emit = [&](double v, int k, int q) {
         __syncthreads();
         red[ty][tx] = v;
         __syncthreads();
@@ -153,7 +125,109 @@ __global__ void __launch_bounds__(256, 2) predict_partial_kernel(
             double s = 0.0;
 #pragma unroll
             for (int r = 0; r < 8; r++) s += red[r][tx];
-            out[(long)q * ldb + b] = s;
+            partial[((((long)k * nchunks + chunk) * Q) + q) * ldb + b] = s;
+        }
+    };
+
+    for (int p0 = 0; p0 < cnt; p0 += MP) {
+        const int np = min(MP, cnt - p0);
+        __syncthreads();                                               // the previous pass is done with pwj
+        for (int idx = threadIdx.x; idx < MP * JC; idx += blockDim.x) {
+            const int mm = idx / JC, jl = idx % JC;
+            pwj[mm][jl] = (mm < np && j0 + jl < n) ? pwb[(long)s_mem[p0 + mm] * n + j0 + jl] : 0.0;
+        }
+        __syncthreads();
+        double s1 = 0.0, dv[DT], s2[MP], dp[MP][DT];
+#pragma unroll
+        for (int i = 0; i < DT; i++) dv[i] = 0.0;
+#pragma unroll
+        for (int mm = 0; mm < MP; mm++) {
+            s2[mm] = 0.0;
+#pragma unroll
+            for (int i = 0; i < DT; i++) dp[mm][i] = 0.0;
+        }
+        if (b < B) {
+            // the three global loads of PF design points go out together, ahead of the arithmetic of the first of them:
+            // with one or two points per trip the loop waited a full L2 round trip per trip (ncu: 22 % of the samples
+            // on the first use of t1)
+            constexpr int PF = 4;
+#pragma unroll 1
+            for (int jb = ty; jb < jmax; jb += 8 * PF) {
+                double rr[PF], tt1[PF], tt2[PF];
+#pragma unroll
+                for (int u2 = 0; u2 < PF; u2++) {
+                    const int jl = jb + 8 * u2;
+                    const bool ok = jl < jmax;
+                    const long off = (long)(j0 + (ok ? jl : jb)) * ldb + b;
+                    rr[u2] = ok ? rT[off] : 0.0;
+                    tt1[u2] = ok ? T1[off] : 0.0;
+                    tt2[u2] = (want_grad && ok) ? T2[off] : 0.0;
+                }
+#pragma unroll
+                for (int u2 = 0; u2 < PF; u2++) {
+                    const int jl = min(jb + 8 * u2, JC - 1);             // (beyond jmax: r = t1 = t2 = 0 contribute nothing)
+                    const bool ok = jb + 8 * u2 < jmax;
+                    const double r = rr[u2], t1 = tt1[u2], t2 = tt2[u2];
+                    double pwv[MP];
+#pragma unroll
+                    for (int mm = 0; mm < MP; mm++) pwv[mm] = ok ? pwj[mm][jl] : 0.0;
+                    s1 += t1 * t1;
+#pragma unroll
+                    for (int mm = 0; mm < MP; mm++) s2[mm] += r * pwv[mm];
+                    if (want_grad && ok) {
+                        const double rp = r - cc.onemc;                // R_pre
+#pragma unroll
+                        for (int i = 0; i < DT; i++)
+                            if (i < d) {
+                                const double s = xb[tx * XL + i] - xj[jl * XL + i];
+                                const double dr = rp * (-cc.ginv[i] * s * __drcp_rn(1.0 + fabs(s)));   // matern_covmat.pyx:13-24
+                                dv[i] += t2 * dr;
+#pragma unroll
+                                for (int mm = 0; mm < MP; mm++) dp[mm][i] += dr * pwv[mm];
+                            }
+                    }
+                }
+            }
+        }
+        // the factor-level sums (T1^2, T2 dr_i) are the same for every member: each gets its copy
+#pragma unroll
+        for (int mm = 0; mm < MP; mm++) {
+            if (mm >= np) break;
+            const int k = s_mem[p0 + mm];
+            emit(s2[mm], k, 1);
+            if (want_grad) {
+#pragma unroll
+                for (int i = 0; i < DT; i++)
+                    if (i < d) emit(dp[mm][i], k, 3 + 2 * i);
+            }
+        }
+        {
+            __syncthreads();
+            red[ty][tx] = s1;
+            __syncthreads();
+            if (ty == 0 && b < B) {
+                double s = 0.0;
+#pragma unroll
+                for (int r = 0; r < 8; r++) s += red[r][tx];
+                for (int mm = 0; mm < np; mm++)
+                    partial[((((long)s_mem[p0 + mm] * nchunks + chunk) * Q) + 0) * ldb + b] = s;
+            }
+        }
+        if (want_grad) {
+#pragma unroll
+            for (int i = 0; i < DT; i++)
+                if (i < d) {
+                    __syncthreads();
+                    red[ty][tx] = dv[i];
+                    __syncthreads();
+                    if (ty == 0 && b < B) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int r = 0; r < 8; r++) s += red[r][tx];
+                        for (int mm = 0; mm < np; mm++)
+                            partial[((((long)s_mem[p0 + mm] * nchunks + chunk) * Q) + 2 + 2 * i) * ldb + b] = s;
+                    }
+                }
         }
     }
 }
@@ -449,16 +523,18 @@ int gp_predict(int K, int nf, int nu, int n, int d, int B, const double* theta, 
         SB_TRY(launch_dgemm(g, nf, -1, stream));
     }
     {
-        dim3 grid(cdiv(B, 32), nchunks, K);
-#define SB_PREDICT_PARTIAL(G, DTV)                                                                                  \
-    predict_partial_kernel<G, DTV><<<grid, 256, 0, stream>>>(n, d, B, theta, thetanew, hypcov, fidx, fu, pw, rT, ldb,   \
-                                                              strideT, T1, T2, strideT, G ? 1 : 0, partial, nchunks, Q)
+        dim3 grid(cdiv(B, 32), nchunks, nf);
+#define SB_PREDICT_PARTIAL(G, DTV, MPV)                                                                             \
+    predict_partial_factor_kernel<G, DTV, MPV><<<grid, 256, 0, stream>>>(n, d, B, K, theta, thetanew, hypcov, fidx, fu, pw, \
+                                                                         rT, ldb, strideT, T1, T2, strideT, partial,    \
+                                                                         nchunks, Q)
+        SB_CHECK_ARG(K <= WOODBURY_MAXK, "gp_predict: k=%d components exceed %d", K, WOODBURY_MAXK);
         if (want_grad) {
-            if (d <= 4) SB_PREDICT_PARTIAL(true, 4);
-            else if (d <= 8) SB_PREDICT_PARTIAL(true, 8);
-            else SB_PREDICT_PARTIAL(true, 16);
+            if (d <= 4) SB_PREDICT_PARTIAL(true, 4, 3);
+            else if (d <= 8) SB_PREDICT_PARTIAL(true, 8, 2);
+            else SB_PREDICT_PARTIAL(true, 16, 1);
         } else {
-            SB_PREDICT_PARTIAL(false, 1);
+            SB_PREDICT_PARTIAL(false, 1, 4);
         }
 #undef SB_PREDICT_PARTIAL
         SB_LAUNCH_CHECK();
