@@ -683,6 +683,9 @@ __global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p, const __gri
         __syncthreads();
         if (tid == 0) atomicAdd(p.prog + (long)z * p.mtp + tI, 1);
     }
+    // a dependency that never arrived (SPIN_LIMIT) aborted the waits: the factors are not valid, say so for every matrix
+    if (ld_acquire(abort_flag))
+        for (int zz = tid; zz < p.batch; zz += DT) p.info[zz] = 0x7fffffff;
     if (p.stats && tid == 0) {
         long long* st = p.stats + 8 * (long)blockIdx.x;
         st[0] = clock64() - c_begin;

@@ -116,6 +116,18 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// 1 / x for x known to be a normal number >= 1 (here always 1 + |s|): MUFU.RCP64H seed and two Newton steps, branch
+// free.  __drcp_rn adds a range check and a slow path (BSSY / BRA / BSYNC around every call) that these loops, which
+// take one reciprocal per pair and dimension, do not need; the result is within 1 ulp of the rounded quotient.
+__device__ __forceinline__ double rcp_ge1(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
 // block-wide sum; `red` must hold >= 32 doubles; result valid in all threads
 __device__ __forceinline__ double block_sum(double v, double* red) {
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

@@ -191,36 +191,47 @@ __global__ void __launch_bounds__(256, DT <= 8 ? 3 : 2) gp_grad_contract_kernel(
     if (j < n) {
         const double aj = alpha[j];
         const double* b = xb + tx * XLD;
-        for (int r = ty; r < GT; r += 4) {
-            int i = i0 + r;
-            if (i >= n) break;
-            if (j > i) continue;
-            double w = 0.5 * Rinv[(long)i * ldr + j] - cq * alpha[i] * aj;
-            if (i == j) {                                          // only d/dh_v lives on the diagonal
-                if (gvarb) acc_v += w * gc.ev * gvarb[(long)z * strideGvar + i];
-                continue;
+        // four rows per trip: their W entries are loaded together, ahead of the arithmetic of the first
+        constexpr int PF = 4;
+#pragma unroll 1
+        for (int rb = ty; rb < GT; rb += 4 * PF) {
+            double wl[PF];
+#pragma unroll
+            for (int u2 = 0; u2 < PF; u2++) {
+                const int i = i0 + rb + 4 * u2;
+                wl[u2] = (i < n && j <= i) ? (0.5 * Rinv[(long)i * ldr + j] - cq * alpha[i] * aj) : 0.0;
             }
-            w *= 2.0;                                              // (a,b) and (b,a)
-            const double* a = xa + r * XLD;
-            double prod = gc.c, ssum = 0.0, wsum[DT];
 #pragma unroll
-            for (int k = 0; k < DT; k++)
-                if (k < d) {
-                    double S = fabs(a[k] - b[k]);
-                    double op = 1.0 + S;
-                    prod *= op;
-                    ssum -= S;
-                    // dR0/dgamma_k / R_pre.  (One reciprocal of the product plus leave-one-out products was
-                    // measured slower: the kernel is FP64-pipe bound and __drcp_rn is only a few DFMAs.)
-                    wsum[k] = (S * S) * __drcp_rn(op);
+            for (int u2 = 0; u2 < PF; u2++) {
+                const int r = rb + 4 * u2, i = i0 + r;
+                if (i >= n || j > i) continue;
+                double w = wl[u2];
+                if (i == j) {                                          // only d/dh_v lives on the diagonal
+                    if (gvarb) acc_v += w * gc.ev * gvarb[(long)z * strideGvar + i];
+                    continue;
                 }
-            double rp = prod * exp(ssum);
-            double wr = w * omn * rp;
+                w *= 2.0;                                              // (a,b) and (b,a)
+                const double* a = xa + r * XLD;
+                double prod = gc.c, ssum = 0.0, wsum[DT];
 #pragma unroll
-            for (int k = 0; k < DT; k++)
-                if (k < d) acc[k] += wr * wsum[k];                 // (1-nu) dR0/dgamma_k
-            acc_g += w * omn * gc.onemc * (gc.c - rp);             // (1-nu) dR0/dgamma_d
-            acc_n -= w * gc.nu * omn * (rp + gc.onemc);            // nu (1-nu) (I - R0), PCGPwM.py:878
+                for (int k = 0; k < DT; k++)
+                    if (k < d) {
+                        double S = fabs(a[k] - b[k]);
+                        double op = 1.0 + S;
+                        prod *= op;
+                        ssum -= S;
+                        // dR0/dgamma_k / R_pre.  (One reciprocal of the product plus leave-one-out products was
+                        // measured slower: the kernel is FP64-pipe bound and the reciprocal is only a few DFMAs.)
+                        wsum[k] = (S * S) * rcp_ge1(op);
+                    }
+                double rp = prod * exp(ssum);
+                double wr = w * omn * rp;
+#pragma unroll
+                for (int k = 0; k < DT; k++)
+                    if (k < d) acc[k] += wr * wsum[k];                 // (1-nu) dR0/dgamma_k
+                acc_g += w * omn * gc.onemc * (gc.c - rp);             // (1-nu) dR0/dgamma_d
+                acc_n -= w * gc.nu * omn * (rp + gc.onemc);            // nu (1-nu) (I - R0), PCGPwM.py:878
+            }
         }
     }
     // warp shuffles, then one pass through shared memory (fixed order)

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256, 2) predict_partial_factor_kernel(
                         for (int i = 0; i < DT; i++)
                             if (i < d) {
                                 const double s = xb[tx * XL + i] - xj[jl * XL + i];
-                                const double dr = rp * (-cc.ginv[i] * s * __drcp_rn(1.0 + fabs(s)));   // matern_covmat.pyx:13-24
+                                const double dr = rp * (-cc.ginv[i] * s * rcp_ge1(1.0 + fabs(s)));   // matern_covmat.pyx:13-24
                                 dv[i] += t2 * dr;
 #pragma unroll
                                 for (int mm = 0; mm < MP; mm++) dp[mm][i] += dr * pwv[mm];
