@@ -4,6 +4,7 @@
 // write with the fastest thread index along the contiguous output dimension.
 // Standalone covmat is HBM-write bound: 8 n1 n2 (+ 8 D n1 n2 with gradients) bytes.
 #include "covmat.cuh"
+#include "covmat_dev.cuh"
 
 namespace sb {
 namespace {
@@ -11,15 +12,10 @@ namespace {
 constexpr int TS = 32;            // tile side
 constexpr int XLD = MAXD + 1;     // padded row length of the staged coordinates
 
-struct PairConsts {
-    double c;        // 1 / (1 + exp(gamma_d))
-    double onemc;    // exp(gamma_d) / (1 + exp(gamma_d))
-};
-
-__device__ __forceinline__ PairConsts pair_consts(double gamma_d) {
-    double e = exp(gamma_d);
-    return PairConsts{1.0 / (1.0 + e), e / (1.0 + e)};
-}
+using gpdev::PairConsts;
+using gpdev::pair_consts;
+using gpdev::GpConsts;
+using gpdev::load_gp_consts;
 
 // R_pre = c prod(1+S_k) exp(-sum S_k)                       (matern_covmat.pyx:34-48)
 __device__ __forceinline__ double rpre_pair(const double* a, const double* b, int d, double c) {
@@ -80,23 +76,6 @@ __global__ void __launch_bounds__(256) matern_covmat_kernel(const double* __rest
                 dR[k * plane + (long)i * n2 + j] = (-ginv[k] * s / (1.0 + fabs(s))) * rp;
             }
         }
-    }
-}
-
-struct GpConsts {
-    double ell[MAXD];
-    double c, onemc, nu, ev;
-};
-
-__device__ __forceinline__ void load_gp_consts(GpConsts* gc, const double* __restrict__ hyp, int d) {
-    if (threadIdx.x < d) gc->ell[threadIdx.x] = exp(hyp[threadIdx.x]);
-    if (threadIdx.x == 32) {
-        PairConsts pc = pair_consts(hyp[d]);
-        gc->c = pc.c;
-        gc->onemc = pc.onemc;
-        double e = exp(hyp[d + 2]);
-        gc->nu = e / (1.0 + e);                                    // PCGPwM.py:853
-        gc->ev = exp(hyp[d + 1]);
     }
 }
 
@@ -182,9 +161,8 @@ __global__ void __launch_bounds__(256, DT <= 8 ? 3 : 2) gp_grad_contract_kernel(
     __syncthreads();
     const double cq = 0.5 * n / ((n + s0) * sig2hat[z]);           // PCGPwM.py:898-902
     const double omn = 1.0 - gc.nu;
-    double acc[DT], acc_g = 0.0, acc_v = 0.0, acc_n = 0.0;      // length-scales | gamma_d | h_v | h_nu
-#pragma unroll
-    for (int k = 0; k < DT; k++) acc[k] = 0.0;
+    gpdev::GradAcc<DT> G;                                           // length-scales | gamma_d | h_v | h_nu
+    G.clear();
 
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int j = j0 + tx;
@@ -207,30 +185,10 @@ __global__ void __launch_bounds__(256, DT <= 8 ? 3 : 2) gp_grad_contract_kernel(
                 if (i >= n || j > i) continue;
                 double w = wl[u2];
                 if (i == j) {                                          // only d/dh_v lives on the diagonal
-                    if (gvarb) acc_v += w * gc.ev * gvarb[(long)z * strideGvar + i];
+                    if (gvarb) G.v += w * gc.ev * gvarb[(long)z * strideGvar + i];
                     continue;
                 }
-                w *= 2.0;                                              // (a,b) and (b,a)
-                const double* a = xa + r * XLD;
-                double prod = gc.c, ssum = 0.0, wsum[DT];
-#pragma unroll
-                for (int k = 0; k < DT; k++)
-                    if (k < d) {
-                        double S = fabs(a[k] - b[k]);
-                        double op = 1.0 + S;
-                        prod *= op;
-                        ssum -= S;
-                        // dR0/dgamma_k / R_pre.  (One reciprocal of the product plus leave-one-out products was
-                        // measured slower: the kernel is FP64-pipe bound and the reciprocal is only a few DFMAs.)
-                        wsum[k] = (S * S) * rcp_ge1(op);
-                    }
-                double rp = prod * exp(ssum);
-                double wr = w * omn * rp;
-#pragma unroll
-                for (int k = 0; k < DT; k++)
-                    if (k < d) acc[k] += wr * wsum[k];                 // (1-nu) dR0/dgamma_k
-                acc_g += w * omn * gc.onemc * (gc.c - rp);             // (1-nu) dR0/dgamma_d
-                acc_n -= w * gc.nu * omn * (rp + gc.onemc);            // nu (1-nu) (I - R0), PCGPwM.py:878
+                gpdev::contract_offdiag<DT>(G, w, xa + r * XLD, b, d, gc, omn);
             }
         }
     }
@@ -239,11 +197,11 @@ __global__ void __launch_bounds__(256, DT <= 8 ? 3 : 2) gp_grad_contract_kernel(
 #pragma unroll
     for (int k = 0; k < DT; k++)
         if (k < d) {
-            double sv = warp_sum(acc[k]);
+            double sv = warp_sum(G.ls[k]);
             if (lane == 0) red[k][warp] = sv;
         }
     {
-        double sg = warp_sum(acc_g), sv = warp_sum(acc_v), sn = warp_sum(acc_n);
+        double sg = warp_sum(G.g), sv = warp_sum(G.v), sn = warp_sum(G.nn);
         if (lane == 0) {
             red[d][warp] = sg;
             red[d + 1][warp] = sv;
@@ -349,6 +307,13 @@ int gp_grad_contract(int batch, int n, int d, const double* theta, long strideTh
     else gp_grad_contract_kernel<16><<<grid, 256, 0, stream>>>(n, d, theta, strideTheta, gvar, strideGvar, hyp, Rinv, ldr,
                                                       strideR, alpha, strideAlpha, sig2hat, s0, partial, ntiles);
     SB_LAUNCH_CHECK();
+    gp_grad_finalize_kernel<<<batch, 32 * (d + 3), 0, stream>>>(d, ntiles, partial, hyp, regmean, regstd, grad);
+    SB_LAUNCH_CHECK();
+    return 0;
+}
+
+int gp_grad_finalize(int batch, int d, int ntiles, const double* partial, const double* hyp, const double* regmean,
+                     const double* regstd, double* grad, cudaStream_t stream) {
     gp_grad_finalize_kernel<<<batch, 32 * (d + 3), 0, stream>>>(d, ntiles, partial, hyp, regmean, regstd, grad);
     SB_LAUNCH_CHECK();
     return 0;

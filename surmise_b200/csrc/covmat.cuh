@@ -23,6 +23,10 @@ int gp_grad_contract(int batch, int n, int d, const double* theta, long strideTh
                      const double* Rinv, long ldr, long strideR, const double* alpha, long strideAlpha,
                      const double* sig2hat, double s0, double* partial, double* grad, cudaStream_t stream);
 int grad_contract_tiles(int n);
+// the fixed-order sum over the tile partials plus the prior term (second half of gp_grad_contract; also finishes the
+// partials written by the GEMM's contraction epilogue, dgemm.cuh GradContractEpilogue)
+int gp_grad_finalize(int batch, int d, int ntiles, const double* partial, const double* hyp, const double* regmean,
+                     const double* regstd, double* grad, cudaStream_t stream);
 
 // rT[u][j][b] = R0(thetanew_b, theta_j; hypcov_u)   (b contiguous, leading dimension ldb)
 int cross_cov_t(int nu, int n, int d, int B, const double* theta, const double* thetanew, const double* hypcov,
