@@ -248,7 +248,31 @@ def _missing_index(miss, torch):
     return idx, valid
 
 
-def _impute_schur(Up, sp2, eps_impute, cur, obs, idx, valid, ops, torch):
+def _all_kept_projector(G, eps_pc, eps_impute, ops, torch):
+    """P = U diag((lam - eps_pc) / (lam - eps_pc + eps_impute)) U' WITHOUT an eigen-decomposition, for a sweep in which
+    every one of the m components passes the threshold (the first imputation sweeps: the +-2 seed pollutes every
+    direction).  Then P is a rational function of G alone,
+        P = I - eps_impute (G - (eps_pc - eps_impute) I)^-1,
+    i.e. one SPD inverse on the blocked Cholesky / trtri / lauum kernels.  Returns None unless G - eps_pc I is positive
+    definite (checked by a Cholesky factorisation: exactly the reference's condition S^2 - eps_pc > 0 for all S)."""
+    m = G.shape[0]
+    lda = (m + 7) // 8 * 8
+    eye = torch.eye(m, dtype=G.dtype, device=G.device)
+    W = torch.zeros((2, m, lda), dtype=G.dtype, device=G.device)
+    W[0, :, :m] = G - eps_pc * eye
+    W[1, :, :m] = G - (eps_pc - eps_impute) * eye
+    if m <= ops.small_max_n():
+        return None                                   # tiny problems: the eigen path is cheap enough
+    Linv, info = ops.potrf_batched(W, m, m)
+    if bool((info != 0).any()):
+        return None
+    ops.trtri_batched(W, Linv, m)
+    low = torch.tril(ops.lauum_batched(Linv[1:2], m)[0, :, :m])
+    Ainv = low + torch.tril(low, -1).T
+    return eye - eps_impute * Ainv
+
+
+def _impute_schur(Up, sp2, eps_impute, cur, obs, idx, valid, ops, torch, P=None):
     """The ridge update of the missing entries (PCGPwM.py:576-586) through the |missing| x |missing| system.
 
     The reference solves, per row, the k x k system (H + D) sol = J with H = Up' diag(obs) Up, D = diag(eps / sp2),
@@ -256,26 +280,28 @@ def _impute_schur(Up, sp2, eps_impute, cur, obs, idx, valid, ops, torch):
     H + D = Lam - M' M with Lam = I + D and M = Up[missing rows of this output row], and by the Woodbury identity the
     filled values are  w = (I - P_mm)^-1 P_mo cur_o  with P = Up Lam^-1 Up' (m x m, once per sweep): one GEMM for
     all rows plus a batched Cholesky of size |missing| instead of size k.  Early sweeps keep k ~ m components
-    (k^3 per row); |missing| is the missing fraction of m.  Returns the filled values, (nr, qmax), 0 where padded."""
-    lam_inv = sp2 / (sp2 + eps_impute)
-    P = ops.mm((Up * lam_inv).contiguous(), Up.contiguous(), tb=True)
+    (k^3 per row); |missing| is the missing fraction of m.  P may be handed in (see _all_kept_projector).
+    Returns the filled values, (nr, qmax), 0 where padded."""
+    if P is None:
+        lam_inv = sp2 / (sp2 + eps_impute)
+        P = ops.mm((Up * lam_inv).contiguous(), Up.contiguous(), tb=True)
     Z = ops.mm((obs * cur).contiguous(), P)                        # (nr, m): P_{.,o} cur_o for every column
     z = torch.gather(Z, 1, idx) * valid
     nr, qmax = idx.shape
     w = torch.zeros_like(z)
-    eye = torch.eye(qmax, dtype=Up.dtype, device=Up.device)
+    eye = torch.eye(qmax, dtype=cur.dtype, device=cur.device)
     per_row = 8 * qmax * qmax * 4
     step = max(1, min(nr, _batch_cap(qmax, ops), _CHUNK_BYTES // max(per_row, 1)))
     small = qmax <= ops.small_max_n()                 # the register-resident sweep kernel solves these directly
     for lo in range(0, nr, step):
         hi = min(lo + step, nr)
         ii = idx[lo:hi]
-        vv = valid[lo:hi].to(Up.dtype)
+        vv = valid[lo:hi].to(cur.dtype)
         S = P[ii[:, :, None], ii[:, None, :]] * (vv[:, :, None] * vv[:, None, :])
         S = eye - S                                                # padded rows / columns: identity
         if small:
             lda = (qmax + 7) // 8 * 8
-            A = torch.zeros((hi - lo, qmax + 1, lda), dtype=Up.dtype, device=Up.device)
+            A = torch.zeros((hi - lo, qmax + 1, lda), dtype=cur.dtype, device=cur.device)
             A[:, :qmax, :qmax] = S
             A[:, qmax, :qmax] = z[lo:hi]
             info = ops.spd_solve_small(A, qmax)
@@ -319,11 +345,22 @@ def standardize(f, eps_pc, eps_impute, n_iter=40):
         miss = miss_all[rows].bool()
         obs = (~miss).to(torch.float64)
         idx, valid = _missing_index(miss, torch)
-        warm, pad = None, 8
+        warm, pad, retry_block = None, 8, False
         cap = ops.syevj_max_p()
+        all_kept = True                                           # until a sweep says otherwise (it starts that way)
         for sweep in range(n_iter):                               # PCGPwM.py:573-587
             G = ops.mm(fs, fs, ta=True)
-            if warm is not None or sweep == 0:
+            cur = fs[rows]
+            if all_kept and G.shape[0] > idx.shape[1]:
+                P = _all_kept_projector(G, eps_pc, eps_impute, ops, torch)
+                if P is not None:                                 # every component kept: no decomposition needed
+                    note['all_kept_sweeps'] = note.get('all_kept_sweeps', 0) + 1
+                    note.setdefault('kept_per_sweep', []).append(int(G.shape[0]))
+                    w = _impute_schur(None, None, eps_impute, cur, obs, idx, valid, ops, torch, P=P)
+                    fs[rows] = cur.scatter(1, idx, torch.where(valid, w, torch.gather(cur, 1, idx)))
+                    continue
+                all_kept = False
+            if warm is not None or sweep == 0 or retry_block:
                 U, lam = _eig_above(G, eps_pc, warm, ops, torch, note)
             else:                                                 # the last sweep kept more components than a block holds
                 U, lam = _full_eig(G, torch)
@@ -332,8 +369,11 @@ def standardize(f, eps_pc, eps_impute, n_iter=40):
             Up = U[:, keep].contiguous()
             sp2 = lam[keep] - eps_pc
             nk = int(Up.shape[1])
+            note.setdefault('kept_per_sweep', []).append(nk)
             warm = U[:, :min(nk + pad, U.shape[1])] if nk + pad <= cap else None
-            cur = fs[rows]
+            # the count collapses within a few sweeps (C3: 1000, 1000, 1000, 675, 261, 35, 33, ...): once it has at least
+            # halved towards the block size, try the block iteration (two cheap steps tell if the block is too small)
+            retry_block = warm is None and nk <= 4 * cap
             if nk > idx.shape[1]:                                 # more components than missing entries per row
                 w = _impute_schur(Up, sp2, eps_impute, cur, obs, idx, valid, ops, torch)
                 filled = cur.scatter(1, idx, torch.where(valid, w, torch.gather(cur, 1, idx)))
