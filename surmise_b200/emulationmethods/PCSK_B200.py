@@ -26,40 +26,42 @@ def hyper_prior(theta):
 
 
 def standardize(f):
-    """PCSK.py:353-386 for complete data: column offset / scale, no imputation, extravar = 0."""
-    offset = np.zeros(f.shape[1])
-    scale = np.zeros(f.shape[1])
-    for k in range(f.shape[1]):
-        offset[k] = np.nanmean(f[:, k])
-        scale[k] = np.nanstd(f[:, k]) / np.sqrt(1 - np.isnan(f[:, k]).mean())
-        if scale[k] == 0:
-            raise ValueError("You have a row that is non-varying.")
-    return {'offset': offset, 'scale': scale, 'fs': (f - offset) / scale, 'extravar': 0 * scale}
+    """Column-wise standardisation of the (n, m) outputs, PCSK has no imputation (PCSK.py:353-386): the offset is the
+    mean over the finite cells, the scale their standard deviation inflated by 1/sqrt(observed fraction)."""
+    seen = np.isfinite(f) | np.isinf(f)                       # only NaN counts as missing, as in the reference
+    count = seen.sum(axis=0)
+    offset = np.nansum(f, axis=0) / count
+    centred = np.where(seen, f - offset, 0.0)
+    scale = np.sqrt((centred ** 2).sum(axis=0) / count) / np.sqrt(count / f.shape[0])
+    if not np.all(scale != 0):
+        raise ValueError("You have a row that is non-varying.")
+    return dict(offset=offset, scale=scale, fs=(f - offset) / scale, extravar=np.zeros_like(scale))
 
 
 def principal_components(fitinfo, simsd):
-    """PCSK.py:389-424: components kept where S^2 > epsilonPC and the simulation noise does not dominate."""
+    """Loadings, scores and the per-component share of simulation noise (PCSK.py:389-424).  A user-supplied basis is
+    taken as is; otherwise the left singular vectors of fs' are kept where S^2 > epsilonPC and the standardised
+    simulation variance, projected on the component, stays below 8 times the component's own variance (or the first
+    `numpcs` of them when that is positive)."""
     spc = fitinfo['standardpcinfo']
     fs = spc['fs']
-    stdvarsadj = (simsd.T / spc['scale']) ** 2
+    noise = np.square(simsd.T / spc['scale'])                 # (n, m) simulation variances in standardised units
+
+    def noise_share(basis):
+        return (noise @ np.square(basis)) / np.var(fs @ basis, axis=0)
+
     if 'U' in spc:
-        pct, pcw = 1 * spc['U'], 1 * spc['S']
+        basis, weights = np.array(spc['U'], copy=True), np.array(spc['S'], copy=True)
     else:
-        U, S, _ = np.linalg.svd(fs.T, full_matrices=False)
-        pc = fs @ U
-        ucpcsc = (stdvarsadj @ (U ** 2)) / (pc.var(0))
-        if fitinfo['numpcs'] <= 0:
-            keep = (ucpcsc.mean(0) < 8.) * (S ** 2 > fitinfo['epsilonPC'])
+        U, S, _vt = np.linalg.svd(fs.T, full_matrices=False)
+        if fitinfo['numpcs'] > 0:
+            chosen = np.arange(fitinfo['numpcs'])
         else:
-            keep = range(0, fitinfo['numpcs'])
-        pct = U[:, keep]
-        pcw = np.sqrt((S ** 2)[keep])
-    fitinfo['pcw'] = pcw
-    fitinfo['pcto'] = 1 * pct
-    fitinfo['pct'] = pct
-    fitinfo['pcti'] = pct
-    fitinfo['pc'] = fs @ pct
-    fitinfo['unscaled_pcstdvar'] = (stdvarsadj @ (pct ** 2)) / (fitinfo['pc'].var(0))
+            chosen = np.flatnonzero((noise_share(U).mean(axis=0) < 8.0) & (S ** 2 > fitinfo['epsilonPC']))
+        basis, weights = U[:, chosen], S[chosen]
+    scores = fs @ basis
+    fitinfo.update(pcw=weights, pcto=basis.copy(), pct=basis, pcti=basis, pc=scores,
+                   unscaled_pcstdvar=(noise @ np.square(basis)) / scores.var(axis=0))
 
 
 def fit(fitinfo, x, theta, f, epsilonPC=0.001, lognugmean=-10, lognugLB=-20, varconstant=None, dampalpha=0.3,
