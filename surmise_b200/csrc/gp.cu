@@ -57,6 +57,27 @@ struct CovConsts {
 
 constexpr int JC = 256;          // design points per CTA in the predict epilogue
 
+// members of every factor: mem_off (nf + 1) and mem_list (K), components in increasing order within a factor
+__global__ void __launch_bounds__(256) factor_members_kernel(int K, int nf, const int* __restrict__ fidx,
+                                                             int* __restrict__ mem_off, int* __restrict__ mem_list) {
+    for (int f = threadIdx.x; f < nf; f += blockDim.x) {
+        int c = 0;
+        for (int k = 0; k < K; k++) c += (fidx[k] == f);
+        mem_off[f + 1] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mem_off[0] = 0;
+        for (int f = 0; f < nf; f++) mem_off[f + 1] += mem_off[f];
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < nf; f += blockDim.x) {
+        int o = mem_off[f];
+        for (int k = 0; k < K; k++)
+            if (fidx[k] == f) mem_list[o++] = k;
+    }
+}
+
 // Per (FACTOR, 32 new thetas, 256 design points): partial sums over j of T1^2, r pw and (with gradients) T2 dr_i,
 // dr_i pw, where dr_i = dR0/dtheta*_i is rebuilt from r -- with everything that depends only on the
 // factor computed once for all the components that share it -- T1^2, the derivative dr_i of the cross-covariance
@@ -66,8 +87,8 @@ constexpr int JC = 256;          // design points per CTA in the predict epilogu
 template <bool WANT_GRAD, int DT, int MP>
 __global__ void __launch_bounds__(256, 2) predict_partial_factor_kernel(
     int n, int d, int B, int K, const double* __restrict__ theta, const double* __restrict__ thetanew,
-    const double* __restrict__ hypcovb, const int* __restrict__ fidx, const int* __restrict__ fu,
-    const double* __restrict__ pwb, const double* __restrict__ rTb, long ldb, long strideU,
+    const double* __restrict__ hypcovb, const int* __restrict__ mem_off, const int* __restrict__ mem_list,
+    const int* __restrict__ fu, const double* __restrict__ pwb, const double* __restrict__ rTb, long ldb, long strideU,
     const double* __restrict__ T1b, const double* __restrict__ T2b, long strideT, double* __restrict__ partial,
     int nchunks, int Q) {
     constexpr bool want_grad = WANT_GRAD;
@@ -77,7 +98,6 @@ __global__ void __launch_bounds__(256, 2) predict_partial_factor_kernel(
     __shared__ double pwj[MP][JC];
     __shared__ double red[8][33];
     __shared__ CovConsts cc;
-    __shared__ int s_mem[WOODBURY_MAXK], s_cnt;
     const int f = blockIdx.z, chunk = blockIdx.y, b0 = blockIdx.x * 32;
     const int u = fu[f];
     const double* hc = hypcovb + (long)u * (d + 1);
@@ -89,15 +109,10 @@ __global__ void __launch_bounds__(256, 2) predict_partial_factor_kernel(
         double e = exp(hc[d]);
         cc.onemc = e / (1.0 + e);
     }
-    if (threadIdx.x == 64) {                                           // the components that use this factor, in order
-        int c = 0;
-        for (int k = 0; k < K; k++)
-            if (fidx[k] == f && c < WOODBURY_MAXK) s_mem[c++] = k;
-        s_cnt = c;
-    }
-    __syncthreads();
-    const int cnt = s_cnt;
+    const int* s_mem = mem_list + mem_off[f];                          // the components that use this factor, in order
+    const int cnt = mem_off[f + 1] - mem_off[f];
     if (cnt == 0) return;
+    __syncthreads();
     const int j0 = chunk * JC;
     if (want_grad) {                                                   // the scaled points are only needed for dr_i
         for (int idx = threadIdx.x; idx < JC * d; idx += blockDim.x) {
@@ -474,6 +489,7 @@ size_t gp_predict_workspace(int K, int nf, int nu, int n, int d, int B, int want
     w.take<double>((size_t)nf * n * ldb);
     if (want_grad) w.take<double>((size_t)nf * n * ldb);
     w.take<double>((size_t)K * cdiv(n, JC) * Q * ldb);
+    w.take<int>((size_t)nf + 1 + K);                 // members of every factor
     return w.off;
 }
 
@@ -502,6 +518,8 @@ int gp_predict(int K, int nf, int nu, int n, int d, int B, const double* theta, 
     double* T1 = w.take<double>((size_t)nf * strideT);
     double* T2 = want_grad ? w.take<double>((size_t)nf * strideT) : nullptr;
     double* partial = w.take<double>((size_t)K * nchunks * Q * ldb);
+    int* mem_off = w.take<int>((size_t)nf + 1 + K);
+    int* mem_list = mem_off + nf + 1;
 
     SB_TRY(cross_cov_t(nu, n, d, B, theta, thetanew, hypcov, rT, ldb, strideT, stream));
     {                                           // T1 = Linv r'            (n x B per factor)
@@ -525,10 +543,11 @@ int gp_predict(int K, int nf, int nu, int n, int d, int B, const double* theta, 
     {
         dim3 grid(cdiv(B, 32), nchunks, nf);
 #define SB_PREDICT_PARTIAL(G, DTV, MPV)                                                                             \
-    predict_partial_factor_kernel<G, DTV, MPV><<<grid, 256, 0, stream>>>(n, d, B, K, theta, thetanew, hypcov, fidx, fu, pw, \
+    predict_partial_factor_kernel<G, DTV, MPV><<<grid, 256, 0, stream>>>(n, d, B, K, theta, thetanew, hypcov, mem_off, mem_list, fu, pw, \
                                                                          rT, ldb, strideT, T1, T2, strideT, partial,    \
                                                                          nchunks, Q)
-        SB_CHECK_ARG(K <= WOODBURY_MAXK, "gp_predict: k=%d components exceed %d", K, WOODBURY_MAXK);
+        factor_members_kernel<<<1, 256, 0, stream>>>(K, nf, fidx, mem_off, mem_list);
+        SB_LAUNCH_CHECK();
         if (want_grad) {
             if (d <= 4) SB_PREDICT_PARTIAL(true, 4, 3);
             else if (d <= 8) SB_PREDICT_PARTIAL(true, 8, 2);
