@@ -720,7 +720,7 @@ def c5_run(C, fi, w, y, yvar, torch, sampperchain, sampler='PTLMC_B200', **extra
             'posterior_mean_abs_err': float(np.mean(np.abs(post.mean(0) - w['theta_true'][0]))),
             'distinct_factors': int(fi['_b200'].get('nf_total', fi['_b200']['Linv'].shape[0])),
             'device_chain': {k: v for k, v in cal.get('_b200sampler', {}).items()
-                             if k in ('cuda_graph', 'steps_per_graph', 'accept_rate', 'swap_rate', 'preoptimise_s',
+                             if k in ('cuda_graph', 'steps_per_graph', 'accept_rate', 'swap_rate', 'preoptimise_s', 'exchange',
                                       'setup_and_capture_s', 'loop_s', 'ms_per_step_in_loop')}}
 
 

@@ -6,7 +6,7 @@ import sys
 ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, 'surmise_b200', 'csrc')
 OUT = os.path.join(ROOT, 'surmise_b200', 'lib', 'libsurmise_b200.so')
-SOURCES = ['capi.cu', 'dgemm.cu', 'chol.cu', 'covmat.cu', 'gp.cu', 'woodbury.cu', 'nll_small.cu', 'sampler.cu', 'pca.cu', 'chol_dag.cu', 'dgemm_tma.cu']
+SOURCES = ['capi.cu', 'dgemm.cu', 'chol.cu', 'covmat.cu', 'gp.cu', 'woodbury.cu', 'nll_small.cu', 'sampler.cu', 'pca.cu', 'chol_dag.cu', 'dgemm_tma.cu', 'peer.cu']
 
 
 STAMP = OUT + '.srchash'

@@ -132,15 +132,18 @@ int sb200_pc_backproject(int m, int k, int B, int d, const double* phi, const do
  *   device masks the others here; their ll / dll are still written and are the caller's to discard.
  *   seg_k, seg_stride: 0, 0 for dense (B,k) / (B,k,d) inputs.  Otherwise the k components arrive in k / seg_k groups,
  *   each a dense (B, seg_k[, d]) block, consecutive groups seg_stride doubles apart -- exactly what an all-gather of the
- *   per-rank blocks of a PC-sharded prediction (sb200_gp_predict with out_ld = seg_k) leaves in memory; phiT / G are
- *   then given in that component order, with zero rows for padded components. */
+ *   per-rank blocks of a PC-sharded prediction (sb200_gp_predict with out_ld = seg_k) leaves in memory.  seg_pos NULL:
+ *   k counts the padded slots too and phiT / G are given in that order, with zero rows for the padded components;
+ *   seg_pos (k ints, device): k counts the REAL components only, seg_pos[a] is the padded slot of component a, and
+ *   phiT / G are the ordinary (k, m) / (2, k, k) arrays -- the k x k work then does not grow with the number of ranks. */
 int sb200_woodbury_loglik(int B, int k, int m, int d, const double* predvecs, const double* predvars,
                           const double* predvecs_grad, const double* predvars_grad, const double* phiT,
                           const double* resid0, const double* extravar, const double* sinv, const double* G,
                           int want_grad, int variant, double* ll, double* dll, int* fired, const int* row_valid,
-                          int seg_k, long seg_stride, void* stream);
+                          int seg_k, long seg_stride, const int* seg_pos, void* stream);
 int sb200_woodbury_trigger(int B, int k, int m, const double* predvars, const double* phiT, const double* extravar,
-                           int* fired, const int* row_valid, int seg_k, long seg_stride, void* stream);
+                           int* fired, const int* row_valid, int seg_k, long seg_stride, const int* seg_pos,
+                           void* stream);
 
 /* One step of the device-resident PT-LMC sampler: what surmise's PTLMC (utilitiesmethods/PTLMC.py:203-273) does between
  * two evaluations of the log-posterior, for a population of B = numtemps + numchain chains kept on the device.
@@ -216,6 +219,21 @@ int sb200_pca_sumsq(long count, const double* x, double* out, double* scratch, v
 int sb200_syevj_max_p(void);
 int sb200_syevj_batched(int batch, int p, const double* H, long ldh, long stride_h, double* W, long stride_w,
                         double* Z, long ldz, long stride_z, int max_sweeps, int* sweeps, void* stream);
+
+/* All-gather of per-rank blocks through NVLink peer memory, for the PC-sharded device-resident sampler (the exchange
+ * step between predict and the replicated Woodbury kernel; SURVEY 8e "allgather of the results").  Every rank owns a
+ * buffer that is mapped into all peers (symmetric memory); peer_bufs is a DEVICE array of `world` base addresses of
+ * those buffers as seen from this rank.  post: the `count` doubles at `block` are stored into every peer's buffer at
+ * slot_offset (doubles), then the flag word (peer buffer + flag_offset doubles, 64-bit words, index = rank) is raised to
+ * epoch[0] + 1 with release semantics at system scope.  wait: one CTA spins on this rank's own flags (my_flags =
+ * own buffer + flag_offset) until every peer has reached epoch[0] + 1, then stores that epoch; a peer that does not
+ * arrive within ~2 s sets *error instead of hanging.  epoch, arrive (world ints, zero) and error are device words
+ * owned by the caller; no host value changes between steps, so the pair can be replayed inside a CUDA graph. */
+int sb200_peer_allgather_post(const double* block, long count, const unsigned long long* peer_bufs, long slot_offset,
+                              long flag_offset, int rank, int world, const unsigned long long* epoch, int* arrive,
+                              void* stream);
+int sb200_peer_allgather_wait(const unsigned long long* my_flags, int rank, int world, unsigned long long* epoch,
+                              int* error, void* stream);
 
 #ifdef __cplusplus
 }

@@ -82,7 +82,7 @@ ev.launch()
 torch.cuda.synchronize()
 got = torch.cat([ev.ll[:, None], ev.dll], 1).cpu().numpy()
 say(check='shard_state', loglik_max_abs_diff=float(np.max(np.abs(full - ll3))),
-    evaluator_max_rel=float(np.max(np.abs(got - full) / (np.abs(full) + 1e-300))), padded_components=int(ev.consts['phiT'].shape[0]))
+    evaluator_max_rel=float(np.max(np.abs(got - full) / (np.abs(full) + 1e-300))), padded_components=int(ev.world * ev.kmax), exchange='peer memory' if ev.peer else 'nccl')
 
 
 # 4. device-resident chain: sharded factors vs replicated factors, same seed
@@ -104,7 +104,10 @@ class prior:
 
 
 post = {}
-for name, fi, extra in (('replicated', f1, {}), ('sharded', dict(f1), {'shard_factors': True})):
+for name, fi, extra in (('replicated', f1, {}), ('sharded', dict(f1), {'shard_factors': True}),
+                        ('sharded_peer', dict(f1), {'shard_factors': True})):
+    # the sharded chain once with the NCCL all-gather and once with the exchange over NVLink peer memory (csrc/peer.cu)
+    os.environ['SB200_PEER_EXCHANGE'] = '1' if name == 'sharded_peer' else '0'
     cal = {'thetaprior': prior, 'yvar': yvar}
     np.random.seed(11)
     C.fit(cal, emu_of(fi), x, y, sampler='PTLMC_B200', numsamp=2000, numtemps=6, numchain=26, sampperchain=300, **extra)
@@ -114,6 +117,8 @@ dist.all_gather_object(same, post['sharded'][0].tobytes())
 say(check='device_chain', replicated_stats=post['replicated'][1], sharded_stats=post['sharded'][1],
     posterior_mean_replicated=post['replicated'][0].mean(0).tolist(), posterior_mean_sharded=post['sharded'][0].mean(0).tolist(),
     max_abs_diff_draws=float(np.max(np.abs(post['replicated'][0] - post['sharded'][0]))),
+    peer_exchange_stats=post['sharded_peer'][1],
+    max_abs_diff_draws_peer_exchange=float(np.max(np.abs(post['replicated'][0] - post['sharded_peer'][0]))),
     identical_on_all_ranks=bool(all(s == same[0] for s in same)))
 dist.barrier()
 dist.destroy_process_group()

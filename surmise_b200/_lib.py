@@ -45,8 +45,8 @@ SIGNATURES = {
     'sb200_gp_predict': (_i, [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _p, _i, _l,
                               _p, _p, _p, _p, _p, _z, _p]),
     'sb200_pc_backproject': (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-    'sb200_woodbury_loglik': (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _l, _p]),
-    'sb200_woodbury_trigger': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _i, _l, _p]),
+    'sb200_woodbury_loglik': (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _l, _p, _p]),
+    'sb200_woodbury_trigger': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _i, _l, _p, _p]),
     'sb200_ptlmc_step': (_i, [_i, _i, _i, _i, _i, _i, C.c_ulonglong, _d] + [_p] * 17 + [_p]),
     'sb200_host_tempexchange': (None, [_p, _p, _i, _p, _p, _i, _p]),
     'sb200_dgemm': (_i, [_i, _i, _i, _i, _i, _d, _p, _l, _l, _p, _l, _l, _d, _p, _l, _l, _i, _i, _i, _p]),
@@ -61,6 +61,8 @@ SIGNATURES = {
     'sb200_pca_col_stats': (_i, [_i, _i, _p, _l, _p, _p, _p, _p, _z, _p]),
     'sb200_pca_standardize': (_i, [_i, _i, _p, _l, _p, _p, _p, _l, _p, _p, _p]),
     'sb200_pca_sumsq': (_i, [_l, _p, _p, _p, _p]),
+    'sb200_peer_allgather_post': (_i, [_p, _l, _p, _l, _l, _i, _i, _p, _p, _p]),
+    'sb200_peer_allgather_wait': (_i, [_p, _i, _i, _p, _p, _p]),
     'sb200_syevj_max_p': (_i, []),
     'sb200_syevj_batched': (_i, [_i, _i, _p, _l, _l, _p, _l, _p, _l, _l, _i, _p, _p]),
 }

@@ -15,6 +15,8 @@ Requires an emulator fitted with method='PCGPwM_B200' (its device state is read 
 """
 import copy
 
+import os
+
 import numpy as np
 
 from ..emulationmethods import PCGPwM_B200 as _emu_method
@@ -213,12 +215,17 @@ class DeviceLogpost:
         self.fitinfo['_b200sampler'] = stats
 
 
+_PEER_READY = {'done': False}
+
+
 class _DeviceEvaluator:
     """ll (B), dll (B,d) of the proposals in `thetap` (B,d), rows masked by `valid` (int32) -- all device buffers of
     fixed address.  launch() enqueues predict + Woodbury on the current stream.  With factors sharded over ranks
     (PCGPwM_B200 fit option factors='owner') every rank evaluates the components whose factor it owns straight into
-    its block of one buffer, the blocks are all-gathered in place (NCCL), and the Woodbury kernel reads the gathered
-    blocks as they lie (segmented layout): one collective, no repacking."""
+    its block of one buffer, the blocks are exchanged -- through NVLink peer memory by this library's own kernels
+    (symmetric buffers, sb200_peer_allgather_post / _wait; csrc/peer.cu), or with an NCCL all-gather where symmetric
+    memory is not available (SB200_PEER_EXCHANGE=0 forces that) -- and the Woodbury kernel reads the gathered blocks as
+    they lie (segmented layout): no repacking."""
 
     def __init__(self, fitinfo, emu, x, y, B, d):
         ops = _ops()
@@ -236,7 +243,7 @@ class _DeviceEvaluator:
         sh = st.get('shard')
         if sh is None:
             K = st['pw'].shape[0]
-            self.consts, self.segments, self.comm = consts, None, None
+            self.consts, self.segments, self.comm, self.peer = consts, None, None, None
             self.pred = (torch.empty((B, K), **f64), torch.empty((B, K), **f64), torch.empty((B, K, d), **f64),
                          torch.empty((B, K, d), **f64))
             return
@@ -248,44 +255,116 @@ class _DeviceEvaluator:
         world, rank = sh['world'], sh['rank']
         kmax = max(max(sh['counts']), 1)
         chunk = B * kmax * (2 + 2 * d)
-        self.gathered = torch.zeros(world * chunk, **f64)
-        blocks = self.gathered.view(world, chunk)
-        blocks[:, B * kmax:2 * B * kmax] = 1.0                 # padded components: predvar 1, everything else 0
-        self.local = blocks[rank]
-
-        def views(block):
-            o = B * kmax
-            return (block[:o].view(B, kmax), block[o:2 * o].view(B, kmax), block[2 * o:2 * o + o * d].view(B, kmax, d),
-                    block[2 * o + o * d:].view(B, kmax, d))
-        self.pred_local, self.pred = views(self.local), views(blocks[0])
+        chunk += chunk & 1                                     # even: blocks stay 16-byte aligned
+        self.world, self.rank, self.chunk = world, rank, chunk
         self.kl, self.kmax = int(st['local']['pw'].shape[0]), kmax
         self.segments = (kmax, chunk)
-        # constants in gathered component order, zero rows / columns for the padded components
-        K, Kp = st['pw'].shape[0], world * kmax
-        pos = np.zeros(K, dtype=np.int64)                      # padded position of component j
+        self.peer = None
+        # Exchange of the blocks: NCCL all-gather by default.  The peer-memory exchange (csrc/peer.cu) is 2-3 % faster per
+        # step (4 x B200: 0.797 vs 0.817 ms) but torch's first symmetric-memory rendezvous costs ~1.5 s per process, more
+        # than a short chain gains: it is used when asked for (SB200_PEER_EXCHANGE=1) or once a process has paid that
+        # price already (a second calibration in the same process); SB200_PEER_EXCHANGE=0 never uses it.
+        mode = os.environ.get('SB200_PEER_EXCHANGE', 'auto')
+        if mode == '1' or (mode != '0' and _PEER_READY['done']):
+            try:
+                self._init_peer(torch, dev)
+                _PEER_READY['done'] = True
+            except Exception:
+                if mode == '1':
+                    raise
+                self.peer = None
+        if self.peer is None:
+            self.gathered = torch.zeros(world * chunk, **f64)
+            self._blocks = [self._init_blocks(self.gathered.view(world, chunk))]
+        # where every real component sits among the padded, rank-ordered slots: the Woodbury kernel visits only those, so
+        # its k x k work does not grow with the number of ranks (padding to world x kmax slots doubled it on 4 ranks)
+        K = st['pw'].shape[0]
+        pos = np.zeros(K, dtype=np.int32)
         offs = np.concatenate([[0], np.cumsum(sh['counts'])])
         order = np.argsort(sh['owner'], kind='stable')
         for r in range(world):
             for c, j in enumerate(order[offs[r]:offs[r + 1]]):
                 pos[j] = r * kmax + c
-        pos_t = torch.from_numpy(pos).to(dev)
-        phiT = torch.zeros((Kp, consts['phiT'].shape[1]), **f64)
-        phiT[pos_t] = consts['phiT']
-        G = torch.zeros((2, Kp, Kp), **f64)
-        G[:, pos_t[:, None], pos_t[None, :]] = consts['G']
-        self.consts = dict(consts, phiT=phiT, G=G)
+        self.seg_pos = torch.from_numpy(pos).to(dev)
+        self.consts = consts
+
+    def _views(self, block):
+        B, kmax, d = self.B, self.kmax, self.d
+        o = B * kmax
+        return (block[:o].view(B, kmax), block[o:2 * o].view(B, kmax), block[2 * o:2 * o + o * d].view(B, kmax, d),
+                block[2 * o + o * d:2 * o + 2 * o * d].view(B, kmax, d))
+
+    def _init_blocks(self, blocks):
+        """blocks: (world, chunk) view of one gathered buffer.  Padded components: predvar 1, everything else 0."""
+        o = self.B * self.kmax
+        blocks.zero_()
+        blocks[:, o:2 * o] = 1.0
+        return {'all': blocks, 'local': blocks[self.rank], 'pred_local': self._views(blocks[self.rank]),
+                'pred': self._views(blocks[0])}
+
+    def _init_peer(self, torch, dev):
+        """Blocks in symmetric memory (every rank's buffer mapped into every peer), exchanged by sb200_peer_allgather_*
+        over NVLink instead of an NCCL all-gather; two buffers, used by alternate steps (see csrc/peer.cu)."""
+        import torch.distributed._symmetric_memory as symm
+        from .._lib import lib
+        if not hasattr(lib, 'sb200_peer_allgather_post'):
+            raise RuntimeError('library without the peer exchange')
+        world, chunk = self.world, self.chunk
+        dist = self.comm.dist
+        total = 2 * world * chunk + world                       # [parity 0 | parity 1 | world flag words]
+        buf = symm.empty(total, dtype=torch.float64, device=dev)
+        group = dist.group.WORLD
+        try:
+            hdl = symm.rendezvous(buf, group)
+        except Exception:
+            hdl = symm.rendezvous(buf, group.group_name)
+        buf.zero_()
+        halves = [self._init_blocks(buf[p * world * chunk:(p + 1) * world * chunk].view(world, chunk)) for p in (0, 1)]
+        torch.cuda.synchronize()
+        dist.barrier()                                          # nobody posts into a buffer that is still being initialised
+        ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+        self._blocks = halves
+        self.peer = {'buf': buf, 'hdl': hdl, 'ptrs': ptrs, 'flag_off': 2 * world * chunk, 'par': 0,
+                     'epoch': torch.zeros(1, dtype=torch.int64, device=dev),
+                     'arrive': torch.zeros(world, dtype=torch.int32, device=dev),
+                     'error': torch.zeros(1, dtype=torch.int32, device=dev)}
+
+    def check(self):
+        """After the chain: raise if a peer's block did not arrive in time (the kernels never hang on it)."""
+        if self.segments is not None and self.peer is not None and int(self.peer['error'].item()) != 0:
+            raise RuntimeError('directbayeswoodbury_B200: a rank did not deliver its prediction block in time')
 
     def launch(self):
         ops = self.ops
         if self.segments is None:
             ops.gp_predict(self.st, self.thetap, True, out=self.pred, population=self.B)
-        else:
+            ops.woodbury_loglik(self.consts, *self.pred, out=(self.ll, self.dll, self.fired), row_valid=self.valid)
+            return
+        if self.peer is None:
+            blk = self._blocks[0]
             if self.kl:
-                ops.gp_predict(self.st['local'], self.thetap, True, out=self.pred_local, population=self.B,
+                ops.gp_predict(self.st['local'], self.thetap, True, out=blk['pred_local'], population=self.B,
                                out_ld=self.kmax)
-            self.comm.dist.all_gather_into_tensor(self.gathered, self.local)
-        ops.woodbury_loglik(self.consts, *self.pred, out=(self.ll, self.dll, self.fired), row_valid=self.valid,
-                            segments=self.segments)
+            self.comm.dist.all_gather_into_tensor(self.gathered, blk['local'])
+        else:
+            from .._lib import lib, check
+            pr = self.peer
+            par = pr['par']
+            pr['par'] ^= 1
+            blk = self._blocks[par]
+            if self.kl:
+                ops.gp_predict(self.st['local'], self.thetap, True, out=blk['pred_local'], population=self.B,
+                               out_ld=self.kmax)
+            stream = ops._stream(self.torch)
+            check(lib.sb200_peer_allgather_post(blk['local'].data_ptr(), self.chunk, pr['ptrs'].data_ptr(),
+                                                (par * self.world + self.rank) * self.chunk, pr['flag_off'], self.rank,
+                                                self.world, pr['epoch'].data_ptr(), pr['arrive'].data_ptr(), stream),
+                  'sb200_peer_allgather_post')
+            check(lib.sb200_peer_allgather_wait(pr['buf'].data_ptr() + 8 * pr['flag_off'], self.rank, self.world,
+                                                pr['epoch'].data_ptr(), pr['error'].data_ptr(), stream),
+                  'sb200_peer_allgather_wait')
+        ops.woodbury_loglik(self.consts, *blk['pred'], out=(self.ll, self.dll, self.fired), row_valid=self.valid,
+                            segments=self.segments, seg_pos=self.seg_pos)
 
 
 def loglik(fitinfo, emu, theta, y, x):

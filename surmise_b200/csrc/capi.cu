@@ -198,17 +198,17 @@ int sb200_woodbury_loglik(int B, int k, int m, int d, const double* predvecs, co
                           const double* predvecs_grad, const double* predvars_grad, const double* phiT,
                           const double* resid0, const double* extravar, const double* sinv, const double* G,
                           int want_grad, int variant, double* ll, double* dll, int* fired, const int* row_valid,
-                          int seg_k, long seg_stride, void* stream) {
+                          int seg_k, long seg_stride, const int* seg_pos, void* stream) {
     SB_CHECK_ARG(predvecs && predvars && phiT && resid0 && extravar && sinv && G && ll && fired,
                  "woodbury_loglik: NULL pointer");
     return woodbury_loglik(B, k, m, d, predvecs, predvars, predvecs_grad, predvars_grad, phiT, resid0, extravar, sinv,
-                           G, want_grad, variant, ll, dll, fired, row_valid, seg_k, seg_stride, ST(stream));
+                           G, want_grad, variant, ll, dll, fired, row_valid, seg_k, seg_stride, seg_pos, ST(stream));
 }
 
 int sb200_woodbury_trigger(int B, int k, int m, const double* predvars, const double* phiT, const double* extravar,
-                           int* fired, const int* row_valid, int seg_k, long seg_stride, void* stream) {
+                           int* fired, const int* row_valid, int seg_k, long seg_stride, const int* seg_pos, void* stream) {
     SB_CHECK_ARG(predvars && phiT && extravar && fired, "woodbury_trigger: NULL pointer");
-    return woodbury_trigger(B, k, m, predvars, phiT, extravar, fired, row_valid, seg_k, seg_stride, ST(stream));
+    return woodbury_trigger(B, k, m, predvars, phiT, extravar, fired, row_valid, seg_k, seg_stride, seg_pos, ST(stream));
 }
 
 int sb200_ptlmc_step(int B, int d, int numtemps, int tune, int nsave, int mode, unsigned long long seed, double taracc,
@@ -294,6 +294,19 @@ int sb200_syevj_batched(int batch, int p, const double* H, long ldh, long stride
                         double* Z, long ldz, long stride_z, int max_sweeps, int* sweeps, void* stream) {
     SB_CHECK_ARG(H && W && Z, "syevj: NULL pointer");
     return syevj_batched(batch, p, H, ldh, stride_h, W, stride_w, Z, ldz, stride_z, max_sweeps, sweeps, ST(stream));
+}
+
+int sb200_peer_allgather_post(const double* block, long count, const unsigned long long* peer_bufs, long slot_offset,
+                              long flag_offset, int rank, int world, const unsigned long long* epoch, int* arrive,
+                              void* stream) {
+    SB_CHECK_ARG(block && peer_bufs && epoch && arrive, "peer_allgather_post: NULL pointer");
+    return peer_allgather_post(block, count, peer_bufs, slot_offset, flag_offset, rank, world, epoch, arrive, ST(stream));
+}
+
+int sb200_peer_allgather_wait(const unsigned long long* my_flags, int rank, int world, unsigned long long* epoch, int* error,
+                              void* stream) {
+    SB_CHECK_ARG(my_flags && epoch && error, "peer_allgather_wait: NULL pointer");
+    return peer_allgather_wait(my_flags, rank, world, epoch, error, ST(stream));
 }
 
 }  // extern "C"

@@ -48,9 +48,9 @@ constexpr int WOODBURY_MAXK = 112;
 int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const double* predvars, const double* dpv,
                     const double* dpvar, const double* phiT, const double* resid0, const double* extravar,
                     const double* sinv, const double* G, int want_grad, int variant, double* ll, double* dll,
-                    int* fired, const int* row_valid, int segk, long segstride, cudaStream_t stream);
+                    int* fired, const int* row_valid, int segk, long segstride, const int* seg_pos, cudaStream_t stream);
 int woodbury_trigger(int B, int K, int m, const double* predvars, const double* phiT, const double* extravar,
-                     int* fired, const int* row_valid, int segk, long segstride, cudaStream_t stream);
+                     int* fired, const int* row_valid, int segk, long segstride, const int* seg_pos, cudaStream_t stream);
 
 
 // sampler.cu: one step of the device-resident PT-LMC sampler (surmise utilitiesmethods/PTLMC.py:203-273)
@@ -58,5 +58,11 @@ int ptlmc_step(int B, int d, int numtemps, int tune, int nsave, int mode, unsign
                double* thetac, double* fval, double* dfval, double* thetap, double* z, double* adjrho, const double* ll,
                const double* dll, const double* temps, const double* lo, const double* hi, const double* hc,
                const double* cov0, double* scal, long long* kstep, double* save, int* row_valid, cudaStream_t stream);
+
+// peer.cu: all-gather of per-rank blocks through NVLink peer memory (symmetric buffers), see the file header
+int peer_allgather_post(const double* block, long count, const unsigned long long* peer_bufs, long slot_off, long flag_off,
+                        int rank, int world, const unsigned long long* epoch, int* arrive, cudaStream_t stream);
+int peer_allgather_wait(const unsigned long long* my_flags, int rank, int world, unsigned long long* epoch, int* error,
+                        cudaStream_t stream);
 
 }  // namespace sb

@@ -21,6 +21,9 @@ constexpr int WT = 128;
 __device__ __forceinline__ long seg_at(int b, int a, int segk, long segstride) {
     return (long)(a / segk) * segstride + (long)b * segk + (a % segk);
 }
+// With a position table (seg_pos[a] = where component a sits among the padded, rank-ordered components) the padded
+// slots are never visited: the k x k work stays that of the real components, however many ranks share them.
+__device__ __forceinline__ int seg_idx(const int* __restrict__ seg_pos, int a) { return seg_pos ? seg_pos[a] : a; }
 
 // Entry i of the d-vector of component a of proposal b in a segmented (B, K, d) table: the segment offset counts
 // doubles (it is the same block stride as for the scalar tables), only the position inside a block scales with d.
@@ -32,12 +35,12 @@ __global__ void __launch_bounds__(WT) woodbury_trigger_kernel(int B, int K, int 
                                                               const double* __restrict__ phiT,
                                                               const double* __restrict__ extravar,
                                                               const int* __restrict__ row_valid, int segk,
-                                                              long segstride, int* fired) {
+                                                              long segstride, const int* __restrict__ seg_pos, int* fired) {
     const int b = blockIdx.x;
     if (row_valid && !row_valid[b]) return;          // rows the caller will discard (prior = -inf) take no part in the test
     extern __shared__ double sh[];
     double* v = sh;
-    for (int a = threadIdx.x; a < K; a += WT) v[a] = predvars[seg_at(b, a, segk, segstride)];
+    for (int a = threadIdx.x; a < K; a += WT) v[a] = predvars[seg_at(b, seg_idx(seg_pos, a), segk, segstride)];
     __syncthreads();
     bool hit = false;
     for (int x = threadIdx.x; x < m; x += WT) {
@@ -62,7 +65,8 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
                                                              const double* __restrict__ sinvb,
                                                              const double* __restrict__ Gb, int* fired,
                                                              int forced_variant, int want_grad, int segk, long segstride,
-                                                             double* __restrict__ ll, double* __restrict__ dll) {
+                                                             const int* __restrict__ seg_pos, double* __restrict__ ll,
+                                                             double* __restrict__ dll) {
     extern __shared__ double sh[];
     double* Lm = sh;                    // K*K : A, then L, then Ainv
     double* Xm = Lm + K * K;            // K*K : L^-1
@@ -82,8 +86,8 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
     const double* G = Gb + (long)variant * K * K;
 
     for (int a = tid; a < K; a += WT) {
-        D[a] = sqrt(predvars[seg_at(b, a, segk, segstride)]);
-        pvv[a] = predvecs[seg_at(b, a, segk, segstride)];
+        D[a] = sqrt(predvars[seg_at(b, seg_idx(seg_pos, a), segk, segstride)]);
+        pvv[a] = predvecs[seg_at(b, seg_idx(seg_pos, a), segk, segstride)];
     }
     __syncthreads();
     double t1 = 0.0;
@@ -170,10 +174,10 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
     for (int i = 0; i < d; i++) {
         double val = 0.0;
         for (int a = tid; a < K; a += WT) {
-            double dpa = dpv[seg_at_d(b, a, i, d, segk, segstride)];
-            double dD = 0.5 * dpvar[seg_at_d(b, a, i, d, segk, segstride)] / D[a];
+            double dpa = dpv[seg_at_d(b, seg_idx(seg_pos, a), i, d, segk, segstride)];
+            double dD = 0.5 * dpvar[seg_at_d(b, seg_idx(seg_pos, a), i, d, segk, segstride)] / D[a];
             double gd = 0.0;
-            for (int c = 0; c < K; c++) gd += G[a * K + c] * dpv[seg_at_d(b, c, i, d, segk, segstride)];
+            for (int c = 0; c < K; c++) gd += G[a * K + c] * dpv[seg_at_d(b, seg_idx(seg_pos, c), i, d, segk, segstride)];
             double dJ2 = -D[a] * gd + dD * q[a];
             // -1/2 dterm3 - 1/2 (dterm1 - dterm2), term by term (dbw.py:344-381 in k-space)
             val += -dD * Nv[a] + q[a] * dpa + dJ2 * J3[a] - dD * J3[a] * MJ3[a];
@@ -188,13 +192,14 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
 int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const double* predvars, const double* dpv,
                     const double* dpvar, const double* phiT, const double* resid0, const double* extravar,
                     const double* sinv, const double* G, int want_grad, int variant, double* ll, double* dll,
-                    int* fired, const int* row_valid, int segk, long segstride, cudaStream_t stream) {
+                    int* fired, const int* row_valid, int segk, long segstride, const int* seg_pos, cudaStream_t stream) {
     SB_CHECK_ARG(B > 0 && m > 0, "woodbury: empty batch");
-    if (segk <= 0 || segk >= K) {
+    if (segk <= 0 || (segk >= K && !seg_pos)) {
         segk = K;
         segstride = 0;
+        seg_pos = nullptr;
     }
-    SB_CHECK_ARG(K % segk == 0, "woodbury: k=%d is not a multiple of the segment width %d", K, segk);
+    SB_CHECK_ARG(seg_pos || K % segk == 0, "woodbury: k=%d is not a multiple of the segment width %d", K, segk);
     SB_CHECK_ARG(K >= 1 && K <= WOODBURY_MAXK, "woodbury: k=%d outside [1,%d]", K, WOODBURY_MAXK);
     SB_CHECK_ARG(!want_grad || (dpv && dpvar && dll), "woodbury: gradient buffers are NULL");
     size_t smem = (size_t)(2 * K * K + m + 7 * K + 32) * sizeof(double);
@@ -207,27 +212,28 @@ int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const do
     if (variant < 0) {
         SB_CUDA(cudaMemsetAsync(fired, 0, sizeof(int), stream));
         woodbury_trigger_kernel<<<B, WT, K * sizeof(double), stream>>>(B, K, m, predvars, phiT, extravar, row_valid, segk,
-                                                                       segstride, fired);
+                                                                       segstride, seg_pos, fired);
         SB_LAUNCH_CHECK();
     }
     woodbury_loglik_kernel<<<B, WT, smem, stream>>>(B, K, m, d, predvecs, predvars, dpv, dpvar, phiT, resid0, sinv, G,
-                                                    fired, variant > 0 ? 1 : variant, want_grad, segk, segstride, ll,
-                                                    dll);
+                                                    fired, variant > 0 ? 1 : variant, want_grad, segk, segstride, seg_pos,
+                                                    ll, dll);
     SB_LAUNCH_CHECK();
     return 0;
 }
 
 int woodbury_trigger(int B, int K, int m, const double* predvars, const double* phiT, const double* extravar,
-                     int* fired, const int* row_valid, int segk, long segstride, cudaStream_t stream) {
+                     int* fired, const int* row_valid, int segk, long segstride, const int* seg_pos, cudaStream_t stream) {
     SB_CHECK_ARG(B > 0 && m > 0 && K >= 1, "woodbury_trigger: empty batch");
-    if (segk <= 0 || segk >= K) {
+    if (segk <= 0 || (segk >= K && !seg_pos)) {
         segk = K;
         segstride = 0;
+        seg_pos = nullptr;
     }
-    SB_CHECK_ARG(K % segk == 0, "woodbury_trigger: k=%d is not a multiple of the segment width %d", K, segk);
+    SB_CHECK_ARG(seg_pos || K % segk == 0, "woodbury_trigger: k=%d is not a multiple of the segment width %d", K, segk);
     SB_CUDA(cudaMemsetAsync(fired, 0, sizeof(int), stream));
     woodbury_trigger_kernel<<<B, WT, K * sizeof(double), stream>>>(B, K, m, predvars, phiT, extravar, row_valid, segk,
-                                                                   segstride, fired);
+                                                                   segstride, seg_pos, fired);
     SB_LAUNCH_CHECK();
     return 0;
 }

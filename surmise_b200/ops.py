@@ -342,19 +342,21 @@ def woodbury_trigger(consts, pvar, row_valid=None):
     B, K = pvar.shape
     fired = torch.empty(1, dtype=torch.int32, device=pvar.device)
     check(lib.sb200_woodbury_trigger(B, K, consts['phiT'].shape[1], _ptr(pvar), _ptr(consts['phiT']),
-                                     _ptr(consts['extravar']), _ptr(fired), _ptr(row_valid), 0, 0, _stream(torch)),
+                                     _ptr(consts['extravar']), _ptr(fired), _ptr(row_valid), 0, 0, 0, _stream(torch)),
           'sb200_woodbury_trigger')
     return fired
 
 
-def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1, out=None, row_valid=None, segments=None):
+def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1, out=None, row_valid=None, segments=None,
+                    seg_pos=None):
     """Batched directbayeswoodbury log-likelihood (+ gradient) (dbw.py:261-383).
 
     consts: dict of device tensors phiT (k,m), resid0 (m), extravar (m), sinv (2,m), G (2,k,k).
     row_valid: optional int32 (B,) mask of the rows that take part in the batch-wide variance test.
     segments: None for dense (B,k) inputs, or (seg_k, seg_stride) when pv / pvar / dpv / dpvar are the FIRST blocks
     (B, seg_k[, d]) of an all-gathered PC-sharded prediction whose blocks lie seg_stride doubles apart; k is then
-    consts['phiT'].shape[0] (see include/surmise_b200.h).
+    consts['phiT'].shape[0] (see include/surmise_b200.h).  seg_pos: optional int32 device tensor (k,) with the padded slot
+    of every real component; consts are then the ordinary unpadded arrays.
     Returns device tensors ll (B,), dll (B,d) or None, fired (int32 scalar tensor).
     """
     torch = _torch()
@@ -376,7 +378,8 @@ def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1, out=None
     check(lib.sb200_woodbury_loglik(B, K, m, d, _ptr(pv), _ptr(pvar), _ptr(dpv), _ptr(dpvar), _ptr(consts['phiT']),
                                     _ptr(consts['resid0']), _ptr(consts['extravar']), _ptr(consts['sinv']),
                                     _ptr(consts['G']), int(want_grad), int(variant), _ptr(ll), _ptr(dll), _ptr(fired),
-                                    _ptr(row_valid), int(seg_k), int(seg_stride), _stream(torch)), 'sb200_woodbury_loglik')
+                                    _ptr(row_valid), int(seg_k), int(seg_stride), _ptr(seg_pos), _stream(torch)),
+          'sb200_woodbury_loglik')
     return ll, dll, fired
 
 

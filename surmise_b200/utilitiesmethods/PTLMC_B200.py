@@ -206,6 +206,8 @@ def _device_chain(dl, thetac, fval, dfval, temps, cov0, hc, numtemps, numchain, 
     lo, hi = dl.box
     ev = dl.evaluator(B, d)
     dev = ev.thetap.device
+    if getattr(ev, 'peer', None) is not None:
+        steps_per_graph -= steps_per_graph % 2                # the peer exchange alternates two buffers: whole pairs per replay
     t64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
     seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2 ** 31 + int(np.random.randint(0, 2 ** 31 - 1))
     tau0 = -1.0
@@ -256,7 +258,11 @@ def _device_chain(dl, thetac, fval, dfval, temps, cov0, hc, numtemps, numchain, 
     ops.ptlmc_step(st, 1, ev.ll, ev.dll)
     save, scal = ops.to_host([st['save'], st['scal']])
     t_end = time.perf_counter()
+    if hasattr(ev, 'check'):
+        ev.check()
     stats = {'theta_evaluated_on_device': total * B, 'mcmc_steps': total, 'cuda_graph': used_graph,
+             'exchange': ('none' if getattr(ev, 'segments', None) is None else
+                          ('peer memory' if getattr(ev, 'peer', None) is not None else 'nccl all_gather')),
              'setup_and_capture_s': t_loop - t_begin, 'loop_s': t_end - t_loop,
              'ms_per_step_in_loop': 1e3 * (t_end - t_loop) / max(total - 1 - done_before, 1),
              'steps_per_graph': steps_per_graph if used_graph else 0, 'accept_rate': float(scal[2] / (total * B)),

@@ -346,6 +346,12 @@ def test_woodbury_segmented_layout_equals_dense(ops, golden, world):
     e_d = rel(dll1.cpu().numpy(), dll0.cpu().numpy())
     report('woodbury_segmented_w%d' % world, ll=e_l, dll=e_d)
     assert e_l < 1e-12 and e_d < 1e-10
+    # the same layout read through a position table: only the real components are visited, the constants stay unpadded
+    ll2, dll2, _ = ops.woodbury_loglik(consts, *views, variant=0, segments=(kmax, chunk),
+                                       seg_pos=dev(np.array(pos, dtype=np.int32)))
+    torch.cuda.synchronize()
+    assert float(np.max(np.abs((ll2 - ll0).cpu().numpy()) / np.abs(ll0.cpu().numpy()))) < 1e-13
+    assert rel(dll2.cpu().numpy(), dll0.cpu().numpy()) < 1e-12
 
 
 def test_logpost_closure_contract(ops, golden):
