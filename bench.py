@@ -610,11 +610,11 @@ def single_gpu_same_work(w, theta_d, mean_d, std_d, dev, torch, ops, chunk=32):
 
 
 def _fit_twice(M, torch, x, theta, f, barrier=None, **kw):
-    """(first-call seconds, warm seconds, fitinfo of the warm call).  Both calls fit the SAME seeded problem: with
-    different seeds the number of distinct factors (and so the size of the factor buffer) differs between the calls, and
-    the warm call then pays a cudaMalloc of a few hundred MB (0.1 s at C2) or not, at random."""
-    walls, fi = [], None
-    for rep in range(2):
+    """(first-call seconds, warm seconds = the better of two further calls, fitinfo of the last call).  All calls fit the
+    SAME seeded problem; a warm call can still pay a cudaMalloc of a few hundred MB for the factor buffer (0.1 s at C2)
+    when torch's caching allocator has split the block the previous call returned -- hence the better of two."""
+    first, best, best_fi = None, None, None
+    for rep in range(3):                              # first call, then the better of two warm calls
         np.random.seed(1)
         fi = {'method': 'PCGPwM_B200'}
         if barrier is not None:
@@ -625,8 +625,13 @@ def _fit_twice(M, torch, x, theta, f, barrier=None, **kw):
         torch.cuda.synchronize()
         if barrier is not None:
             barrier()
-        walls.append(time.perf_counter() - t0)
-    return walls[0], walls[1], fi
+        wall = time.perf_counter() - t0
+        if rep == 0:
+            first = wall
+        elif best is None or wall < best:
+            best, best_fi = wall, fi
+        del fi
+    return first, best, best_fi
 
 
 def _holdout(M, fi, x, truth, d, B=128):
