@@ -11,14 +11,14 @@
  *     own: what exists process-wide is (a) a thread-local last-error string, (b) the one-time per-device kernel
  *     attribute set-up (mutex-guarded, safe for concurrent first calls from several host threads), and (c) the
  *     instrumentation / testing switches declared below -- an atomic launch counter, the optional GEMM timing record
- *     (mutex-guarded), sb200_gp_force_blocked_path and sb200_debug_panel_stamps (atomics; set them only while no
+ *     (mutex-guarded), sb200_gp_force_blocked_path, sb200_woodbury_force_global and sb200_debug_panel_stamps (atomics; set them only while no
  *     call is in flight).  None of (c) changes a numerical result;
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); outputs are valid
  *     after the stream is synchronised;
  *   - return value: 0 success, < 0 invalid argument, > 0 a cudaError_t; sb200_last_error() explains;
  *   - numerical breakdown (a non-positive pivot) is reported per problem in `info` (LAPACK
  *     convention: j > 0 = leading minor j not positive definite), never by aborting;
- *   - parameter dimension d <= 16, principal components k <= 112 for the Woodbury kernel.
+ *   - parameter dimension d <= 16 (the per-dimension loops live in registers).
  */
 #ifndef SURMISE_B200_H
 #define SURMISE_B200_H
@@ -144,6 +144,20 @@ int sb200_woodbury_loglik(int B, int k, int m, int d, const double* predvecs, co
 int sb200_woodbury_trigger(int B, int k, int m, const double* predvars, const double* phiT, const double* extravar,
                            int* fired, const int* row_valid, int seg_k, long seg_stride, const int* seg_pos,
                            void* stream);
+/* The kernel keeps the two k x k matrices of a proposal (I + D G D, its factor and inverse) in shared memory while
+ * (2 k^2 + m + 7 k + 32) doubles fit 227 KB -- k <= 112 at m <= 3000; sb200_woodbury_workspace then returns 0 and
+ * sb200_woodbury_loglik needs no scratch.  Beyond that each CTA works on a slice of a caller-provided global buffer
+ * (same code, L2-resident): size it with sb200_woodbury_workspace(B, k, m) (at most 1 GiB; the proposals are then taken
+ * in chunks) and call sb200_woodbury_loglik_ws; sb200_woodbury_loglik itself reports such a shape as an argument
+ * error.  sb200_woodbury_force_global(1) sends every shape through the scratch path (testing switch, as (c) above). */
+size_t sb200_woodbury_workspace(int B, int k, int m);
+int sb200_woodbury_loglik_ws(int B, int k, int m, int d, const double* predvecs, const double* predvars,
+                             const double* predvecs_grad, const double* predvars_grad, const double* phiT,
+                             const double* resid0, const double* extravar, const double* sinv, const double* G,
+                             int want_grad, int variant, double* ll, double* dll, int* fired, const int* row_valid,
+                             int seg_k, long seg_stride, const int* seg_pos, void* workspace, size_t workspace_bytes,
+                             void* stream);
+void sb200_woodbury_force_global(int on);
 
 /* One step of the device-resident PT-LMC sampler: what surmise's PTLMC (utilitiesmethods/PTLMC.py:203-273) does between
  * two evaluations of the log-posterior, for a population of B = numtemps + numchain chains kept on the device.

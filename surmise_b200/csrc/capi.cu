@@ -202,8 +202,26 @@ int sb200_woodbury_loglik(int B, int k, int m, int d, const double* predvecs, co
     SB_CHECK_ARG(predvecs && predvars && phiT && resid0 && extravar && sinv && G && ll && fired,
                  "woodbury_loglik: NULL pointer");
     return woodbury_loglik(B, k, m, d, predvecs, predvars, predvecs_grad, predvars_grad, phiT, resid0, extravar, sinv,
-                           G, want_grad, variant, ll, dll, fired, row_valid, seg_k, seg_stride, seg_pos, ST(stream));
+                           G, want_grad, variant, ll, dll, fired, row_valid, seg_k, seg_stride, seg_pos, nullptr, 0,
+                           ST(stream));
 }
+
+size_t sb200_woodbury_workspace(int B, int k, int m) { return woodbury_workspace(B, k, m); }
+
+int sb200_woodbury_loglik_ws(int B, int k, int m, int d, const double* predvecs, const double* predvars,
+                             const double* predvecs_grad, const double* predvars_grad, const double* phiT,
+                             const double* resid0, const double* extravar, const double* sinv, const double* G,
+                             int want_grad, int variant, double* ll, double* dll, int* fired, const int* row_valid,
+                             int seg_k, long seg_stride, const int* seg_pos, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+    SB_CHECK_ARG(predvecs && predvars && phiT && resid0 && extravar && sinv && G && ll && fired,
+                 "woodbury_loglik: NULL pointer");
+    return woodbury_loglik(B, k, m, d, predvecs, predvars, predvecs_grad, predvars_grad, phiT, resid0, extravar, sinv,
+                           G, want_grad, variant, ll, dll, fired, row_valid, seg_k, seg_stride, seg_pos, workspace,
+                           workspace_bytes, ST(stream));
+}
+
+void sb200_woodbury_force_global(int on) { woodbury_force_global(on); }
 
 int sb200_woodbury_trigger(int B, int k, int m, const double* predvars, const double* phiT, const double* extravar,
                            int* fired, const int* row_valid, int seg_k, long seg_stride, const int* seg_pos, void* stream) {

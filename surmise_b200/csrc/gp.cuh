@@ -43,14 +43,16 @@ int pc_backproject(int m, int K, int B, int d, const double* phi, const double* 
                    double* mean, double* var, double* covxhalf, double* mean_grad, double* covxhalf_grad,
                    cudaStream_t stream);
 
-constexpr int WOODBURY_MAXK = 112;
 // sinv: (2, m) = 1/yvar and 1/(yvar+|extravar|);  G: (2, K, K) = Phi' diag(sinv_v) Phi;  fired: device int
 int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const double* predvars, const double* dpv,
                     const double* dpvar, const double* phiT, const double* resid0, const double* extravar,
                     const double* sinv, const double* G, int want_grad, int variant, double* ll, double* dll,
-                    int* fired, const int* row_valid, int segk, long segstride, const int* seg_pos, cudaStream_t stream);
+                    int* fired, const int* row_valid, int segk, long segstride, const int* seg_pos, void* ws,
+                    size_t ws_bytes, cudaStream_t stream);
+size_t woodbury_workspace(int B, int K, int m);      // 0 while the k x k systems fit shared memory (k <= 112 at m <= 3000)
 int woodbury_trigger(int B, int K, int m, const double* predvars, const double* phiT, const double* extravar,
                      int* fired, const int* row_valid, int segk, long segstride, const int* seg_pos, cudaStream_t stream);
+void woodbury_force_global(int on);      // tests: k x k matrices in global scratch at any k (the k > 112 path)
 
 
 // sampler.cu: one step of the device-resident PT-LMC sampler (surmise utilitiesmethods/PTLMC.py:203-273)

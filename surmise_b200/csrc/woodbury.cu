@@ -9,11 +9,15 @@
 // The batch-wide "extravar" trigger (dbw.py:277-284) is a pre-pass that ORs a device flag; the
 // main kernel then selects Sigma = yvar or yvar + |extravar| (both Gram matrices are precomputed).
 #include "gp.cuh"
+#include <algorithm>
+#include <atomic>
 
 namespace sb {
 namespace {
 
 constexpr int WT = 128;
+constexpr size_t WOODBURY_SCRATCH_BYTES = (size_t)1 << 30;      // cap of the global-scratch path's workspace
+std::atomic<bool> g_woodbury_force_global{false};      // testing switch: the global-scratch path at any k
 
 // Component a of proposal b in a (possibly) segmented (B, K) table: components arrive in groups of `segk` (one group
 // per rank of a PC-sharded prediction, each a dense (B, segk) block, `segstride` doubles apart -- the layout an
@@ -66,11 +70,13 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
                                                              const double* __restrict__ Gb, int* fired,
                                                              int forced_variant, int want_grad, int segk, long segstride,
                                                              const int* __restrict__ seg_pos, double* __restrict__ ll,
-                                                             double* __restrict__ dll) {
+                                                             double* __restrict__ dll, double* gws, int b0) {
     extern __shared__ double sh[];
-    double* Lm = sh;                    // K*K : A, then L, then Ainv
-    double* Xm = Lm + K * K;            // K*K : L^-1
-    double* w = Xm + K * K;             // m   : Sigma^-1 r
+    // The two k x k matrices live in shared memory when they fit (k <= WOODBURY_SMEM_K); beyond that each CTA works on
+    // its own slice of a global scratch buffer (L2 resident), with the same code -- block-level barriers order both.
+    double* Lm = gws ? gws + (size_t)blockIdx.x * 2 * K * K : sh;      // K*K : A, then L, then Ainv
+    double* Xm = Lm + K * K;                                           // K*K : L^-1
+    double* w = gws ? sh : Xm + K * K;                                 // m   : Sigma^-1 r
     double* D = w + m;                  // K each below
     double* pvv = D + K;
     double* q = pvv + K;
@@ -79,9 +85,9 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
     double* Nv = J3 + K;
     double* MJ3 = Nv + K;
     double* red = MJ3 + K;              // 32
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x + b0, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int variant = forced_variant >= 0 ? forced_variant : ((*fired) ? 1 : 0);
-    if (forced_variant >= 0 && blockIdx.x == 0 && threadIdx.x == 0) *fired = forced_variant;
+    if (forced_variant >= 0 && b == 0 && threadIdx.x == 0) *fired = forced_variant;
     const double* sinv = sinvb + (long)variant * m;
     const double* G = Gb + (long)variant * K * K;
 
@@ -189,10 +195,22 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
 
 }  // namespace
 
+// k x k matrices in shared memory?  (m-vector + 7 k-vectors + the two matrices within 227 KB: k <= 112 at m <= 3000)
+static bool woodbury_fits_smem(int K, int m) {
+    return (size_t)(2 * (size_t)K * K + m + 7 * K + 32) * sizeof(double) <= 227 * 1024 && !g_woodbury_force_global;
+}
+
+size_t woodbury_workspace(int B, int K, int m) {
+    if (B <= 0 || K <= 0 || woodbury_fits_smem(K, m)) return 0;
+    const size_t kk = (size_t)2 * K * K * sizeof(double);
+    return kk * std::min<size_t>((size_t)B, std::max<size_t>(1, WOODBURY_SCRATCH_BYTES / kk));
+}
+
 int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const double* predvars, const double* dpv,
                     const double* dpvar, const double* phiT, const double* resid0, const double* extravar,
                     const double* sinv, const double* G, int want_grad, int variant, double* ll, double* dll,
-                    int* fired, const int* row_valid, int segk, long segstride, const int* seg_pos, cudaStream_t stream) {
+                    int* fired, const int* row_valid, int segk, long segstride, const int* seg_pos, void* ws,
+                    size_t ws_bytes, cudaStream_t stream) {
     SB_CHECK_ARG(B > 0 && m > 0, "woodbury: empty batch");
     if (segk <= 0 || (segk >= K && !seg_pos)) {
         segk = K;
@@ -200,10 +218,15 @@ int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const do
         seg_pos = nullptr;
     }
     SB_CHECK_ARG(seg_pos || K % segk == 0, "woodbury: k=%d is not a multiple of the segment width %d", K, segk);
-    SB_CHECK_ARG(K >= 1 && K <= WOODBURY_MAXK, "woodbury: k=%d outside [1,%d]", K, WOODBURY_MAXK);
+    SB_CHECK_ARG(K >= 1, "woodbury: k=%d", K);
     SB_CHECK_ARG(!want_grad || (dpv && dpvar && dll), "woodbury: gradient buffers are NULL");
-    size_t smem = (size_t)(2 * K * K + m + 7 * K + 32) * sizeof(double);
-    SB_CHECK_ARG(smem <= 227 * 1024, "woodbury: k=%d, m=%d need %zu B of shared memory", K, m, smem);
+    const size_t smem_vec = (size_t)(m + 7 * K + 32) * sizeof(double), kk = (size_t)2 * K * K * sizeof(double);
+    const bool in_smem = woodbury_fits_smem(K, m);
+    const size_t smem = in_smem ? smem_vec + kk : smem_vec;
+    SB_CHECK_ARG(smem <= 227 * 1024, "woodbury: k=%d, m=%d need %zu B of shared memory for the m- and k-vectors", K, m, smem);
+    SB_CHECK_ARG(in_smem || (ws && ws_bytes >= kk),
+                 "woodbury: k=%d, m=%d keep their k x k systems in global scratch: pass a workspace of "
+                 "sb200_woodbury_workspace(B, k, m) bytes (sb200_woodbury_loglik_ws)", K, m);
     static DeviceOnce once;
     SB_TRY(once.run([&]() -> int {
         SB_CUDA(cudaFuncSetAttribute(woodbury_loglik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -215,12 +238,18 @@ int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const do
                                                                        segstride, seg_pos, fired);
         SB_LAUNCH_CHECK();
     }
-    woodbury_loglik_kernel<<<B, WT, smem, stream>>>(B, K, m, d, predvecs, predvars, dpv, dpvar, phiT, resid0, sinv, G,
-                                                    fired, variant > 0 ? 1 : variant, want_grad, segk, segstride, seg_pos,
-                                                    ll, dll);
-    SB_LAUNCH_CHECK();
+    // in shared memory: one launch; in global scratch: the proposals in chunks that fit the caller's workspace
+    const int chunk = in_smem ? B : (int)std::min<size_t>((size_t)B, ws_bytes / kk);
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        woodbury_loglik_kernel<<<std::min(chunk, B - b0), WT, smem, stream>>>(
+            B, K, m, d, predvecs, predvars, dpv, dpvar, phiT, resid0, sinv, G, fired, variant > 0 ? 1 : variant, want_grad,
+            segk, segstride, seg_pos, ll, dll, in_smem ? nullptr : static_cast<double*>(ws), b0);
+        SB_LAUNCH_CHECK();
+    }
     return 0;
 }
+
+void woodbury_force_global(int on) { g_woodbury_force_global.store(on != 0); }
 
 int woodbury_trigger(int B, int K, int m, const double* predvars, const double* phiT, const double* extravar,
                      int* fired, const int* row_valid, int segk, long segstride, const int* seg_pos, cudaStream_t stream) {

@@ -83,6 +83,7 @@ def workspace(nbytes):
 
 def release_workspaces():
     _workspaces.clear()
+    _wb_scratch.clear()
 
 
 # ----------------------------------------------------------------------------------------------
@@ -375,12 +376,36 @@ def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1, out=None
         ll = torch.empty(B, dtype=torch.float64, device=dev)
         dll = torch.empty((B, d), dtype=torch.float64, device=dev) if want_grad else None
         fired = torch.empty(1, dtype=torch.int32, device=dev)
-    check(lib.sb200_woodbury_loglik(B, K, m, d, _ptr(pv), _ptr(pvar), _ptr(dpv), _ptr(dpvar), _ptr(consts['phiT']),
-                                    _ptr(consts['resid0']), _ptr(consts['extravar']), _ptr(consts['sinv']),
-                                    _ptr(consts['G']), int(want_grad), int(variant), _ptr(ll), _ptr(dll), _ptr(fired),
-                                    _ptr(row_valid), int(seg_k), int(seg_stride), _ptr(seg_pos), _stream(torch)),
-          'sb200_woodbury_loglik')
+    # k x k systems beyond shared memory (k > 112 at m <= 3000) work in a global scratch buffer of their own
+    nbytes = lib.sb200_woodbury_workspace(B, K, m)
+    ws = _woodbury_scratch(torch, dev, nbytes) if nbytes else None
+    check(lib.sb200_woodbury_loglik_ws(B, K, m, d, _ptr(pv), _ptr(pvar), _ptr(dpv), _ptr(dpvar), _ptr(consts['phiT']),
+                                       _ptr(consts['resid0']), _ptr(consts['extravar']), _ptr(consts['sinv']),
+                                       _ptr(consts['G']), int(want_grad), int(variant), _ptr(ll), _ptr(dll), _ptr(fired),
+                                       _ptr(row_valid), int(seg_k), int(seg_stride), _ptr(seg_pos), _ptr(ws),
+                                       ws.numel() if ws is not None else 0, _stream(torch)),
+          'sb200_woodbury_loglik_ws')
     return ll, dll, fired
+
+
+_wb_scratch = {}
+
+
+def _woodbury_scratch(torch, dev, nbytes):
+    """Grow-only per-device buffer for the Woodbury kernel's global-scratch path (separate from `workspace`, whose
+    contents a prediction running ahead on the same stream may still be using)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    ws = _wb_scratch.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _wb_scratch.pop(key, None)
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        _wb_scratch[key] = ws
+    return ws
+
+
+def woodbury_force_global(on):
+    """Testing switch: k x k systems in global scratch at any k (the path large k takes)."""
+    lib.sb200_woodbury_force_global(int(bool(on)))
 
 
 def ptlmc_step(state, mode, ll=None, dll=None):

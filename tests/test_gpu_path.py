@@ -354,6 +354,83 @@ def test_woodbury_segmented_layout_equals_dense(ops, golden, world):
     assert rel(dll2.cpu().numpy(), dll0.cpu().numpy()) < 1e-12
 
 
+def test_woodbury_global_scratch_path_equals_shared_memory_path(ops, golden):
+    """k x k systems beyond shared memory live in global scratch (include/surmise_b200.h: sb200_woodbury_loglik_ws);
+    the arithmetic is the same code, so on shapes both paths take the results agree bit for bit -- also when the
+    workspace only holds a few proposals at a time."""
+    import torch
+    from surmise_b200._lib import lib, check
+    g = golden('emu_c1')
+    phi = g['st_pcti'] * g['st_scale'][:, None]
+    yv, ev = g['yvar'], g['st_extravar']
+    sinv = np.stack([1 / yv, 1 / (yv + np.abs(ev))])
+    G = np.stack([phi.T @ (phi * s[:, None]) for s in sinv])
+    consts = {'phiT': dev(phi.T.copy()), 'resid0': dev(g['y'] - g['st_offset']), 'extravar': dev(ev),
+              'sinv': dev(sinv), 'G': dev(G)}
+    args = [dev(np.asarray(g[k])) for k in ('predvecs', 'predvars', 'predvecs_grad', 'predvars_grad')]
+    B, K = args[0].shape
+    m, d = phi.shape[0], args[2].shape[2]
+    ll0, dll0, f0 = ops.woodbury_loglik(consts, *args)
+    assert lib.sb200_woodbury_workspace(B, K, m) == 0
+    ops.woodbury_force_global(True)
+    try:
+        need = lib.sb200_woodbury_workspace(B, K, m)
+        assert need == B * 2 * K * K * 8
+        ll1, dll1, f1 = ops.woodbury_loglik(consts, *args)
+        # a workspace for three proposals: ceil(B / 3) launches
+        ws = torch.empty(3 * 2 * K * K * 8 + 8, dtype=torch.uint8, device='cuda')
+        ll2, dll2 = torch.empty_like(ll0), torch.empty_like(dll0)
+        f2 = torch.empty(1, dtype=torch.int32, device='cuda')
+        p = lambda t: t.data_ptr()
+        check(lib.sb200_woodbury_loglik_ws(B, K, m, d, p(args[0]), p(args[1]), p(args[2]), p(args[3]), p(consts['phiT']),
+                                           p(consts['resid0']), p(consts['extravar']), p(consts['sinv']), p(consts['G']),
+                                           1, -1, p(ll2), p(dll2), p(f2), None, 0, 0, None, p(ws), ws.numel(),
+                                           torch.cuda.current_stream().cuda_stream), 'sb200_woodbury_loglik_ws')
+        # without a workspace the shape is an argument error, not a silent wrong answer
+        rc = lib.sb200_woodbury_loglik(B, K, m, d, p(args[0]), p(args[1]), p(args[2]), p(args[3]), p(consts['phiT']),
+                                       p(consts['resid0']), p(consts['extravar']), p(consts['sinv']), p(consts['G']),
+                                       1, -1, p(ll2), p(dll2), p(f2), None, 0, 0, None,
+                                       torch.cuda.current_stream().cuda_stream)
+        assert rc < 0
+    finally:
+        ops.woodbury_force_global(False)
+    torch.cuda.synchronize()
+    for a, b in ((ll0, ll1), (dll0, dll1), (ll0, ll2), (dll0, dll2)):
+        assert torch.equal(a, b)
+    assert int(f0.cpu()[0]) == int(f1.cpu()[0]) == int(f2.cpu()[0])
+
+
+def test_woodbury_more_components_than_shared_memory_holds(ops):
+    """k = 150 principal components at m = 400 (2 k^2 doubles = 360 KB > 227 KB): global-scratch path against the
+    oracle's k-space restatement of directbayeswoodbury.py:261-383, and against the m-space Gaussian density."""
+    rng = np.random.default_rng(11)
+    B, K, m, d = 9, 150, 400, 3
+    phi = rng.standard_normal((m, K)) / np.sqrt(K)
+    offset, ev = rng.standard_normal(m), 1e-3 * rng.random(m)
+    yvar, y = 0.05 + 0.1 * rng.random(m), rng.standard_normal(m)
+    pv, pvar = rng.standard_normal((B, K)), 0.05 + rng.random((B, K))
+    dpv, dpvar = rng.standard_normal((B, K, d)), 0.1 * rng.standard_normal((B, K, d))
+    ll_o, dll_o, fired_o = wo.loglik_pcspace(pv, pvar, phi, offset, ev, yvar, y, dpv, dpvar)
+    cs = wo.woodbury_constants(phi, offset, ev, yvar, y)
+    consts = {'phiT': dev(phi.T.copy()), 'resid0': dev(y - offset), 'extravar': dev(ev),
+              'sinv': dev(np.stack([c['sinv'] for c in cs])), 'G': dev(np.stack([c['G'] for c in cs]))}
+    from surmise_b200._lib import lib
+    assert lib.sb200_woodbury_workspace(B, K, m) == B * 2 * K * K * 8
+    ll, dll, fired = ops.woodbury_loglik(consts, dev(pv), dev(pvar), dev(dpv), dev(dpvar))
+    ll, dll = ll.cpu().numpy(), dll.cpu().numpy()
+    assert bool(int(fired.cpu()[0])) == fired_o
+    e_l, e_d = float(np.max(np.abs(ll - ll_o[:, 0]) / np.abs(ll_o[:, 0]))), rel(dll, dll_o)
+    report('woodbury_k150', ll=e_l, dll=e_d)
+    assert e_l < 1e-11 and e_d < 1e-9
+    # the density itself: r ~ N(0, Sigma + Phi diag(v) Phi'), up to the theta-independent -1/2 log|Sigma| - m/2 log 2 pi
+    ov = yvar + (np.abs(ev) if fired_o else 0.0)
+    for b in range(B):
+        r = y - offset - phi @ pv[b]
+        S = np.diag(ov) + (phi * pvar[b]) @ phi.T
+        ref = -0.5 * (np.linalg.slogdet(S)[1] - np.sum(np.log(ov))) - 0.5 * r @ np.linalg.solve(S, r)
+        assert abs(ll[b] - ref) < 1e-9 * abs(ref)
+
+
 def test_logpost_closure_contract(ops, golden):
     """Shapes / -inf handling of the closure handed to samplers (dbw.py:100-129)."""
     from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
