@@ -7,6 +7,8 @@
 //   gp_predict    : PC-space predictive mean/variance (+ d/dtheta)          (PCGPwM.py:219-270)
 //   pc_backproject: mean/var/covxhalf (+ gradients) through Phi             (PCGPwM.py:273-327)
 #include "gp.cuh"
+#include <cstdlib>
+#include <mutex>
 #include "chol.cuh"
 #include "covmat.cuh"
 #include "dgemm.cuh"
@@ -334,6 +336,35 @@ long lda_for(int n) { return round_up(n, 8); }
 }  // namespace
 
 // testing hook: route small problems through the blocked (multi-launch) path as well
+// Per-device side stream (+ fork / join events) for work that overlaps the main stream inside one entry point; created
+// on first use, part of the one-time per-device set-up (include/surmise_b200.h, conventions (b)).
+struct SideLane {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    std::mutex mu;
+};
+static int side_lane(SideLane** out) {
+    static SideLane lanes[64];
+    static DeviceOnce once;
+    static int enabled = -1;
+    *out = nullptr;
+    if (enabled < 0) {
+        const char* env = getenv("SB200_TRMV_SIDE");
+        enabled = (env && env[0] == '0') ? 0 : 1;
+    }
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    if (!enabled || dev < 0 || dev >= 64) return 0;
+    SB_TRY(once.run([&]() -> int {
+        SB_CUDA(cudaStreamCreateWithFlags(&lanes[dev].s, cudaStreamNonBlocking));
+        SB_CUDA(cudaEventCreateWithFlags(&lanes[dev].fork, cudaEventDisableTiming));
+        SB_CUDA(cudaEventCreateWithFlags(&lanes[dev].join, cudaEventDisableTiming));
+        return 0;
+    }));
+    *out = &lanes[dev];
+    return 0;
+}
+
 static std::atomic<bool> g_force_blocked{false};      // testing switch (sb200_gp_force_blocked_path)
 void gp_force_blocked_path(int on) { g_force_blocked.store(on != 0); }
 
@@ -389,7 +420,16 @@ int gp_nll_grad(int batch, int n, int d, const double* theta, long strideTheta, 
         tmp = w.take<double>((size_t)batch * trtri_tmp_elems(n));
         alpha = w.take<double>((size_t)batch * n);
         partial = w.take<double>((size_t)batch * grad_contract_tiles(n) * MAXP);
-        SB_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * batch * strideL, stream));
+        // No clearing of Linv (640 MB per C2 step): the factorisation writes every diagonal 64 x 64 block in full (zeros
+        // above the diagonal included), the trtri levels every block below them, and the products that follow restrict
+        // their k-ranges to those tiles -- the strictly upper tiles are never read.  tests/test_gpu_blocks.py poisons
+        // the workspace with NaN to hold this; SB200_LINV_MEMSET=1 restores the memset (A/B experiments).
+        static int clear = -1;
+        if (clear < 0) {
+            const char* env = getenv("SB200_LINV_MEMSET");
+            clear = (env && env[0] == '1') ? 1 : 0;
+        }
+        if (clear) SB_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * batch * strideL, stream));
         c.Dinv = Linv; c.ldd = lda; c.strideD = strideL; c.blockD = (long)NB * lda + NB;
     } else {
         c.Dinv = w.take<double>((size_t)batch * cdiv(n, NB) * NB * NB);
@@ -400,8 +440,23 @@ int gp_nll_grad(int batch, int n, int d, const double* theta, long strideTheta, 
     SB_LAUNCH_CHECK();
     if (!want_grad) return 0;
     SB_TRY(trtri_batched(batch, n, A, lda, strideA, Linv, lda, strideL, tmp, (long)trtri_tmp_elems(n), stream));
-    SB_TRY(trmv_lower_t_batched(batch, n, Linv, lda, strideL, nullptr, A + (long)n * lda, strideA, alpha, n, stream));
-    SB_TRY(lauum_batched(batch, n, Linv, lda, strideL, A, lda, strideA, stream));     // Rinv (lower) overwrites L
+    // alpha = Linv' z streams the factor once (HBM bound) while Rinv = Linv' Linv is DMMA bound and reads the same
+    // factor: the two run side by side, the matrix-vector product on a per-device side stream forked from `stream` and
+    // joined before the contraction (SB200_TRMV_SIDE=0: one after the other on `stream`, A/B experiments)
+    SideLane* lane = nullptr;
+    SB_TRY(side_lane(&lane));
+    if (lane) {
+        std::lock_guard<std::mutex> lk(lane->mu);              // fork ... join is enqueued as one unit per device
+        SB_CUDA(cudaEventRecord(lane->fork, stream));
+        SB_CUDA(cudaStreamWaitEvent(lane->s, lane->fork, 0));
+        SB_TRY(trmv_lower_t_batched(batch, n, Linv, lda, strideL, nullptr, A + (long)n * lda, strideA, alpha, n, lane->s));
+        SB_CUDA(cudaEventRecord(lane->join, lane->s));
+        SB_TRY(lauum_batched(batch, n, Linv, lda, strideL, A, lda, strideA, stream)); // Rinv (lower) overwrites L
+        SB_CUDA(cudaStreamWaitEvent(stream, lane->join, 0));
+    } else {
+        SB_TRY(trmv_lower_t_batched(batch, n, Linv, lda, strideL, nullptr, A + (long)n * lda, strideA, alpha, n, stream));
+        SB_TRY(lauum_batched(batch, n, Linv, lda, strideL, A, lda, strideA, stream)); // Rinv (lower) overwrites L
+    }
     SB_TRY(gp_grad_contract(batch, n, d, theta, strideTheta, gvar, strideGvar, hyp, regmean, regstd, A, lda, strideA,
                             alpha, n, sig2hat, s0, partial, grad, stream));
     return 0;

@@ -95,6 +95,39 @@ def test_nll_grad_vs_oracle_batched(ops, n, d, nb):
         assert e_v < 1e-9 and e_g < 1e-9                    # the north-star bar (measured: <= 3e-12 / 4e-11)
 
 
+@pytest.mark.parametrize('n,d,nb', [(61, 3, 2), (130, 4, 3), (208, 5, 2), (700, 8, 2), (1000, 6, 3), (2000, 8, 2)])
+def test_nll_grad_does_not_read_uninitialised_workspace(ops, n, d, nb):
+    """The blocked path no longer clears its inverse-factor buffer (only the tiles the factorisation and the trtri
+    levels write are ever read): with the workspace poisoned by NaN before the call the results are finite, identical
+    to a call on a zeroed workspace, and within the bar of the oracle (PCGPwM.py:850-907)."""
+    rng = np.random.default_rng(n)
+    theta = rng.uniform(size=(n, d))
+    G = np.sin(theta @ rng.normal(size=(d, nb))).T + 0.05 * rng.normal(size=(nb, n))
+    GV = rng.uniform(size=(nb, n)) * (rng.uniform(size=(nb, n)) < 0.2) * 0.3
+    mean, LB, UB, std = po.hyper_regulariser(theta, -10, -20)
+    hyps = np.array([mean] + [LB + rng.uniform(0.3, 0.7, size=mean.shape) * (UB - LB) for _ in range(nb - 1)])
+    hyps[:, -1] = np.maximum(hyps[:, -1], -12)
+    data = ops.GPData(theta, G, GV)
+    ops.force_blocked_path(True)
+    try:
+        ops.gp_nll_grad(data, hyps, mean, std, 0.01, True)                     # sizes the workspace
+        out = []
+        for byte in (0, 255):                                                   # 0xFF.. is a NaN in every double
+            ops.workspace(1).fill_(byte)
+            out.append(ops.gp_nll_grad(data, hyps, mean, std, 0.01, True))
+    finally:
+        ops.force_blocked_path(False)
+    (v0, g0, c0), (v1, g1, c1) = out
+    assert np.all(c0 == 0) and np.all(c1 == 0)
+    assert np.all(np.isfinite(v1)) and np.all(np.isfinite(g1))
+    assert np.array_equal(v0, v1) and np.array_equal(g0, g1)
+    if n <= 1000:
+        i = nb - 1
+        info = {'theta': theta, 'g': G[i], 'gvar': GV[i], 'sig2ofconst': 0.01, 'hypregmean': mean, 'hypregstd': std}
+        v, dv = po.negloglik_eigh(hyps[i], info), po.negloglikgrad_eigh(hyps[i], info)
+        assert abs(v1[i] - v) / (abs(v) + n) < 1e-9 and rel(g1[i], dv) < 1e-9
+
+
 @pytest.mark.parametrize('n,d', [(30, 2), (63, 3), (64, 5), (160, 8), (200, 10), (207, 16)])
 def test_nll_small_fused_kernel_equals_blocked_path(ops, n, d):
     """The single-launch sweep kernel (n <= 207) and the blocked DMMA path are two routes to the same numbers."""
