@@ -4,6 +4,7 @@
 // write with the fastest thread index along the contiguous output dimension.
 // Standalone covmat is HBM-write bound: 8 n1 n2 (+ 8 D n1 n2 with gradients) bytes.
 #include "covmat.cuh"
+#include <cstdlib>
 #include "covmat_dev.cuh"
 
 namespace sb {
@@ -35,6 +36,31 @@ __device__ __forceinline__ void stage_scaled(double* dst, const double* __restri
         int gr = row0 + r;
         dst[r * XLD + k] = (gr < nrows) ? X[(long)gr * d + k] / ell[k] : 0.0;
     }
+}
+
+// rows of X divided by the length-scales, every row padded with zeros up to DT dimensions: the pair loops below then
+// run over all DT dimensions unguarded (a padded dimension multiplies the product by exactly 1 and adds exactly 0)
+template <int DT>
+__device__ __forceinline__ void stage_scaled_n(double* dst, const double* __restrict__ X, int row0, int nrows, int d,
+                                               const double* ell, int rows) {
+    for (int idx = threadIdx.x; idx < rows * DT; idx += blockDim.x) {
+        int r = idx / DT, k = idx % DT;
+        int gr = row0 + r;
+        dst[r * XLD + k] = (gr < nrows && k < d) ? X[(long)gr * d + k] / ell[k] : 0.0;
+    }
+}
+
+// rpre_pair over zero-padded coordinates, fully unrolled: same operations in the same order as the runtime-d loop
+template <int DT>
+__device__ __forceinline__ double rpre_pair_t(const double* a, const double* b, double c) {
+    double prod = c, ssum = 0.0;
+#pragma unroll
+    for (int k = 0; k < DT; k++) {
+        double S = fabs(a[k] - b[k]);
+        prod *= (1.0 + S);
+        ssum -= S;
+    }
+    return prod * exp(ssum);
 }
 
 template <int GRAD>
@@ -79,6 +105,7 @@ __global__ void __launch_bounds__(256) matern_covmat_kernel(const double* __rest
     }
 }
 
+template <int DT>
 __global__ void __launch_bounds__(256) gp_assemble_kernel(int n, int d, const double* __restrict__ thetab,
                                                           long strideTheta, const double* __restrict__ gb, long strideG,
                                                           const double* __restrict__ gvarb, long strideGvar,
@@ -94,22 +121,29 @@ __global__ void __launch_bounds__(256) gp_assemble_kernel(int n, int d, const do
     double* A = Ab + (long)z * strideA;
     load_gp_consts(&gc, hyp, d);
     __syncthreads();
-    stage_scaled(xa, theta, i0, n, d, gc.ell);
-    stage_scaled(xb, theta, j0, n, d, gc.ell);
+    stage_scaled_n<DT>(xa, theta, i0, n, d, gc.ell, TS);
+    stage_scaled_n<DT>(xb, theta, j0, n, d, gc.ell, TS);
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int j = j0 + tx;
     if (j >= n) return;
-    for (int r = ty; r < TS; r += 8) {
-        int i = i0 + r;
-        if (i > n) break;
+    double bj[DT];
+#pragma unroll
+    for (int k = 0; k < DT; k++) bj[k] = xb[tx * XLD + k];
+    // the thread's four pairs are independent straight-line code (rows past n are staged as zeros: harmless)
+    double r0[TS / 8];
+#pragma unroll
+    for (int u = 0; u < TS / 8; u++) r0[u] = rpre_pair_t<DT>(xa + (ty + 8 * u) * XLD, bj, gc.c) + gc.onemc;
+#pragma unroll
+    for (int u = 0; u < TS / 8; u++) {
+        const int i = i0 + ty + 8 * u;
+        if (i > n) continue;
         if (i == n) {                                              // augmented row: g'
             A[(long)n * lda + j] = gb[(long)z * strideG + j];
             continue;
         }
         if (j > i) continue;
-        double r0 = rpre_pair(xa + r * XLD, xb + tx * XLD, d, gc.c) + gc.onemc;
-        double v = (1.0 - gc.nu) * r0;                             // PCGPwM.py:852-857
+        double v = (1.0 - gc.nu) * r0[u];                          // PCGPwM.py:852-857
         if (i == j) {
             v += gc.nu;
             if (gvarb) v += gc.ev * gvarb[(long)z * strideGvar + i];
@@ -121,18 +155,9 @@ __global__ void __launch_bounds__(256) gp_assemble_kernel(int n, int d, const do
 // one CTA per 64x64 tile of the lower triangle (16 pairs per thread); partial[z][tile][0..p)
 constexpr int GT = 64;
 
-__device__ __forceinline__ void stage_scaled_n(double* dst, const double* __restrict__ X, int row0, int nrows, int d,
-                                               const double* ell, int rows) {
-    for (int idx = threadIdx.x; idx < rows * d; idx += blockDim.x) {
-        int r = idx / d, k = idx % d;
-        int gr = row0 + r;
-        dst[r * XLD + k] = (gr < nrows) ? X[(long)gr * d + k] / ell[k] : 0.0;
-    }
-}
-
 // DT: compile-time bound on d (the per-dimension loops are unrolled into registers up to DT, not MAXD)
-template <int DT>
-__global__ void __launch_bounds__(256, DT <= 8 ? 3 : 2) gp_grad_contract_kernel(int n, int d, const double* __restrict__ thetab,
+template <int DT, int OCC>
+__global__ void __launch_bounds__(256, OCC) gp_grad_contract_kernel(int n, int d, const double* __restrict__ thetab,
                                                                long strideTheta, const double* __restrict__ gvarb,
                                                                long strideGvar, const double* __restrict__ hypb,
                                                                const double* __restrict__ Rinvb, long ldr, long strideR,
@@ -156,8 +181,8 @@ __global__ void __launch_bounds__(256, DT <= 8 ? 3 : 2) gp_grad_contract_kernel(
     const double* alpha = alphab + (long)z * strideAlpha;
     load_gp_consts(&gc, hyp, d);
     __syncthreads();
-    stage_scaled_n(xa, theta, i0, n, d, gc.ell, GT);
-    stage_scaled_n(xb, theta, j0, n, d, gc.ell, GT);
+    stage_scaled_n<DT>(xa, theta, i0, n, d, gc.ell, GT);
+    stage_scaled_n<DT>(xb, theta, j0, n, d, gc.ell, GT);
     __syncthreads();
     const double cq = 0.5 * n / ((n + s0) * sig2hat[z]);           // PCGPwM.py:898-902
     const double omn = 1.0 - gc.nu;
@@ -188,7 +213,7 @@ __global__ void __launch_bounds__(256, DT <= 8 ? 3 : 2) gp_grad_contract_kernel(
                     if (gvarb) G.v += w * gc.ev * gvarb[(long)z * strideGvar + i];
                     continue;
                 }
-                gpdev::contract_offdiag<DT>(G, w, xa + r * XLD, b, d, gc, omn);
+                gpdev::contract_offdiag<DT>(G, w, xa + r * XLD, b, gc, omn);
             }
         }
     }
@@ -233,6 +258,7 @@ __global__ void gp_grad_finalize_kernel(int d, int ntiles, const double* __restr
     }
 }
 
+template <int DT>
 __global__ void __launch_bounds__(256) cross_cov_t_kernel(int n, int d, int B, const double* __restrict__ theta,
                                                           const double* __restrict__ thetanew,
                                                           const double* __restrict__ hypcovb, double* __restrict__ rTb,
@@ -243,19 +269,25 @@ __global__ void __launch_bounds__(256) cross_cov_t_kernel(int n, int d, int B, c
     if (threadIdx.x < d) ell[threadIdx.x] = exp(hc[threadIdx.x]);
     __syncthreads();
     const int j0 = blockIdx.y * TS, b0 = blockIdx.x * TS;
-    stage_scaled(xa, theta, j0, n, d, ell);
-    stage_scaled(xb, thetanew, b0, B, d, ell);
+    stage_scaled_n<DT>(xa, theta, j0, n, d, ell, TS);
+    stage_scaled_n<DT>(xb, thetanew, b0, B, d, ell, TS);
     __syncthreads();
     const PairConsts pc = pair_consts(hc[d]);
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int b = b0 + tx;
     if (b >= B) return;
     double* rT = rTb + (long)u * strideU;
-    for (int r = ty; r < TS; r += 8) {
-        int j = j0 + r;
-        if (j >= n) break;
-        // argument order (new, fit) as in covmat(theta_new, theta_fit): |a-b| is symmetric
-        rT[(long)j * ldb + b] = rpre_pair(xb + tx * XLD, xa + r * XLD, d, pc.c) + pc.onemc;
+    double bn[DT];
+#pragma unroll
+    for (int k = 0; k < DT; k++) bn[k] = xb[tx * XLD + k];
+    double v[TS / 8];
+    // argument order (new, fit) as in covmat(theta_new, theta_fit): |a-b| is symmetric
+#pragma unroll
+    for (int q = 0; q < TS / 8; q++) v[q] = rpre_pair_t<DT>(bn, xa + (ty + 8 * q) * XLD, pc.c) + pc.onemc;
+#pragma unroll
+    for (int q = 0; q < TS / 8; q++) {
+        const int j = j0 + ty + 8 * q;
+        if (j < n) rT[(long)j * ldb + b] = v[q];
     }
 }
 
@@ -285,8 +317,15 @@ int gp_assemble(int batch, int n, int d, const double* theta, long strideTheta, 
                 cudaStream_t stream) {
     SB_CHECK_ARG(d >= 1 && d <= MAXD, "gp_assemble: d=%d outside [1,%d]", d, MAXD);
     dim3 grid(cdiv(n, TS), cdiv(n + 1, TS), batch);
-    gp_assemble_kernel<<<grid, 256, 0, stream>>>(n, d, theta, strideTheta, g, strideG, gvar, strideGvar, hyp, A, lda,
-                                                 strideA);
+#define SB_ASSEMBLE(DT) \
+    gp_assemble_kernel<DT><<<grid, 256, 0, stream>>>(n, d, theta, strideTheta, g, strideG, gvar, strideGvar, hyp, A, lda, strideA)
+    if (d <= 4) SB_ASSEMBLE(4);
+    else if (d <= 6) SB_ASSEMBLE(6);
+    else if (d <= 8) SB_ASSEMBLE(8);
+    else if (d <= 10) SB_ASSEMBLE(10);
+    else if (d <= 12) SB_ASSEMBLE(12);
+    else SB_ASSEMBLE(16);
+#undef SB_ASSEMBLE
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -298,14 +337,22 @@ int gp_grad_contract(int batch, int n, int d, const double* theta, long strideTh
     SB_CHECK_ARG(d >= 1 && d <= MAXD, "gp_grad_contract: d=%d outside [1,%d]", d, MAXD);
     int ntiles = grad_contract_tiles(n);
     dim3 grid(ntiles, batch);
-    if (d <= 4) gp_grad_contract_kernel<4><<<grid, 256, 0, stream>>>(n, d, theta, strideTheta, gvar, strideGvar, hyp, Rinv, ldr,
-                                                      strideR, alpha, strideAlpha, sig2hat, s0, partial, ntiles);
-    else if (d <= 8) gp_grad_contract_kernel<8><<<grid, 256, 0, stream>>>(n, d, theta, strideTheta, gvar, strideGvar, hyp, Rinv, ldr,
-                                                      strideR, alpha, strideAlpha, sig2hat, s0, partial, ntiles);
-    else if (d <= 12) gp_grad_contract_kernel<12><<<grid, 256, 0, stream>>>(n, d, theta, strideTheta, gvar, strideGvar, hyp, Rinv, ldr,
-                                                      strideR, alpha, strideAlpha, sig2hat, s0, partial, ntiles);
-    else gp_grad_contract_kernel<16><<<grid, 256, 0, stream>>>(n, d, theta, strideTheta, gvar, strideGvar, hyp, Rinv, ldr,
-                                                      strideR, alpha, strideAlpha, sig2hat, s0, partial, ntiles);
+    static int occ3 = -1;                     // SB200_CONTRACT_OCC=2|3: CTAs per SM for d <= 8 (A/B experiments)
+    if (occ3 < 0) {
+        const char* env = getenv("SB200_CONTRACT_OCC");
+        occ3 = (env && env[0] == '2') ? 0 : 1;
+    }
+#define SB_CONTRACT(DT, OCC)                                                                                            \
+    gp_grad_contract_kernel<DT, OCC><<<grid, 256, 0, stream>>>(n, d, theta, strideTheta, gvar, strideGvar, hyp, Rinv, ldr, \
+                                                               strideR, alpha, strideAlpha, sig2hat, s0, partial, ntiles)
+    if (d <= 4) SB_CONTRACT(4, 3);
+    else if (d <= 6) SB_CONTRACT(6, 3);
+    else if (d <= 8 && occ3) SB_CONTRACT(8, 3);
+    else if (d <= 8) SB_CONTRACT(8, 2);
+    else if (d <= 10) SB_CONTRACT(10, 2);
+    else if (d <= 12) SB_CONTRACT(12, 2);
+    else SB_CONTRACT(16, 2);
+#undef SB_CONTRACT
     SB_LAUNCH_CHECK();
     gp_grad_finalize_kernel<<<batch, 32 * (d + 3), 0, stream>>>(d, ntiles, partial, hyp, regmean, regstd, grad);
     SB_LAUNCH_CHECK();
@@ -323,7 +370,14 @@ int cross_cov_t(int nu, int n, int d, int B, const double* theta, const double* 
                 double* rT, long ldb, long strideU, cudaStream_t stream) {
     SB_CHECK_ARG(d >= 1 && d <= MAXD, "cross_cov_t: d=%d outside [1,%d]", d, MAXD);
     dim3 grid(cdiv(B, TS), cdiv(n, TS), nu);
-    cross_cov_t_kernel<<<grid, 256, 0, stream>>>(n, d, B, theta, thetanew, hypcov, rT, ldb, strideU);
+#define SB_CROSS(DT) cross_cov_t_kernel<DT><<<grid, 256, 0, stream>>>(n, d, B, theta, thetanew, hypcov, rT, ldb, strideU)
+    if (d <= 4) SB_CROSS(4);
+    else if (d <= 6) SB_CROSS(6);
+    else if (d <= 8) SB_CROSS(8);
+    else if (d <= 10) SB_CROSS(10);
+    else if (d <= 12) SB_CROSS(12);
+    else SB_CROSS(16);
+#undef SB_CROSS
     SB_LAUNCH_CHECK();
     return 0;
 }

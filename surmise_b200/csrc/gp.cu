@@ -103,9 +103,9 @@ __global__ void __launch_bounds__(256, 2) predict_partial_factor_kernel(
     const int f = blockIdx.z, chunk = blockIdx.y, b0 = blockIdx.x * 32;
     const int u = fu[f];
     const double* hc = hypcovb + (long)u * (d + 1);
-    if (threadIdx.x < d) {
-        cc.ell[threadIdx.x] = exp(hc[threadIdx.x]);
-        cc.ginv[threadIdx.x] = exp(-hc[threadIdx.x]);
+    if (threadIdx.x < DT) {                                            // dimensions d..DT-1 are padding: ginv = 0
+        cc.ell[threadIdx.x] = threadIdx.x < d ? exp(hc[threadIdx.x]) : 1.0;
+        cc.ginv[threadIdx.x] = threadIdx.x < d ? exp(-hc[threadIdx.x]) : 0.0;
     }
     if (threadIdx.x == 32) {
         double e = exp(hc[d]);
@@ -117,13 +117,16 @@ __global__ void __launch_bounds__(256, 2) predict_partial_factor_kernel(
     __syncthreads();
     const int j0 = chunk * JC;
     if (want_grad) {                                                   // the scaled points are only needed for dr_i
-        for (int idx = threadIdx.x; idx < JC * d; idx += blockDim.x) {
-            int r = idx / d, c = idx % d;
-            xj[r * XL + c] = (j0 + r < n) ? theta[(long)(j0 + r) * d + c] / cc.ell[c] : 0.0;
+        // zero-padded up to DT dimensions: the derivative loop below then runs unguarded over all DT of them (a padded
+        // dimension has s = 0 and ginv = 0, it adds exactly zero); guarded by `i < d` every dimension became a branch
+        // region of its own and the DT reciprocal chains ran one after the other
+        for (int idx = threadIdx.x; idx < JC * DT; idx += blockDim.x) {
+            int r = idx / DT, c = idx % DT;
+            xj[r * XL + c] = (j0 + r < n && c < d) ? theta[(long)(j0 + r) * d + c] / cc.ell[c] : 0.0;
         }
-        for (int idx = threadIdx.x; idx < 32 * d; idx += blockDim.x) {
-            int r = idx / d, c = idx % d;
-            xb[r * XL + c] = (b0 + r < B) ? thetanew[(long)(b0 + r) * d + c] / cc.ell[c] : 0.0;
+        for (int idx = threadIdx.x; idx < 32 * DT; idx += blockDim.x) {
+            int r = idx / DT, c = idx % DT;
+            xb[r * XL + c] = (b0 + r < B && c < d) ? thetanew[(long)(b0 + r) * d + c] / cc.ell[c] : 0.0;
         }
     }
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -194,14 +197,13 @@ __global__ void __launch_bounds__(256, 2) predict_partial_factor_kernel(
                     if (want_grad && ok) {
                         const double rp = r - cc.onemc;                // R_pre
 #pragma unroll
-                        for (int i = 0; i < DT; i++)
-                            if (i < d) {
-                                const double s = xb[tx * XL + i] - xj[jl * XL + i];
-                                const double dr = rp * (-cc.ginv[i] * s * rcp_ge1(1.0 + fabs(s)));   // matern_covmat.pyx:13-24
-                                dv[i] += t2 * dr;
+                        for (int i = 0; i < DT; i++) {
+                            const double s = xb[tx * XL + i] - xj[jl * XL + i];
+                            const double dr = rp * (-cc.ginv[i] * s * rcp_ge1(1.0 + fabs(s)));       // matern_covmat.pyx:13-24
+                            dv[i] += t2 * dr;
 #pragma unroll
-                                for (int mm = 0; mm < MP; mm++) dp[mm][i] += dr * pwv[mm];
-                            }
+                            for (int mm = 0; mm < MP; mm++) dp[mm][i] += dr * pwv[mm];
+                        }
                     }
                 }
             }
@@ -606,6 +608,7 @@ int gp_predict(int K, int nf, int nu, int n, int d, int B, const double* theta, 
         if (want_grad) {
             if (d <= 4) SB_PREDICT_PARTIAL(true, 4, 3);
             else if (d <= 8) SB_PREDICT_PARTIAL(true, 8, 2);
+            else if (d <= 12) SB_PREDICT_PARTIAL(true, 12, 1);
             else SB_PREDICT_PARTIAL(true, 16, 1);
         } else {
             SB_PREDICT_PARTIAL(false, 1, 4);
