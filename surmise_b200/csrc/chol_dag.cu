@@ -36,6 +36,7 @@ constexpr int STAGE_ELEMS = 3 * BK * NB;                           // A (128 row
 constexpr int SM_PIPE = DSTAGES * STAGE_ELEMS;                     // doubles
 constexpr int SM_FACTOR = 3 * NB * SLD;                            // X, T (128 rows); S, W, invd alias T in diagonal tasks
 constexpr int SM_DOUBLES = SM_PIPE > SM_FACTOR ? SM_PIPE : SM_FACTOR;
+constexpr int YIELD_SLOTS = 512;                                   // per-SM yield counters (%smid < 512)
 constexpr long long SPIN_LIMIT = 4000000000LL;                     // ~2 s of clock64: a lost dependency aborts, not hangs
 
 struct DagArgs {
@@ -44,6 +45,7 @@ struct DagArgs {
     int n, mrows, batch, nt, mtp, total;        // nt column tiles (64), mtp row pairs (128 rows)
     int* info; int* prog; int* ticket;      // prog: batch * mtp counters; ticket[0] = next task, ticket[1] = abort flag
     int* xflag;                             // batch * nt: 1 once L_jj and its inverse are in global memory
+    int* smflag;                            // per SM: number of 64 x 64 factorisations running there (NULL: no yielding)
     int nowait;                             // experiments only (SB200_DAG_NOWAIT=1): ignore dependencies, results are wrong
     long long* stats;                       // instrumentation (may be NULL): per CTA [total, waiting, diagonal, solve, tasks, factor, chunk, ndiag]
 };
@@ -363,6 +365,9 @@ __global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p, const __gri
     constexpr int WM = 32, WN = 32, MI = WM / 8, NI = WN / 8, WARPS_N = NB / WN;      // 4 x 2 warps on a 128 x 64 tile
     const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
     int* abort_flag = p.ticket + 1;
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;\n" : "=r"(smid));
+    int* my_yield = (p.smflag && smid < (unsigned)YIELD_SLOTS) ? p.smflag + smid : nullptr;
     const int avail0 = p.nowait ? (1 << 30) : 0;
     if (TMA) {
         if (tid == 0) {
@@ -465,6 +470,14 @@ __global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p, const __gri
                 const unsigned it = git + (unsigned)ktl, slot = it % DSTAGES, ph = (it / DSTAGES) & 1;
                 mbar_wait(&empty_bar[slot], ph ^ 1);
                 const int slab = ktl / KT_PER_SLAB;
+                // The 64 x 64 factorisations are the serial chain of the whole factorisation, and their DFMAs share the
+                // FP64 pipe with this CTA's DMMAs (18 us alone, 36 us beside a busy neighbour): while one runs on this
+                // SM, an update task stops feeding its pipeline at the next slab boundary.
+                if (my_yield && !diag && (ktl % KT_PER_SLAB) == 0 && ld_acquire(my_yield) > 0) {
+                    const long long t0 = clock64();
+                    while (ld_acquire(my_yield) > 0 && clock64() - t0 < 200000) __nanosleep(200);
+                    c_wait += clock64() - t0;
+                }
                 if (slab >= avail) {
                     const long long t0 = clock64();
                     for (;;) {
@@ -602,7 +615,9 @@ __global__ void __launch_bounds__(DT, 2) potrf_dag_kernel(DagArgs p, const __gri
                     }
             __syncthreads();
             const long long c_f0 = clock64();
+            if (my_yield && tid == 0) atomicAdd(my_yield, 1);
             const int bad_at = factor_invert_64(S, X, W, invd, c0, tid);
+            if (my_yield && tid == 0) atomicSub(my_yield, 1);
             c_factor += clock64() - c_f0;
             c_ndiag++;
             double* D = p.Dinv + (long)z * p.strideD + (long)tj * p.blockD;
@@ -706,7 +721,7 @@ std::atomic<long long*> g_dag_stats{nullptr};
 void debug_dag_stats(long long* p) { g_dag_stats.store(p); }
 
 size_t potrf_dag_scratch_ints(int batch, int mrows) {      // row-pair counters, ticket + abort flag, diagonal flags
-    return (size_t)batch * cdiv(mrows, 2 * NB) + 2 + (size_t)batch * cdiv(mrows, NB);
+    return (size_t)batch * cdiv(mrows, 2 * NB) + 2 + (size_t)batch * cdiv(mrows, NB) + YIELD_SLOTS;
 }
 
 bool potrf_dag_usable(const CholBatch& c) {
@@ -771,6 +786,14 @@ int potrf_dag(const CholBatch& c, cudaStream_t stream) {
     a.prog = c.dag_scratch;
     a.ticket = c.dag_scratch + (size_t)c.batch * a.mtp;
     a.xflag = a.ticket + 2;
+    {
+        static int yield = -1;                     // SB200_DAG_YIELD=0: no yielding to the diagonal tasks (A/B experiments)
+        if (yield < 0) {
+            const char* env = getenv("SB200_DAG_YIELD");
+            yield = (env && env[0] == '0') ? 0 : 1;
+        }
+        a.smflag = yield ? a.xflag + (size_t)c.batch * a.nt : nullptr;
+    }
     a.stats = g_dag_stats.load();
     {
         const char* env = getenv("SB200_DAG_NOWAIT");
