@@ -9,7 +9,7 @@ python scripts/prof_paths.py nll > gpurun_out/plain_nll.log 2>&1 &&
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:'potrf_dag|dgemm_tma|dgemm_dmma|gp_grad_contract|gp_assemble|trmv_lower' -s 17 -c 17 -o gpurun_out/prof_nll_r2 -f python scripts/prof_paths.py nll > gpurun_out/ncu_nll.log 2>&1
 ncu -i gpurun_out/prof_nll_r2.ncu-rep --page raw --csv > gpurun_out/prof_nll_r2_raw.csv 2>/dev/null
 python scripts/prof_c5_chain.py 40 > gpurun_out/plain_c5.log 2>&1 &&
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:'cross_cov|predict_partial_kernel<1|predict_reduce|woodbury_loglik|ptlmc_step' -s 200 -c 10 -o gpurun_out/prof_c5_r2 -f python scripts/prof_c5_chain.py 40 > gpurun_out/ncu_c5.log 2>&1
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:'cross_cov|predict_partial|predict_reduce|woodbury_loglik|ptlmc_step' -s 200 -c 10 -o gpurun_out/prof_c5_r2 -f python scripts/prof_c5_chain.py 40 > gpurun_out/ncu_c5.log 2>&1
 ncu -i gpurun_out/prof_c5_r2.ncu-rep --page raw --csv > gpurun_out/prof_c5_r2_raw.csv 2>/dev/null
 python scripts/pca_profile.py C4 > gpurun_out/plain_pca.log 2>&1 &&
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'syevj|col_partial|standardize_kernel' -c 6 -o gpurun_out/prof_pca_r2 -f python scripts/pca_profile.py C4 > gpurun_out/ncu_pca.log 2>&1
