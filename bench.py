@@ -436,16 +436,19 @@ def main():
 
     # roofline leg: per-launch CUDA-event timing of the dominant kernel (the DMMA GEMM) over K more steps
     import ctypes
-    _lib.lib.sb200_gemm_profile_enable(1)
-    barrier()
-    for _ in range(K):
-        step_device()
-    barrier()
-    _lib.lib.sb200_gemm_profile_enable(0)
-    g_ms, g_fl = ctypes.c_double(0), ctypes.c_double(0)
-    g_n = _lib.lib.sb200_gemm_profile_collect(ctypes.byref(g_ms), ctypes.byref(g_fl))
-    c_ms, c_fl = ctypes.c_double(0), ctypes.c_double(0)
-    c_n = _lib.lib.sb200_kernel_profile_collect(1, ctypes.byref(c_ms), ctypes.byref(c_fl))   # task-graph Cholesky launches
+    # two passes: the first fills the library's pool of timing events (creating two events per launch keeps the host
+    # behind the device on the small launches, and the gaps land inside the brackets); the second is the measurement
+    for _pass in range(2):
+        _lib.lib.sb200_gemm_profile_enable(1)
+        barrier()
+        for _ in range(K):
+            step_device()
+        barrier()
+        _lib.lib.sb200_gemm_profile_enable(0)
+        g_ms, g_fl = ctypes.c_double(0), ctypes.c_double(0)
+        g_n = _lib.lib.sb200_gemm_profile_collect(ctypes.byref(g_ms), ctypes.byref(g_fl))
+        c_ms, c_fl = ctypes.c_double(0), ctypes.c_double(0)
+        c_n = _lib.lib.sb200_kernel_profile_collect(1, ctypes.byref(c_ms), ctypes.byref(c_fl))   # task-graph Cholesky launches
     clk.__exit__(None, None, None)
 
     # strong scaling reference point: the SAME k-component step on one GPU (rank 0 alone, the others wait)

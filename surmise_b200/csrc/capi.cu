@@ -26,7 +26,24 @@ struct GemmSample { cudaEvent_t a, b; double flops; int kind; };
 static std::mutex g_prof_mu;
 static std::vector<GemmSample> g_prof;
 static std::atomic<bool> g_prof_on{false};
+static std::vector<cudaEvent_t> g_event_pool;      // guarded by g_prof_mu
 bool gemm_profile_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+// The events of a collected sample go back to a pool: creating two events per launch kept the host behind the device
+// on the small launches of the roofline leg, and the gaps ended up inside the event brackets (GEMM time 4.06 -> 4.25 ms
+// on a slow host).
+int profile_event_pair(cudaEvent_t* a, cudaEvent_t* b) {
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        if (g_event_pool.size() >= 2) {
+            *a = g_event_pool.back(); g_event_pool.pop_back();
+            *b = g_event_pool.back(); g_event_pool.pop_back();
+            return 0;
+        }
+    }
+    SB_CUDA(cudaEventCreate(a));
+    SB_CUDA(cudaEventCreate(b));
+    return 0;
+}
 void gemm_profile_add(cudaEvent_t a, cudaEvent_t b, double flops) { kernel_profile_add(0, a, b, flops); }
 void kernel_profile_add(int kind, cudaEvent_t a, cudaEvent_t b, double flops) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -81,8 +98,8 @@ int sb200_gemm_profile_dump(double* ms, double* flops, int cap) {
             flops[n] = smp.flops;
             n++;
         }
-        cudaEventDestroy(smp.a);
-        cudaEventDestroy(smp.b);
+        sb::g_event_pool.push_back(smp.a);
+        sb::g_event_pool.push_back(smp.b);
     }
     sb::g_prof.clear();
     return n;
@@ -106,8 +123,8 @@ int sb200_kernel_profile_collect(int kind, double* total_ms, double* total_flops
             fl += smp.flops;
             n++;
         }
-        cudaEventDestroy(smp.a);
-        cudaEventDestroy(smp.b);
+        sb::g_event_pool.push_back(smp.a);
+        sb::g_event_pool.push_back(smp.b);
     }
     sb::g_prof.swap(keep);
     if (total_ms) *total_ms = ms;

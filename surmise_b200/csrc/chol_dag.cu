@@ -822,8 +822,7 @@ int potrf_dag(const CholBatch& c, cudaStream_t stream) {
     };
     if (gemm_profile_enabled()) {                  // bench.py's roofline leg: CUDA events around this launch
         cudaEvent_t e0, e1;
-        SB_CUDA(cudaEventCreate(&e0));
-        SB_CUDA(cudaEventCreate(&e1));
+        SB_TRY(profile_event_pair(&e0, &e1));
         SB_CUDA(cudaEventRecord(e0, stream));
         launch();
         SB_CUDA(cudaEventRecord(e1, stream));

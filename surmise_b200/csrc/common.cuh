@@ -20,6 +20,7 @@ void count_launch();
 // optional per-launch timing of the DMMA GEMM (bench.py's roofline leg): when enabled, launch_dgemm brackets
 // each launch with CUDA events on its stream and books the launch's algorithmic flop count
 bool gemm_profile_enabled();
+int profile_event_pair(cudaEvent_t* a, cudaEvent_t* b);      // timing events from a pool (no creation cost once warm)
 void gemm_profile_add(cudaEvent_t start, cudaEvent_t stop, double flops);
 void kernel_profile_add(int kind, cudaEvent_t start, cudaEvent_t stop, double flops);   // 0 = DMMA GEMM, 1 = task-graph Cholesky
 

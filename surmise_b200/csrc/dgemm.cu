@@ -230,8 +230,7 @@ int launch_one(const GemmArgs& g, int batch, cudaStream_t stream) {
     dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), batch);
     if (gemm_profile_enabled()) {
         cudaEvent_t e0, e1;
-        SB_CUDA(cudaEventCreate(&e0));
-        SB_CUDA(cudaEventCreate(&e1));
+        SB_TRY(profile_event_pair(&e0, &e1));
         SB_CUDA(cudaEventRecord(e0, stream));
         kern<<<grid, NTHREADS, smem, stream>>>(g);
         SB_CUDA(cudaEventRecord(e1, stream));

@@ -346,8 +346,7 @@ int launch_tma(const GemmArgs& g, int batch, const CUtensorMap& mapA, const CUte
     dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), batch);
     if (gemm_profile_enabled()) {
         cudaEvent_t e0, e1;
-        SB_CUDA(cudaEventCreate(&e0));
-        SB_CUDA(cudaEventCreate(&e1));
+        SB_TRY(profile_event_pair(&e0, &e1));
         SB_CUDA(cudaEventRecord(e0, stream));
         kern<<<grid, BM * 2, smem, stream>>>(g, mapA, mapA_last, mapB);
         SB_CUDA(cudaEventRecord(e1, stream));
