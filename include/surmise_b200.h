@@ -8,8 +8,10 @@
  *   - every array pointer is a DEVICE pointer to fp64 (or int32 where typed so), row-major;
  *   - the caller owns all memory, including workspaces (size them with the *_workspace queries);
  *     the library never allocates or frees device memory.  The compute entry points keep no mutable state of their
- *     own: what exists process-wide is (a) a thread-local last-error string, (b) the one-time per-device kernel
- *     attribute set-up (mutex-guarded, safe for concurrent first calls from several host threads), and (c) the
+ *     own: what exists process-wide is (a) a thread-local last-error string, (b) the one-time per-device set-up
+ *     (kernel attributes and, for sb200_gp_nll_grad, one non-blocking side stream with two events per device on which a
+ *     bandwidth-bound product runs beside a tensor-bound one; forked from and joined to the caller's stream inside the
+ *     call, capturable; mutex-guarded, safe for concurrent first calls from several host threads), and (c) the
  *     instrumentation / testing switches declared below -- an atomic launch counter, the optional GEMM timing record
  *     (mutex-guarded), sb200_gp_force_blocked_path, sb200_woodbury_force_global and sb200_debug_panel_stamps (atomics; set them only while no
  *     call is in flight).  None of (c) changes a numerical result;
