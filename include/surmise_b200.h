@@ -161,6 +161,18 @@ int sb200_woodbury_loglik_ws(int B, int k, int m, int d, const double* predvecs,
                              void* stream);
 void sb200_woodbury_force_global(int on);
 
+/* directbayeswoodbury.loglik (calibrationmethods/directbayeswoodbury.py:261-306) as written, for an emulator OUTSIDE the
+ * PCGPwM family (no principal-component factors on the device): the caller evaluates that emulator's own predict and
+ * passes its outputs at the B proposals, proposal-major: mean (B,m), var (B,m), covxhalf (B,m,k).
+ *   want_trigger = 1: only the batch-wide unmodelled-variance test (dbw.py:277-279) -> *fired (device int); ll unused.
+ *   want_trigger = 0: ll (B) for observation precision sinv (m) = 1 / obsvar (the caller adds the unmodelled variance
+ *   to obsvar when the test fired, dbw.py:280-284); one CTA per proposal, I + J'J (k x k) factored in shared memory
+ *   ((k^2 + m + k + 32) doubles <= 227 KB).  No gradient in this form (the samplers that need one take a PCGPwM
+ *   emulator). */
+int sb200_woodbury_loglik_mspace(int B, int k, int m, const double* mean, const double* var, const double* covxhalf,
+                                 const double* y, const double* sinv, int want_trigger, double* ll, int* fired,
+                                 void* stream);
+
 /* One step of the device-resident PT-LMC sampler: what surmise's PTLMC (utilitiesmethods/PTLMC.py:203-273) does between
  * two evaluations of the log-posterior, for a population of B = numtemps + numchain chains kept on the device.
  *   mode bit 0: accept / reject the pending proposal thetap given its log-likelihood ll (B) and gradient dll (B,d)

@@ -111,3 +111,26 @@ def loglik_pcspace(pv, pvar, phi, offset, extravar, yvar, y, dpv=None, dpvar=Non
                 dterm3 = 2 * np.sum(dD * Nvec)
                 dll[b, i] = -0.5 * dterm3 - 0.5 * (dterm1 - dterm2)
     return ll, dll, fired
+
+
+def loglik_from_prediction(mean, var, covxhalf, yvar, y, old_var=None, old_covxhalf=None):
+    """directbayeswoodbury.loglik for ANY emulator, given that emulator's outputs     (directbayeswoodbury.py:271-306).
+
+    mean, var (m, B), covxhalf (m, B, k) at the proposals; old_var (m, n), old_covxhalf (m, n, k) at the emulator's own
+    training thetas, needed only when the batch-wide test fires.  Returns (ll (B, 1), fired)."""
+    m, B = mean.shape
+    obsvar = 1 * np.squeeze(yvar) * np.ones(m)
+    fired = extravar_trigger(var, covxhalf)
+    if fired:
+        obsvar = obsvar + np.mean(np.abs(old_var - np.sum(np.square(old_covxhalf), 2)), 1)
+    ll = np.zeros((B, 1))
+    root = np.sqrt(obsvar)
+    for b in range(B):
+        z = (np.squeeze(y) - mean[:, b]) / root                 # standardised residual
+        J = covxhalf[:, b, :] / root[:, None]
+        W, V = np.linalg.eigh(np.eye(J.shape[1]) + J.T @ J)
+        J2 = J.T @ z
+        proj = V.T @ J2
+        ll[b, 0] = -0.5 * (z @ z - np.sum(proj ** 2 / W)) - 0.5 * np.sum(np.log(W))
+    return ll, fired
+

@@ -50,6 +50,7 @@ SIGNATURES = {
     'sb200_woodbury_loglik_ws': (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _l, _p,
                                       _p, _z, _p]),
     'sb200_woodbury_force_global': (None, [_i]),
+    'sb200_woodbury_loglik_mspace': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p]),
     'sb200_woodbury_trigger': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _i, _l, _p, _p]),
     'sb200_ptlmc_step': (_i, [_i, _i, _i, _i, _i, _i, C.c_ulonglong, _d] + [_p] * 17 + [_p]),
     'sb200_host_tempexchange': (None, [_p, _p, _i, _p, _p, _i, _p]),

@@ -11,7 +11,9 @@ with the whole population as one (B, d) array; each such call is ONE fused devic
 Nothing of size m x B x k x d is ever formed (the reference builds covxhalf_gradtheta of that size,
 directbayeswoodbury.py:319-324).
 
-Requires an emulator fitted with method='PCGPwM_B200' (its device state is read from emu._info).
+The fused path needs an emulator fitted with method='PCGPwM_B200' (its device state is read from emu._info) or the
+reference's 'PCGPwM' (adopted onto the device).  Any other emulator (PCGP, indGP, ...) is evaluated through its own
+predict and the likelihood as the reference writes it (dbw.py:261-306) on the device, without gradients.
 """
 import copy
 
@@ -35,6 +37,41 @@ def _device_state(emu):
         raise ValueError("directbayeswoodbury_B200 needs an emulator fitted with method='PCGPwM_B200' "
                          "(or the reference's 'PCGPwM').")
     return info
+
+
+def _pc_family(emu):
+    """True for an emulator that carries (or can be given, PCGPwM_B200.adopt) PC-space factors on the device."""
+    info = getattr(emu, '_info', None)
+    if not isinstance(info, dict):
+        return False
+    if 'phi' in info.get('_b200', {}):
+        return True
+    return '_b200' not in info and 'emulist' in info and 'unscaled_pcstdvar' in info
+
+
+def _loglik_any_emulator(fitinfo, emu, theta, y, x):
+    """directbayeswoodbury.loglik as written (dbw.py:261-306) for an emulator OUTSIDE the PCGPwM family (PCGP, indGP,
+    ...): that emulator's own predict supplies mean / var / covxhalf at the proposals, the batch-wide variance test and
+    the Woodbury-form Gaussian density run on the device (sb200_woodbury_loglik_mspace).  No gradient in this form."""
+    if 'yvar' not in fitinfo:
+        raise ValueError('Must provide yvar in this software.')            # dbw.py:266-269
+    ops = _ops()
+    torch = ops._torch()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    pred = emu.predict(x, theta)
+    mean, var, cxh = (np.asarray(a, dtype=np.float64) for a in (pred.mean(), pred.var(), pred.covxhalf()))
+    m, B = mean.shape
+    if cxh.ndim == 2:
+        cxh = cxh[:, :, None]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    meanT, varT, cxhT = t(mean.T), t(var.T), t(np.transpose(cxh, (1, 0, 2)))
+    obsvar = 1 * np.squeeze(np.asarray(fitinfo['yvar'], dtype=np.float64)) * np.ones(m)
+    if int(ops.woodbury_loglik_mspace(meanT, varT, cxhT, None).item()):       # dbw.py:277-284
+        old = emu.predict(x)
+        obsvar = obsvar + np.mean(np.abs(old.var() - np.sum(np.square(old.covxhalf()), 2)), 1)
+    ll = ops.woodbury_loglik_mspace(meanT, varT, cxhT, t(np.squeeze(np.asarray(y, dtype=np.float64)) * np.ones(m)),
+                                    t(obsvar))
+    return ll.cpu().numpy().reshape(B, 1)
 
 
 def woodbury_constants(fitinfo, emu, x, y):
@@ -160,6 +197,11 @@ def _evaluate(fitinfo, emu, theta, y, x, return_grad):
     evaluates its slice, the batch-wide unmodelled-variance flag (dbw.py:277-284) is OR-reduced so that it is
     still decided over the whole population, and the (B, 1+d) table is all-gathered (NCCL).
     """
+    if not _pc_family(emu):
+        if return_grad:
+            raise ValueError("directbayeswoodbury_B200: the log-likelihood gradient needs an emulator fitted with "
+                             "method='PCGPwM_B200' (or the reference's 'PCGPwM'); other emulators are evaluated without.")
+        return _loglik_any_emulator(fitinfo, emu, np.atleast_2d(theta), y, x)
     if fitinfo.get('shard_theta') and _device_state(emu)['_b200'].get('shard') is None:
         from .. import _dist
         comm = _dist.Comm()
@@ -431,7 +473,8 @@ def make_logpost(fitinfo, emu, x, y, fd_step=10 ** (-6), extra_logp=None, with_g
         return theta0
 
     # lets a device-resident sampler plugin (PTLMC_B200) keep the whole chain on the GPU when the prior allows it
-    logpostfull_wgrad.b200 = DeviceLogpost(fitinfo, emu, x, y, thetaprior, extra_logp) if with_grad else None
+    logpostfull_wgrad.b200 = (DeviceLogpost(fitinfo, emu, x, y, thetaprior, extra_logp)
+                              if with_grad and _pc_family(emu) else None)
     return logpostfull_wgrad, draw_func
 
 
@@ -452,7 +495,8 @@ def fit(fitinfo, emu, x, y, **bayeswoodbury_args):
         # every rank holds the same emulator: keep only this rank's block of the full-data factors and evaluate
         # PC-sharded from here on (collective; all ranks run the same sampler with the same seed)
         _emu_method.shard_state(_device_state(emu))
-    woodbury_constants(fitinfo, emu, x, y)
+    if _pc_family(emu):
+        woodbury_constants(fitinfo, emu, x, y)
     logpost, draw_func = make_logpost(fitinfo, emu, x, y)
     sampler_obj = sampler(logpost_func=logpost, draw_func=draw_func, **bayeswoodbury_args)
     theta = sampler_obj.sampler_info['theta']

@@ -240,6 +240,12 @@ int sb200_woodbury_loglik_ws(int B, int k, int m, int d, const double* predvecs,
 
 void sb200_woodbury_force_global(int on) { woodbury_force_global(on); }
 
+int sb200_woodbury_loglik_mspace(int B, int k, int m, const double* mean, const double* var, const double* covxhalf,
+                                 const double* y, const double* sinv, int want_trigger, double* ll, int* fired,
+                                 void* stream) {
+    return woodbury_loglik_mspace(B, k, m, mean, var, covxhalf, y, sinv, want_trigger, ll, fired, ST(stream));
+}
+
 int sb200_woodbury_trigger(int B, int k, int m, const double* predvars, const double* phiT, const double* extravar,
                            int* fired, const int* row_valid, int seg_k, long seg_stride, const int* seg_pos, void* stream) {
     SB_CHECK_ARG(predvars && phiT && extravar && fired, "woodbury_trigger: NULL pointer");

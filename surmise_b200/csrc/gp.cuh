@@ -52,7 +52,12 @@ int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const do
 size_t woodbury_workspace(int B, int K, int m);      // 0 while the k x k systems fit shared memory (k <= 112 at m <= 3000)
 int woodbury_trigger(int B, int K, int m, const double* predvars, const double* phiT, const double* extravar,
                      int* fired, const int* row_valid, int segk, long segstride, const int* seg_pos, cudaStream_t stream);
-void woodbury_force_global(int on);      // tests: k x k matrices in global scratch at any k (the k > 112 path)
+void woodbury_force_global(int on);
+// generic form for an emulator outside the PCGPwM family: mean (B,m), var (B,m), covxhalf (B,m,K) supplied by the caller;
+// want_trigger = 1: only the batch-wide variance test into *fired;  0: ll (B) with Sigma^-1 = sinv (m)
+int woodbury_loglik_mspace(int B, int K, int m, const double* meanT, const double* varT, const double* cxhT,
+                           const double* y, const double* sinv, int want_trigger, double* ll, int* fired,
+                           cudaStream_t stream);      // tests: k x k matrices in global scratch at any k (the k > 112 path)
 
 
 // sampler.cu: one step of the device-resident PT-LMC sampler (surmise utilitiesmethods/PTLMC.py:203-273)

@@ -193,6 +193,87 @@ __global__ void __launch_bounds__(WT) woodbury_loglik_kernel(int B, int K, int m
     }
 }
 
+
+// ---- generic form: any emulator's predictive mean / covxhalf (directbayeswoodbury.py:261-306 as written) -------------
+// For an emulator outside the PCGPwM family there is no PC-space structure to exploit: the caller evaluates the
+// emulator (its own predict) and hands over mean (B, m), var (B, m) and covxhalf (B, m, K) at the proposals.
+//   r = y - mean_b,  J = Sigma^-1/2 C_b,  l = -1/2 (r' Sigma^-1 r - J2' (I + J'J)^-1 J2) - 1/2 log|I + J'J|,  J2 = J' Sigma^-1/2 r
+// One CTA per proposal; I + J'J (K x K) and its Cholesky factor in shared memory.
+__global__ void __launch_bounds__(WT) mspace_trigger_kernel(int B, int K, int m, const double* __restrict__ varT,
+                                                            const double* __restrict__ cxhT, int* fired) {
+    const int b = blockIdx.x;
+    bool hit = false;
+    for (int x = threadIdx.x; x < m; x += WT) {
+        const double* c = cxhT + ((long)b * m + x) * K;
+        double s = 0.0;
+        for (int a = 0; a < K; a++) s += c[a] * c[a];
+        if (fabs(varT[(long)b * m + x] / (1e-4 + (1.0 + 1e-4) * s)) > 1.0) hit = true;      // dbw.py:277-279
+    }
+    if (__syncthreads_or(hit) && threadIdx.x == 0) atomicOr(fired, 1);
+}
+
+__global__ void __launch_bounds__(WT) mspace_loglik_kernel(int B, int K, int m, const double* __restrict__ meanT,
+                                                           const double* __restrict__ cxhT, const double* __restrict__ y,
+                                                           const double* __restrict__ sinv, double* __restrict__ ll) {
+    extern __shared__ double sh[];
+    double* Am = sh;                    // K*K : I + J'J, then its Cholesky factor (lower)
+    double* w = Am + K * K;             // m   : Sigma^-1 r
+    double* J2 = w + m;                 // K   : C' Sigma^-1 r, then L^-1 of it
+    double* red = J2 + K;               // 32
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* mu = meanT + (long)b * m;
+    const double* C = cxhT + (long)b * m * K;
+    double t1 = 0.0;
+    for (int x = tid; x < m; x += WT) {
+        const double r = y[x] - mu[x];
+        const double wx = sinv[x] * r;
+        w[x] = wx;
+        t1 += r * wx;
+    }
+    const double term1 = block_sum(t1, red);                       // r' Sigma^-1 r   (also publishes w)
+    for (int a = warp; a < K; a += WT / 32) {
+        double s = 0.0;
+        for (int x = lane; x < m; x += 32) s += C[(long)x * K + a] * w[x];
+        s = warp_sum(s);
+        if (lane == 0) J2[a] = s;
+    }
+    for (int idx = tid; idx < K * K; idx += WT) {
+        const int i = idx / K, j = idx % K;
+        double s = 0.0;
+        if (j <= i)
+            for (int x = 0; x < m; x++) s += C[(long)x * K + i] * sinv[x] * C[(long)x * K + j];
+        Am[idx] = (j <= i) ? s + (i == j ? 1.0 : 0.0) : 0.0;
+    }
+    for (int j = 0; j < K; j++) {                                  // Cholesky, lower, in shared memory
+        __syncthreads();
+        const double ljj = sqrt(Am[j * K + j]);
+        __syncthreads();
+        for (int i = j + tid; i < K; i += WT) Am[i * K + j] = (i == j) ? ljj : Am[i * K + j] / ljj;
+        __syncthreads();
+        const int rem = K - j - 1;
+        for (int idx = tid; idx < rem * rem; idx += WT) {
+            const int i = j + 1 + idx / rem, c = j + 1 + idx % rem;
+            if (c <= i) Am[i * K + c] -= Am[i * K + j] * Am[c * K + j];
+        }
+    }
+    __syncthreads();
+    double ldh = 0.0;
+    for (int a = tid; a < K; a += WT) ldh += log(Am[a * K + a]);
+    const double logdet_half = block_sum(ldh, red);                // 1/2 log|I + J'J|
+    for (int j = 0; j < K; j++) {                                  // z = L^-1 J2 by forward substitution, in place
+        __syncthreads();
+        const double zj = J2[j] / Am[j * K + j];
+        __syncthreads();
+        if (tid == 0) J2[j] = zj;
+        for (int i = j + 1 + tid; i < K; i += WT) J2[i] -= Am[i * K + j] * zj;
+    }
+    __syncthreads();
+    double q = 0.0;
+    for (int a = tid; a < K; a += WT) q += J2[a] * J2[a];
+    const double term2 = block_sum(q, red);                        // J2' (I + J'J)^-1 J2
+    if (tid == 0) ll[b] = -0.5 * (term1 - term2) - logdet_half;    // dbw.py:303-304
+}
+
 }  // namespace
 
 // k x k matrices in shared memory?  (m-vector + 7 k-vectors + the two matrices within 227 KB: k <= 112 at m <= 3000)
@@ -246,6 +327,31 @@ int woodbury_loglik(int B, int K, int m, int d, const double* predvecs, const do
             segk, segstride, seg_pos, ll, dll, in_smem ? nullptr : static_cast<double*>(ws), b0);
         SB_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+int woodbury_loglik_mspace(int B, int K, int m, const double* meanT, const double* varT, const double* cxhT,
+                           const double* y, const double* sinv, int want_trigger, double* ll, int* fired,
+                           cudaStream_t stream) {
+    SB_CHECK_ARG(B > 0 && m > 0 && K >= 1, "woodbury_mspace: B=%d m=%d k=%d", B, m, K);
+    SB_CHECK_ARG(B <= 65535 * 1024, "woodbury_mspace: batch too large");
+    if (want_trigger) {                       // only the batch-wide unmodelled-variance test (dbw.py:277-279)
+        SB_CHECK_ARG(varT && cxhT && fired, "woodbury_mspace: NULL pointer");
+        SB_CUDA(cudaMemsetAsync(fired, 0, sizeof(int), stream));
+        mspace_trigger_kernel<<<B, WT, 0, stream>>>(B, K, m, varT, cxhT, fired);
+        SB_LAUNCH_CHECK();
+        return 0;
+    }
+    SB_CHECK_ARG(meanT && cxhT && y && sinv && ll, "woodbury_mspace: NULL pointer");
+    const size_t smem = ((size_t)K * K + m + K + 32) * sizeof(double);
+    SB_CHECK_ARG(smem <= 227 * 1024, "woodbury_mspace: k=%d, m=%d need %zu B of shared memory", K, m, smem);
+    static DeviceOnce once;
+    SB_TRY(once.run([&]() -> int {
+        SB_CUDA(cudaFuncSetAttribute(mspace_loglik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        return 0;
+    }));
+    mspace_loglik_kernel<<<B, WT, smem, stream>>>(B, K, m, meanT, cxhT, y, sinv, ll);
+    SB_LAUNCH_CHECK();
     return 0;
 }
 

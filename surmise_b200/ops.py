@@ -388,6 +388,28 @@ def woodbury_loglik(consts, pv, pvar, dpv=None, dpvar=None, variant=-1, out=None
     return ll, dll, fired
 
 
+def woodbury_loglik_mspace(meanT, varT, cxhT, y, obsvar=None):
+    """directbayeswoodbury.loglik as written (dbw.py:261-306) for an emulator outside the PCGPwM family.
+
+    meanT (B,m), varT (B,m), cxhT (B,m,k): that emulator's predictive mean / variance / covxhalf at the proposals, on the
+    device, proposal-major.  obsvar None: returns the device int32 flag of the batch-wide unmodelled-variance test
+    (dbw.py:277-279); obsvar (m,) device tensor: returns ll (B,) for that observation variance."""
+    torch = _torch()
+    _need_cuda(meanT, varT, cxhT)
+    B, m, K = cxhT.shape
+    dev = cxhT.device
+    if obsvar is None:
+        fired = torch.empty(1, dtype=torch.int32, device=dev)
+        check(lib.sb200_woodbury_loglik_mspace(B, K, m, _ptr(meanT), _ptr(varT), _ptr(cxhT), None, None, 1, None,
+                                               _ptr(fired), _stream(torch)), 'sb200_woodbury_loglik_mspace')
+        return fired
+    sinv = (1.0 / obsvar).contiguous()
+    ll = torch.empty(B, dtype=torch.float64, device=dev)
+    check(lib.sb200_woodbury_loglik_mspace(B, K, m, _ptr(meanT), _ptr(varT), _ptr(cxhT), _ptr(y), _ptr(sinv), 0, _ptr(ll),
+                                           None, _stream(torch)), 'sb200_woodbury_loglik_mspace')
+    return ll
+
+
 _wb_scratch = {}
 
 

@@ -464,6 +464,72 @@ def test_woodbury_more_components_than_shared_memory_holds(ops):
         assert abs(ll[b] - ref) < 1e-9 * abs(ref)
 
 
+class _AnyPrediction:
+    def __init__(self, mean, var, cxh):
+        self._m, self._v, self._c = mean, var, cxh
+
+    def mean(self):
+        return self._m
+
+    def var(self):
+        return self._v
+
+    def covxhalf(self):
+        return self._c
+
+
+class _AnyEmulator:
+    """An emulator outside the PCGPwM family, as the calibrator sees it: predict(x, theta) with the accessor API of
+    surmise.emulation.prediction; predict(x) alone = at its own training thetas (emulation.py)."""
+
+    def __init__(self, m, K, d, seed, var_scale):
+        rng = np.random.default_rng(seed)
+        self.Wm, self.Wc = rng.standard_normal((m, d)), 0.3 * rng.standard_normal((m, K, d))
+        self.theta0 = rng.uniform(size=(11, d))
+        self.var_scale = var_scale
+        self._info = {'method': 'some_other_method'}
+
+    def predict(self, x=None, theta=None):
+        th = self.theta0 if theta is None else np.atleast_2d(theta)
+        mean = self.Wm @ th.T                                                     # (m, B)
+        cxh = np.einsum('mkd,bd->mbk', self.Wc, np.cos(th)) + 0.1                 # (m, B, K)
+        var = self.var_scale * np.sum(cxh ** 2, 2) + 0.01 * (self.var_scale > 1)
+        return _AnyPrediction(mean, var, cxh)
+
+
+@pytest.mark.parametrize('m,K,B,var_scale', [(29, 7, 33, 1.0), (29, 7, 33, 3.0), (5, 1, 1, 1.0), (200, 40, 9, 1.0)])
+def test_loglik_for_an_emulator_outside_the_pcgpwm_family(ops, m, K, B, var_scale):
+    """directbayeswoodbury.loglik as written (dbw.py:261-306) on the device for any emulator's mean / var / covxhalf:
+    against the oracle's restatement (with and without the batch-wide variance test firing) and against the Gaussian
+    density itself; the gradient form is refused, not approximated."""
+    from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
+    d = 3
+    emu = _AnyEmulator(m, K, d, seed=m + K, var_scale=var_scale)
+    rng = np.random.default_rng(B)
+    theta = rng.uniform(size=(B, d))
+    y = rng.standard_normal(m)
+    yvar = 0.05 + 0.1 * rng.random(m)
+    p, old = emu.predict(None, theta), emu.predict(None)
+    ll_o, fired_o = wo.loglik_from_prediction(p.mean(), p.var(), p.covxhalf(), yvar, y, old.var(), old.covxhalf())
+    assert fired_o == (var_scale > 1)
+    ll = C.loglik({'yvar': yvar}, emu, theta, y, None)
+    assert ll.shape == (B, 1)
+    e_l = float(np.max(np.abs(ll - ll_o) / np.abs(ll_o)))
+    report('loglik_any_emulator', m=m, K=K, B=B, fired=float(fired_o), ll=e_l)
+    assert e_l < 1e-10
+    obsvar = yvar + (np.mean(np.abs(old.var() - np.sum(old.covxhalf() ** 2, 2)), 1) if fired_o else 0.0)
+    for b in range(min(B, 4)):
+        r = y - p.mean()[:, b]
+        Cb = p.covxhalf()[:, b, :]
+        S = np.diag(obsvar) + Cb @ Cb.T
+        ref = -0.5 * (np.linalg.slogdet(S)[1] - np.sum(np.log(obsvar))) - 0.5 * r @ np.linalg.solve(S, r)
+        assert abs(ll[b, 0] - ref) < 1e-9 * abs(ref)
+    with pytest.raises(ValueError):
+        C.loglik_grad({'yvar': yvar}, emu, theta, y, None)
+    with pytest.raises(ValueError):
+        C.loglik({}, emu, theta, y, None)
+
+
 def test_logpost_closure_contract(ops, golden):
     """Shapes / -inf handling of the closure handed to samplers (dbw.py:100-129)."""
     from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
