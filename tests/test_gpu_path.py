@@ -530,6 +530,33 @@ def test_loglik_for_an_emulator_outside_the_pcgpwm_family(ops, m, K, B, var_scal
         C.loglik({}, emu, theta, y, None)
 
 
+class _ReplayEmulator:
+    """Hands the calibrator the emulator outputs stored in a golden fixture (at the proposals; at the training thetas
+    when predict is called without theta, as surmise.emulation.emulator.predict does)."""
+    _info = {'method': 'replayed outputs of another method'}
+
+    def __init__(self, g, tag):
+        self.g, self.tag = g, tag
+
+    def predict(self, x=None, theta=None):
+        k = self.tag + ('_old_' if theta is None else '_')
+        return _AnyPrediction(None if theta is None else self.g[self.tag + '_mean'], self.g[k + 'var'], self.g[k + 'covxhalf'])
+
+
+@pytest.mark.parametrize('tag', ['pcgp', 'fired'])
+def test_loglik_for_another_emulator_against_the_reference(ops, golden, tag):
+    """The generic path against the reference's own directbayeswoodbury.loglik outputs (dbw.py:261-306) for a
+    reference-fitted PCGP emulator and for outputs that make the variance test fire: 1e-9 per theta."""
+    from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
+    g = golden('any_emulator')
+    ll = C.loglik({'yvar': g[tag + '_yvar']}, _ReplayEmulator(g, tag), g[tag + '_theta'], g[tag + '_y'], None)
+    ref = g[tag + '_loglik']
+    assert ll.shape == ref.shape
+    e_l = float(np.max(np.abs(ll - ref) / np.abs(ref)))
+    report('loglik_any_emulator_golden_' + tag, ll=e_l)
+    assert e_l < 1e-9
+
+
 def test_logpost_closure_contract(ops, golden):
     """Shapes / -inf handling of the closure handed to samplers (dbw.py:100-129)."""
     from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C

@@ -129,3 +129,17 @@ def test_arbiter_fixture_is_consistent_with_the_goldens(golden, tag):
     pv, pvar = po.predict_pcspace_chol(g['st_theta'], states, g['st_hypind'], g['thetanew'])[:2]
     assert np.max(np.abs(pv - a[tag + '_predvecs'])) / np.max(np.abs(a[tag + '_predvecs'])) < 20 * 2.2e-16 * cond
     assert np.max(np.abs(pvar - a[tag + '_predvars']) / a[tag + '_predvars']) < 50 * 2.2e-16 * cond
+
+
+@pytest.mark.parametrize('tag', ['pcgp', 'fired'])
+def test_loglik_from_any_emulators_prediction(golden, tag):
+    """The oracle's restatement of directbayeswoodbury.loglik for an arbitrary emulator (dbw.py:261-306) against the
+    reference's own outputs: a reference-fitted PCGP emulator, and synthetic outputs for which the variance test fires
+    (tests/golden/make_golden_any_emulator.py)."""
+    g = golden('any_emulator')
+    f = lambda k: g[tag + '_' + k]
+    ll, fired = wo.loglik_from_prediction(f('mean'), f('var'), f('covxhalf'), f('yvar'), f('y'), f('old_var'), f('old_covxhalf'))
+    assert fired == bool(f('fired')) == (tag == 'fired')
+    assert ll.shape == f('loglik').shape
+    assert np.max(np.abs(ll - f('loglik')) / np.abs(f('loglik'))) < 1e-13
+
