@@ -288,3 +288,23 @@ def test_lazy_standardpcinfo_dict(monkeypatch):
     d = fresh()
     d['fs'] = 3
     assert d['fs'] == 3 and d.device('fs') is None
+
+
+def test_calibrator_chooses_its_path_by_the_emulators_state():
+    """directbayeswoodbury_B200: the fused PC-space path for an emulator with device factors or one that can be adopted
+    (a reference PCGPwM fitinfo), the generic path (that emulator's own predict, likelihood of dbw.py:261-306 on the
+    device, no gradient) for anything else -- decided from emu._info alone, no CUDA needed."""
+    from surmise_b200.calibrationmethods import directbayeswoodbury_B200 as C
+
+    class Emu:
+        def __init__(self, info):
+            self._info = info
+    assert C._pc_family(Emu({'_b200': {'phi': object()}}))
+    assert C._pc_family(Emu({'emulist': [], 'unscaled_pcstdvar': np.zeros((2, 1))}))          # reference PCGPwM: adopt()
+    assert not C._pc_family(Emu({'_b200': {'theta': object()}}))                               # e.g. indGP_B200
+    assert not C._pc_family(Emu({'method': 'PCGP', 'emulist': []}))
+    assert not C._pc_family(Emu(None)) and not C._pc_family(object())
+    # the gradient form is refused for the generic path before anything touches the device
+    with pytest.raises(ValueError, match='gradient'):
+        C.loglik_grad({'yvar': np.ones(3)}, Emu({'method': 'PCGP'}), np.zeros((2, 2)), np.zeros(3), None)
+
