@@ -1,6 +1,7 @@
 """profiles/ncu_kernels_r2.json (the FP64-ALU / HBM / latency-bound kernels bench.py lists in `roofline_kernels`) and
 profiles/dram_traffic_r2.json from the raw exports of scripts/gpu_r2_ncu.sh:
-    python scripts/make_ncu_kernels.py gpurun_out/prof_nll_r2_raw.csv gpurun_out/prof_c5_r2_raw.csv gpurun_out/prof_pca_r2_raw.csv
+    python scripts/make_ncu_kernels.py gpurun_out/prof_nll_r2_raw.csv gpurun_out/prof_c5_r2_raw.csv gpurun_out/prof_pca_r2_raw.csv \
+        gpurun_out/prof_covmat_raw.csv
 One representative launch per kernel (the last captured); the tensor kernels are timed live by bench.py and only feed
 the DRAM-traffic file here."""
 import json, os, re, sys
@@ -17,6 +18,8 @@ TABLE = [
     ('trmv_lower_t_kernel', 'alpha = Linv^T y: streams the lower triangle of Linv once (side stream, beside the lauum product)', 'hbm'),
     ('gp_grad_contract_kernel', 'sum_ab W_ab dR_j(a,b) for the d+3 hyper-parameters, dR recomputed per pair', 'fp64'),
     ('gp_assemble_kernel', 'lower triangle of R = (1-nu) R0 + nu I + e^hv diag(gvar), g row', 'fp64'),
+    ('matern_covmat_kernel<0>', 'standalone covariance, 8000 x 8000, d = 10, R only (0.51 GB written): one exp + 5d operations per pair', 'fp64'),
+    ('matern_covmat_kernel<1>', 'standalone covariance with the 11 hyper-parameter gradient planes (6.1 GB written)', 'hbm'),
     ('cross_cov_t_kernel', 'cross-covariance of the proposals with the design, theta-batch contiguous', 'fp64'),
     ('predict_partial_factor_kernel', 'predict epilogue per factor: T1^2, r pw, T2 dr_i, dr_i pw partial sums', 'fp64'),
     ('woodbury_loglik_kernel', 'one CTA per theta: m-space residual, k x k Cholesky / inverse in shared memory, gradient', 'latency'),
